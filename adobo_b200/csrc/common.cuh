@@ -1,0 +1,242 @@
+// adobo_b200 -- shared declarations of the sm_100a CUDA library (see include/adobo_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/adobo_b200.h"
+
+typedef long long i64;
+
+namespace adobo {
+
+// ---- errors -------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+struct Fail {
+  int code;
+};
+
+#define CUDA_CHECK(expr)                                                                      \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      adobo::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      throw adobo::Fail{ADOBO_ERR_CUDA};                                                      \
+    }                                                                                         \
+  } while (0)
+
+#define REQUIRE(cond, code, ...)    \
+  do {                              \
+    if (!(cond)) {                  \
+      adobo::set_error(__VA_ARGS__); \
+      throw adobo::Fail{code};      \
+    }                               \
+  } while (0)
+
+// ---- device buffer ------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  void ensure(size_t n) {
+    if (n <= cap && p) return;
+    release();
+    size_t want = n ? n : 1;
+    CUDA_CHECK(cudaMalloc((void**)&p, want * sizeof(T)));
+    cap = want;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  ~DevBuf() { release(); }
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+struct ProfItem {
+  double ms = 0;
+  i64 launches = 0;
+  double work = 0;  // algorithmic bytes (or flops for the distance kernel) of the launches
+};
+
+struct PendingEvent {
+  const char* name;
+  cudaEvent_t a, b;
+  double work;
+};
+
+// Matrix (sparse, cells x columns) in the two layouts the Lanczos mat-vecs read.
+template <typename VT>
+struct SparsePair {
+  i64 rows = 0;
+  int cols = 0;
+  i64 nnz = 0;
+  DevBuf<i64> rptr;   // CSR row pointers (rows+1)
+  DevBuf<int> cidx;   // CSR column ids
+  DevBuf<VT> rval;    // CSR values
+  DevBuf<i64> cptr;   // CSC column pointers (cols+1)
+  DevBuf<int> ridx;   // CSC row ids (ascending inside a column)
+  DevBuf<VT> cval;    // CSC values
+};
+
+struct Comm;  // NCCL wrapper, api.cu
+
+}  // namespace adobo
+
+struct adobo_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  // ---- count matrix shard (CSR cells x genes) ----
+  i64 n = 0;        // local cells
+  i64 n_total = 0;  // cells over all ranks
+  i64 row_offset = 0;
+  int g = 0;
+  i64 nnz = 0;
+  adobo::DevBuf<i64> indptr;
+  adobo::DevBuf<int> indices;
+  adobo::DevBuf<int> counts;
+  adobo::DevBuf<float> vals;  // normalized values, fp32, same pattern
+  bool have_counts = false, have_norm = false;
+  // ---- HVG ----
+  adobo::DevBuf<double> gsum, gsq;  // per gene sum x, sum x^2 (all ranks after all-reduce)
+  bool have_moments = false;
+  std::vector<double> h_mean, h_var;
+  std::vector<int> hvg_order;  // reference output order
+  // ---- PCA ----
+  adobo::SparsePair<float> sub;  // HVG column subset
+  adobo::DevBuf<int> sub_genes;  // ascending gene ids (h)
+  std::vector<int> h_sub_genes;
+  adobo::DevBuf<double> mu, rs;  // per-column mean and 1/sigma
+  int p = 0;                     // components of the last PCA
+  adobo::DevBuf<double> comp;    // n x p row-major
+  adobo::DevBuf<double> contr;   // h x p row-major
+  adobo::DevBuf<double> sv;      // p
+  bool have_pca = false;
+  // ---- kNN / SNN ----
+  int k = 0;
+  i64 knn_n = 0;
+  adobo::DevBuf<int> nn;  // knn_n x k, 0-based global ids
+  bool have_knn = false;
+  adobo::DevBuf<int> e_src, e_dst;
+  i64 n_edges = 0;
+  // ---- plumbing ----
+  adobo::Comm* comm = nullptr;
+  int world = 1, rank = 0;
+  cudaEvent_t events[64] = {};
+  bool profiling = false;
+  std::map<std::string, adobo::ProfItem> prof;
+  std::vector<adobo::PendingEvent> pending;
+  std::vector<cudaEvent_t> event_pool;
+  i64 launches = 0;
+  double next_work = 0;  // algorithmic bytes/flops of the next LAUNCH (profiling only)
+  adobo::DevBuf<char> flush_buf;
+  adobo::DevBuf<char> scratch;  // general scratch (cub temp storage etc.)
+  void* pinned = nullptr;       // 4 KB pinned host mailbox
+};
+
+namespace adobo {
+
+// ---- launch bookkeeping ---------------------------------------------------------------------
+void prof_begin(adobo_ctx* c, const char* name);
+void prof_end(adobo_ctx* c);
+
+// WORK(ctx, x): algorithmic bytes (flops for knn_shortlist) of the next launch, for the roofline
+#define WORK(ctx, x) ((ctx)->next_work = (double)(x))
+#define LAUNCH(ctx, name, ...)                                                              \
+  do {                                                                                      \
+    if ((ctx)->profiling) adobo::prof_begin((ctx), name);                                   \
+    __VA_ARGS__;                                                                            \
+    (ctx)->launches++;                                                                      \
+    if ((ctx)->profiling) adobo::prof_end((ctx));                                           \
+    cudaError_t _le = cudaGetLastError();                                                   \
+    if (_le != cudaSuccess) {                                                               \
+      adobo::set_error("%s:%d: launch %s -> %s", __FILE__, __LINE__, name,                  \
+                       cudaGetErrorString(_le));                                            \
+      throw adobo::Fail{ADOBO_ERR_CUDA};                                                    \
+    }                                                                                       \
+  } while (0)
+
+// ---- collectives (no-ops when world == 1) ---------------------------------------------------
+void allreduce_sum_f64(adobo_ctx* c, double* dev, size_t count);
+void allreduce_sum_i64(adobo_ctx* c, i64* dev, size_t count);
+// gathers `count_local` elements of every rank into out (rank order); counts[] per rank in elements
+void allgatherv_bytes(adobo_ctx* c, const void* src, void* dst, const std::vector<size_t>& bytes_per_rank);
+void allgather_i64_host(adobo_ctx* c, i64 mine, std::vector<i64>& all);
+
+// ---- stage entry points (one per .cu file) ---------------------------------------------------
+void run_normalize(adobo_ctx* c, double scaling, int log_mode, double small_const, i64* out_lib,
+                   double* out_vals);
+void run_moments(adobo_ctx* c);
+void run_seurat_host(adobo_ctx* c, int ngenes, int num_bins, std::vector<int>& order, std::vector<double>& z);
+void run_gather_subset(adobo_ctx* c, const std::vector<int>& genes_sorted, bool scale);
+
+struct IrlbResult {
+  int steps = 0, nmult = 0;
+};
+// generic driver on a SparsePair; mu/rs may be null (no centring / scaling)
+template <typename VT>
+IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu_dev, const double* rs_dev, int nval,
+                    double tol, int maxit, const double* v0_host, bool var_weigh, DevBuf<double>& outU,
+                    DevBuf<double>& outS, DevBuf<double>& outV);
+template <typename VT>
+void build_csc(adobo_ctx* c, SparsePair<VT>& A);
+
+void run_knn(adobo_ctx* c, const double* comp_dev_local, i64 n_local, int p, int k);
+void run_snn(adobo_ctx* c, const int* nn_dev_all, i64 n_all, i64 row_begin, i64 row_end, int k, double prune,
+             i64* n_edges, i64* pruned, i64* total);
+
+// exclusive scan of int64 counts (n elements) into out[n+1] (out[n] = total); in-place allowed
+void exclusive_scan_i64(adobo_ctx* c, const i64* in, i64* out, i64 n);
+
+// ---- device helpers -------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ i64 warp_sum(i64 v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// streaming 128-bit loads/stores that do not pollute L1
+__device__ __forceinline__ int4 ld_stream(const int4* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(float4* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w));
+}
+#endif
+
+}  // namespace adobo

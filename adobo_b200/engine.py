@@ -1,0 +1,266 @@
+"""Engine: one GPU context of the C-ABI library, holding the device-resident matrix shard.
+
+This is the host-side plumbing the API modules (normalize, hvg, dr, clustering) share.  All
+numerics run in libadobo_b200.so; nothing here computes on the CPU.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+from ._lib import check
+
+LOG_NONE, LOG_2, LOG_E, LOG_10 = 0, 1, 2, 3
+
+
+def as_csr(m):
+    """scipy CSR with int64 indptr / int32 indices, sorted column ids (layout of the C-ABI)."""
+    m = sp.csr_matrix(m)
+    if not m.has_sorted_indices:
+        m = m.sorted_indices()
+    return m
+
+
+class LanczosResult:
+    """Same attributes as adobo.irlbpy.irlb.LanczosResult (irlb.py:261-265)."""
+
+    def __init__(self, **kw):
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+class Engine:
+    def __init__(self, device=None):
+        self.lib = _lib.load()
+        if device is None:
+            device = int(os.environ.get('ADOBO_B200_DEVICE', os.environ.get('LOCAL_RANK', '0')))
+        self.device = device
+        h = C.c_void_p()
+        check(self.lib.adobo_ctx_create(int(device), C.byref(h)))
+        self.h = h
+        self.world, self.rank = 1, 0
+        self.n = self.g = self.nnz = 0
+        self.resident_key = None
+        self._pattern = None
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.adobo_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- multi-GPU ----
+    def init_comm_from_torch(self):
+        """Joins the contexts of a torchrun job: rank 0 makes the NCCL id, torch.distributed
+        (any backend) broadcasts it."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        ident = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            check(self.lib.adobo_comm_unique_id(ident))
+        obj = [ident.tobytes()]
+        dist.broadcast_object_list(obj, src=0)
+        ident = np.frombuffer(obj[0], dtype=np.uint8).copy()
+        check(self.lib.adobo_comm_init(self.h, world, rank, ident))
+        self.world, self.rank = world, rank
+
+    # ---- stopwatch ----
+    def record(self, slot):
+        check(self.lib.adobo_event_record(self.h, slot))
+
+    def elapsed_ms(self, a, b):
+        ms = C.c_float()
+        check(self.lib.adobo_event_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return ms.value
+
+    def sync(self):
+        check(self.lib.adobo_sync(self.h))
+
+    def l2_flush(self):
+        check(self.lib.adobo_l2_flush(self.h))
+
+    def launch_count(self):
+        return int(self.lib.adobo_launch_count(self.h))
+
+    def profile(self, on):
+        check(self.lib.adobo_profile(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        n = 64
+        names = C.create_string_buffer(32 * n)
+        ms = np.zeros(n, dtype=np.float32)
+        cnt = np.zeros(n, dtype=np.int64)
+        work = np.zeros(n, dtype=np.float64)
+        k = C.c_int()
+        check(self.lib.adobo_profile_read(self.h, n, names, ms, cnt, work, C.byref(k)))
+        out = {}
+        for i in range(k.value):
+            nm = names.raw[32 * i:32 * i + 32].split(b'\0')[0].decode()
+            out[nm] = dict(ms=float(ms[i]), launches=int(cnt[i]), work=float(work[i]))
+        return out
+
+    def pin(self, arr):
+        """Page-locks a numpy array in place (cudaHostRegister)."""
+        check(self.lib.adobo_host_register(arr.ctypes.data, arr.nbytes))
+
+    def unpin(self, arr):
+        check(self.lib.adobo_host_unregister(arr.ctypes.data))
+
+    # ---- data in ----
+    def upload_counts(self, counts):
+        m = as_csr(counts)
+        indptr = np.ascontiguousarray(m.indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(m.indices, dtype=np.int32)
+        data = np.ascontiguousarray(m.data)
+        if data.size and (data.min() < -2 ** 31 or data.max() >= 2 ** 31):
+            raise Exception('counts do not fit int32')
+        data = data.astype(np.int32, copy=False)
+        check(self.lib.adobo_upload_counts(self.h, m.shape[0], m.shape[1], indptr, indices, np.ascontiguousarray(data)))
+        self.n, self.g, self.nnz = m.shape[0], m.shape[1], int(indptr[-1])
+        self._pattern = (indptr, indices)
+        self.resident_key = None
+
+    def upload_normalized(self, norm, key=None):
+        m = as_csr(norm)
+        indptr = np.ascontiguousarray(m.indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(m.indices, dtype=np.int32)
+        data = np.ascontiguousarray(m.data, dtype=np.float64)
+        check(self.lib.adobo_upload_normalized(self.h, m.shape[0], m.shape[1], indptr, indices, data))
+        self.n, self.g, self.nnz = m.shape[0], m.shape[1], int(indptr[-1])
+        self._pattern = (indptr, indices)
+        self.resident_key = key
+
+    # ---- stages ----
+    def normalize(self, scaling_factor=10000, log_mode=LOG_2, small_const=1.0, want_values=True):
+        lib = np.empty(self.n, dtype=np.int64)
+        vals = np.empty(self.nnz, dtype=np.float64) if want_values else None
+        check(self.lib.adobo_normalize(self.h, float(scaling_factor), int(log_mode), float(small_const), lib, vals))
+        if not want_values:
+            return None, lib
+        indptr, indices = self._pattern
+        return sp.csr_matrix((vals, indices, indptr), shape=(self.n, self.g)), lib
+
+    def gene_moments(self):
+        mean = np.empty(self.g)
+        var = np.empty(self.g)
+        check(self.lib.adobo_gene_moments(self.h, mean, var))
+        return mean, var
+
+    def hvg_seurat(self, ngenes=1000, num_bins=20):
+        idx = np.empty(max(int(ngenes), 1), dtype=np.int32)
+        z = np.empty(self.g)
+        m = C.c_int32()
+        check(self.lib.adobo_hvg_seurat(self.h, int(ngenes), int(num_bins), idx, C.byref(m), z))
+        return idx[:m.value].astype(np.int64), z
+
+    def irlb(self, genes, ncomp=75, tol=0.0001, maxit=1000, v0=None, seed=None, scale=True, var_weigh=True):
+        genes = np.ascontiguousarray(genes, dtype=np.int32)
+        h = genes.shape[0]
+        if v0 is None:
+            np.random.seed(seed)                 # irlb.py:151-152 (legacy MT19937 stream)
+            v0 = np.random.randn(h)
+        v0 = np.ascontiguousarray(v0, dtype=np.float64)
+        comp = np.empty((self.n, ncomp))
+        contr = np.empty((h, ncomp))
+        s = np.empty(ncomp)
+        steps, nmult = C.c_int32(), C.c_int32()
+        check(self.lib.adobo_irlb(self.h, genes, h, int(ncomp), float(tol), int(maxit), v0, 1 if scale else 0,
+                                  1 if var_weigh else 0, comp, s, contr, C.byref(steps), C.byref(nmult)))
+        return dict(comp=comp, contr=contr, s=s, steps=steps.value, nmult=nmult.value, genes=np.sort(genes))
+
+    def lanczos_csr(self, A, nval, tol=0.0001, maxit=50, seed=None, v0=None):
+        m = as_csr(A)
+        indptr = np.ascontiguousarray(m.indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(m.indices, dtype=np.int32)
+        data = np.ascontiguousarray(m.data, dtype=np.float64)
+        rows, cols = m.shape
+        if v0 is None:
+            np.random.seed(seed)
+            v0 = np.random.randn(cols)
+        v0 = np.ascontiguousarray(v0, dtype=np.float64)
+        U = np.empty((rows, nval))
+        V = np.empty((cols, nval))
+        s = np.empty(nval)
+        steps, nmult = C.c_int32(), C.c_int32()
+        check(self.lib.adobo_lanczos_csr(self.h, rows, cols, indptr, indices, data, int(nval), float(tol), int(maxit),
+                                         v0, U, s, V, C.byref(steps), C.byref(nmult)))
+        return LanczosResult(U=U, s=s, V=V, steps=steps.value, nmult=nmult.value)
+
+    def knn(self, comp=None, k=10, n_local=None, fetch=True):
+        if comp is not None:
+            comp = np.ascontiguousarray(comp, dtype=np.float64)
+            n, p = comp.shape
+        else:
+            n, p = (self.n if n_local is None else n_local), 0
+        out = np.empty((n, k), dtype=np.int64) if fetch else None
+        check(self.lib.adobo_knn(self.h, comp, n, p, int(k), out))
+        return out
+
+    def snn(self, nn_idx=None, k=10, prune_snn=0.067, fetch=True):
+        ne, pr, tot = C.c_int64(), C.c_int64(), C.c_int64()
+        if nn_idx is not None:
+            nn_idx = np.ascontiguousarray(nn_idx, dtype=np.int64)
+            n = nn_idx.shape[0]
+            if nn_idx.shape[1] != k:
+                raise Exception('snn: nn_idx has %d columns but k=%d (run knn with the same k)' % (nn_idx.shape[1], k))
+            check(self.lib.adobo_snn(self.h, nn_idx, n, int(k), float(prune_snn), C.byref(ne), C.byref(pr),
+                                     C.byref(tot)))
+        else:
+            check(self.lib.adobo_snn(self.h, None, 0, int(k), float(prune_snn), C.byref(ne), C.byref(pr), C.byref(tot)))
+        if not fetch:
+            return None, pr.value, tot.value, ne.value
+        src = np.empty(max(ne.value, 1), dtype=np.int32)
+        dst = np.empty(max(ne.value, 1), dtype=np.int32)
+        check(self.lib.adobo_snn_fetch(self.h, src, dst))
+        edges = np.stack([src[:ne.value], dst[:ne.value]], axis=1)
+        return edges, pr.value, tot.value, ne.value
+
+    def embed_path(self, v0, scaling_factor=10000, ngenes=1000, ncomp=75, k=10, prune_snn=0.067):
+        """normalize -> seurat -> irlb pca -> knn -> snn, device resident (no host copies)."""
+        steps, nmult, ne = C.c_int32(), C.c_int32(), C.c_int64()
+        v0 = np.ascontiguousarray(v0, dtype=np.float64)
+        check(self.lib.adobo_embed_path(self.h, float(scaling_factor), int(ngenes), int(ncomp), v0, int(k),
+                                        float(prune_snn), C.byref(steps), C.byref(nmult), C.byref(ne)))
+        return dict(steps=steps.value, nmult=nmult.value, n_edges=ne.value)
+
+    def fetch_pca(self, h, ncomp):
+        comp = np.empty((self.n, ncomp))
+        contr = np.empty((h, ncomp))
+        s = np.empty(ncomp)
+        genes = np.empty(h, dtype=np.int32)
+        check(self.lib.adobo_fetch_pca(self.h, comp, s, contr, genes))
+        return dict(comp=comp, contr=contr, s=s, genes=genes.astype(np.int64))
+
+    def fetch_knn(self, k):
+        out = np.empty((self.n, k), dtype=np.int64)
+        check(self.lib.adobo_fetch_knn(self.h, out))
+        return out
+
+    def fetch_edges(self, ne):
+        src = np.empty(max(ne, 1), dtype=np.int32)
+        dst = np.empty(max(ne, 1), dtype=np.int32)
+        check(self.lib.adobo_snn_fetch(self.h, src, dst))
+        return np.stack([src[:ne], dst[:ne]], axis=1)
+
+
+_default = None
+
+
+def default_engine():
+    """Process-wide engine on ADOBO_B200_DEVICE / LOCAL_RANK / device 0."""
+    global _default
+    if _default is None:
+        _default = Engine()
+    return _default
+
+
+def set_default_engine(e):
+    global _default
+    _default = e

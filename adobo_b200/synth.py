@@ -1,7 +1,7 @@
 """Seeded synthetic count matrices and embeddings of the benchmark shapes.
 
 The generator is the single source of inputs for the parity tests, the golden vectors and
-bench.py: the same arrays feed the CUDA path, the oracle and the reference.  Cells are drawn
+bench.py: the same arrays feed the CUDA path and its CPU checkers.  Cells are drawn
 in blocks of 1,024 with a per-block stream so that any contiguous cell shard of a matrix can
 be regenerated on its own rank without generating the rest.
 
@@ -55,7 +55,7 @@ class CountModel:
 def synth_counts(n_cells, n_genes, density=0.064, seed=43, row_start=0, row_stop=None):
     """CSR (cells x genes) int32 count matrix; rows [row_start, row_stop) of the full matrix.
 
-    indptr is int64, indices int32, data int32 -- the layout the C-ABI takes.
+    indices int32, data int32 (scipy picks the indptr width; Engine widens it to int64 for the C-ABI).
     """
     if row_stop is None:
         row_stop = n_cells

