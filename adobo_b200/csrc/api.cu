@@ -286,6 +286,7 @@ void adobo_ctx_destroy(adobo_ctx* c) {
     cudaEventDestroy(pe.b);
   }
   for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
+  if (c->irlb_ws && c->irlb_ws_free) c->irlb_ws_free(c->irlb_ws);
   if (c->pinned) cudaFreeHost(c->pinned);
   cudaStream_t st = c->stream;
   delete c;

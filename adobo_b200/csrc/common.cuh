@@ -140,6 +140,8 @@ struct adobo_ctx {
   adobo::DevBuf<char> flush_buf;
   adobo::DevBuf<char> scratch;  // general scratch (cub temp storage etc.)
   void* pinned = nullptr;       // 4 KB pinned host mailbox
+  void* irlb_ws = nullptr;      // persistent Lanczos workspace + CUDA graphs (irlb.cu)
+  void (*irlb_ws_free)(void*) = nullptr;
 };
 
 namespace adobo {

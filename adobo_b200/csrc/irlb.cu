@@ -13,6 +13,8 @@
 //
 // Reductions are two-stage and ordered (per-CTA partials, summed by the last CTA to finish), so
 // a given shard layout gives bit-identical results run to run.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace adobo {
@@ -23,11 +25,14 @@ constexpr double EPS2 = 2.0 * 2.220446049250313e-16;
 
 __device__ __forceinline__ double inv_or_zero(double x) { return x > EPS2 ? 1.0 / x : 0.0; }  // irlb.py:84-92
 
-// ---- ordered cross-CTA reductions ------------------------------------------------------------
+// ---- ordered cross-CTA reductions (row kernels run 1024-thread CTAs, at most one per SM) --------
+constexpr int RT_THREADS = 1024;
+constexpr int RT_WARPS = RT_THREADS / 32;
+
 // vector of nd (<= 128) sums; acc[t] is this lane's partial for column lane + 32 t
 __device__ __forceinline__ void reduce_vec_blocks(double (&acc)[4], int nd, double* __restrict__ partials,
                                                   double* __restrict__ out, unsigned* __restrict__ counter) {
-  __shared__ double sh[8][MAXB];
+  __shared__ double sh[RT_WARPS][MAXB];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -35,8 +40,8 @@ __device__ __forceinline__ void reduce_vec_blocks(double (&acc)[4], int nd, doub
   __syncthreads();
   if (threadIdx.x < nd) {
     double s = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) s += sh[w][threadIdx.x];
+#pragma unroll 8
+    for (int w = 0; w < RT_WARPS; ++w) s += sh[w][threadIdx.x];
     partials[(size_t)blockIdx.x * MAXB + threadIdx.x] = s;
   }
   __threadfence();
@@ -44,10 +49,12 @@ __device__ __forceinline__ void reduce_vec_blocks(double (&acc)[4], int nd, doub
   if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
   __syncthreads();
   if (is_last) {
-    if (threadIdx.x < nd) {
+    // warp w sums columns w, w+32, ...: lanes stride the CTA partials (fixed order -> deterministic)
+    for (int col = warp; col < nd; col += RT_WARPS) {
       double s = 0;
-      for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(partials + (size_t)b * MAXB + threadIdx.x);
-      out[threadIdx.x] = s;
+      for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + (size_t)b * MAXB + col);
+      s = warp_sum(s);
+      if (lane == 0) out[col] = s;
     }
     if (threadIdx.x == 0) *counter = 0;
   }
@@ -56,7 +63,7 @@ __device__ __forceinline__ void reduce_vec_blocks(double (&acc)[4], int nd, doub
 // two scalars
 __device__ __forceinline__ void reduce_two_blocks(double a, double b, double* __restrict__ partials,
                                                   double* __restrict__ out, unsigned* __restrict__ counter) {
-  __shared__ double sh2[8][2];
+  __shared__ double sh2[RT_WARPS][2];
   __shared__ bool is_last2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) {
@@ -66,8 +73,8 @@ __device__ __forceinline__ void reduce_two_blocks(double a, double b, double* __
   __syncthreads();
   if (threadIdx.x < 2) {
     double s = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) s += sh2[w][threadIdx.x];
+#pragma unroll 8
+    for (int w = 0; w < RT_WARPS; ++w) s += sh2[w][threadIdx.x];
     partials[(size_t)blockIdx.x * 2 + threadIdx.x] = s;
   }
   __threadfence();
@@ -113,7 +120,7 @@ __global__ void __launch_bounds__(256) spmvT_csc(const i64* __restrict__ cptr, c
 }
 
 // ---- F = A_s^T w - s V[:,j]  and  c = V[:, :nd]^T F  (irlb.py:182-190, first half of orthog) ----
-__global__ void __launch_bounds__(256) v_prep_dots(const double* __restrict__ t, const double* __restrict__ mu,
+__global__ void __launch_bounds__(RT_THREADS, 1) v_prep_dots(const double* __restrict__ t, const double* __restrict__ mu,
                                                    const double* __restrict__ rs, const double* __restrict__ sc,
                                                    const double* __restrict__ V, int ldv, int j, int nd, int h,
                                                    double* __restrict__ ybuf, double* __restrict__ partials,
@@ -139,7 +146,7 @@ __global__ void __launch_bounds__(256) v_prep_dots(const double* __restrict__ t,
 
 // ---- K4  w = A_s x - fn W[:,jprev]  and  c = W[:, :nd]^T w  (irlb.py:165 / 204-216) -------------
 template <typename VT>
-__global__ void __launch_bounds__(256) spmv_dots(const i64* __restrict__ rptr, const int* __restrict__ cidx,
+__global__ void __launch_bounds__(RT_THREADS, 1) spmv_dots(const i64* __restrict__ rptr, const int* __restrict__ cidx,
                                                  const VT* __restrict__ rval, const double* __restrict__ xs,
                                                  const double* __restrict__ sc, const double* __restrict__ W,
                                                  int ldw, int jprev, int nd, i64 n, double* __restrict__ ybuf,
@@ -169,7 +176,7 @@ __global__ void __launch_bounds__(256) spmv_dots(const i64* __restrict__ rptr, c
 }
 
 // ---- y -= Q[:, :nd] c ;  nrm2 = y.y ;  aux = coef.y  (second half of orthog + the norm) ---------
-__global__ void __launch_bounds__(256) update_norm(const double* __restrict__ Q, int ld, int nd,
+__global__ void __launch_bounds__(RT_THREADS, 1) update_norm(const double* __restrict__ Q, int ld, int nd,
                                                    const double* __restrict__ cvec, double* __restrict__ ybuf,
                                                    const double* __restrict__ coef, i64 rows,
                                                    double* __restrict__ partials, double* __restrict__ out2,
@@ -241,117 +248,187 @@ __global__ void w_finish(const double* __restrict__ ybuf, double* __restrict__ s
   }
 }
 
-// ---- one-sided Jacobi SVD of B (m x m, row-major) in one CTA -----------------------------------
-// G = B (column-major in shared memory), columns rotated pairwise (round-robin ordering, one pair
-// per half-warp) until mutually orthogonal: B Vr = U diag(sv).  Outputs column-major, singular
-// values descending.  vglobal != null keeps the accumulated Vr in global memory (large m).
-__global__ void __launch_bounds__(1024, 1) jacobi_svd(const double* __restrict__ B, int m, double* __restrict__ Su,
-                                                      double* __restrict__ svout, double* __restrict__ Sv,
-                                                      double* vglobal, int* __restrict__ info) {
+// ---- one-sided Jacobi SVD of B (m x m, row-major, m <= 128) in one CTA ---------------------------
+// G = B (column-major in shared memory).  Columns are rotated pairwise -- round-robin ordering, all
+// m/2 disjoint pairs of a round at once, LANES lanes per pair with the two columns in registers
+// (R = ceil(m / LANES) rows per lane) -- until mutually orthogonal: B Vr = U diag(sv).  The kernel
+// is bound by the fp64 rate of ONE SM, so the arithmetic is trimmed: column norms are cached
+// (refreshed exactly every sweep), the rotation comes from two rsqrt, and the right vectors are
+// not accumulated but recovered at the end as Vr = B^T U diag(1/sv) (one small GEMM; accurate for
+// the leading columns, which are the only ones the restart uses: k <= m - 3).
+// Outputs column-major, singular values descending.
+template <int LANES, int R>
+__global__ void __launch_bounds__(64 * LANES, 1) jacobi_svd(const double* __restrict__ B, int m, double* __restrict__ Su,
+                                                            double* __restrict__ svout, double* __restrict__ Sv,
+                                                            int* __restrict__ info) {
   extern __shared__ double smem[];
-  double* G = smem;
-  volatile double* Vr = vglobal ? vglobal : (smem + (size_t)m * m);
+  double* G = smem;                       // [m][m] column-major
+  double* nrm = smem + (size_t)m * m;     // [m] squared column norms
+  double* inv = nrm + 128;                // [m] 1 / sv
   __shared__ int rotated;
-  __shared__ double svs[256];
+  __shared__ int rankof[128];
   const int tid = threadIdx.x;
-  const int hw = tid >> 4, sl = tid & 15;
-  const int nhw = blockDim.x >> 4;
+  const int grp = tid / LANES, sl = tid % LANES;
+  constexpr int NGRP = 64;
   for (int idx = tid; idx < m * m; idx += blockDim.x) {
     const int col = idx / m, row = idx - col * m;
     G[idx] = B[(size_t)row * m + col];
-    Vr[idx] = (row == col) ? 1.0 : 0.0;
   }
-  if (tid == 0) rotated = 0;
   __syncthreads();
   const int np = m + (m & 1);
-  const int npairs = np >> 1;
+  const int npairs = np >> 1;  // <= 64: one pair per group
   int sweeps = 0;
   for (; sweeps < 60; ++sweeps) {
-    for (int rd = 0; rd < np - 1; ++rd) {
-      for (int base = 0; base < npairs; base += nhw) {
-        const int pr = base + hw;
-        int p = -1, q = -1;
-        if (pr < npairs) {
-          const int i0 = pr, i1 = np - 1 - pr;
-          p = (i0 == 0) ? 0 : 1 + (((i0 - 1 - rd) % (np - 1)) + (np - 1)) % (np - 1);
-          q = 1 + (((i1 - 1 - rd) % (np - 1)) + (np - 1)) % (np - 1);
-          if (p > q) {
-            const int tmp = p;
-            p = q;
-            q = tmp;
-          }
-        }
-        const bool act = (pr < npairs) && (q < m);
-        double al = 0, be = 0, ga = 0;
-        if (act) {
-          const double* gp = G + (size_t)p * m;
-          const double* gq = G + (size_t)q * m;
-          for (int i = sl; i < m; i += 16) {
-            const double a = gp[i], b = gq[i];
-            al += a * a;
-            be += b * b;
-            ga += a * b;
-          }
-        }
+    // exact column norms at the start of every sweep
+    for (int base = 0; base < m; base += NGRP) {  // warp-uniform trip count (shuffles inside)
+      const int col = base + grp;
+      double sq = 0;
+      if (col < m)
+        for (int i = sl; i < m; i += LANES) sq = fma(G[(size_t)col * m + i], G[(size_t)col * m + i], sq);
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
-          al += __shfl_xor_sync(0xffffffffu, al, o);
-          be += __shfl_xor_sync(0xffffffffu, be, o);
-          ga += __shfl_xor_sync(0xffffffffu, ga, o);
-        }
-        if (act && fabs(ga) > 1e-15 * sqrt(al * be)) {
-          const double zeta = (be - al) / (2.0 * ga);
-          const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
-          double* gp = G + (size_t)p * m;
-          double* gq = G + (size_t)q * m;
-          volatile double* vp = Vr + (size_t)p * m;
-          volatile double* vq = Vr + (size_t)q * m;
-          for (int i = sl; i < m; i += 16) {
-            const double a = gp[i], b = gq[i];
-            gp[i] = cs * a - sn * b;
-            gq[i] = sn * a + cs * b;
-            const double c = vp[i], d = vq[i];
-            vp[i] = cs * c - sn * d;
-            vq[i] = sn * c + cs * d;
+      for (int o = LANES / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      if (col < m && sl == 0) nrm[col] = sq;
+    }
+    if (tid == 0) rotated = 0;
+    bool rotated_local = false;
+    __syncthreads();
+    // round-robin schedule, kept incrementally: slot i of round rd holds player 1 + (i-1-rd) mod (np-1)
+    // (slot 0 holds player 0), pairs are slots (g, np-1-g); going to the next round moves every player
+    // >= 1 one step down the circle (1 wraps to np-1) -- no integer division in the loop.
+    int pa = (grp == 0) ? 0 : grp, pb = np - 1 - grp;
+    bool big = false;
+    for (int rd = 0; rd < np - 1; ++rd) {
+      const int p = min(pa, pb), q = max(pa, pb);
+      const bool act = (grp < npairs) && (q < m);
+      double* gpp = G + (size_t)(act ? p : 0) * m;
+      double* gqp = G + (size_t)(act ? q : 0) * m;
+      double gp[R], gq[R];
+      double ga0 = 0, ga1 = 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int i = sl + LANES * r;
+        const bool ok = act && i < m;
+        gp[r] = ok ? gpp[i] : 0.0;
+        gq[r] = ok ? gqp[i] : 0.0;
+      }
+#pragma unroll
+      for (int r = 0; r < R; r += 2) {
+        ga0 = fma(gp[r], gq[r], ga0);
+        ga1 = fma(gp[r + 1], gq[r + 1], ga1);
+      }
+      double ga = ga0 + ga1;
+#pragma unroll
+      for (int o = LANES / 2; o > 0; o >>= 1) ga += __shfl_xor_sync(0xffffffffu, ga, o);
+      if (act) {
+        const double al = nrm[p], be = nrm[q];
+        const double g2 = ga * ga, ab = al * be;
+        if (g2 > 1e-30 * ab) {
+          // Rotation angle in fp32 (tan of the Jacobi angle; the fp64 convergence test above decides
+          // when to stop, so fp32 here only costs an occasional extra rotation), then an exactly
+          // orthogonal (c, s) in fp64: c = rsqrt(1 + t^2) by two Newton steps from the fp32 seed.
+          const float d32 = (float)(be - al), g32 = (float)ga;
+          const float z = __fdividef(d32, 2.0f * g32);
+          const float t32 = __fdividef(copysignf(1.0f, z), fabsf(z) + sqrtf(fmaf(z, z, 1.0f)));
+          double cs, sn;
+          if (t32 != 0.0f && isfinite(t32)) {
+            const double t = (double)t32;
+            const double w = fma(t, t, 1.0);
+            cs = (double)rsqrtf((float)w);
+            cs = cs * fma(-0.5 * w, cs * cs, 1.5);
+            cs = cs * fma(-0.5 * w, cs * cs, 1.5);
+            sn = cs * t;
+          } else {  // fp32 range exhausted (columns of wildly different norm): all-fp64 angle
+            const double d = be - al;
+            const double rh = rsqrt(fma(d, d, 4.0 * g2));
+            const double c2 = fma(0.5 * fabs(d), rh, 0.5);
+            const double rc = rsqrt(c2);
+            cs = c2 * rc;
+            sn = (d >= 0 ? ga : -ga) * rh * rc;
           }
-          if (sl == 0) rotated = 1;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const int i = sl + LANES * r;
+            if (i < m) {
+              gpp[i] = cs * gp[r] - sn * gq[r];
+              gqp[i] = sn * gp[r] + cs * gq[r];
+            }
+          }
+          if (sl == 0) {
+            const double c2 = cs * cs, s2 = sn * sn, x = 2.0 * cs * sn * ga;
+            nrm[p] = c2 * al - x + s2 * be;
+            nrm[q] = s2 * al + x + c2 * be;
+          }
+          big = big || (g2 > 1e-16 * ab);
+          rotated_local = true;
         }
       }
+      if (pa > 0) pa = (pa == 1) ? np - 1 : pa - 1;
+      pb = (pb == 1) ? np - 1 : pb - 1;
       __syncthreads();
     }
-    const int any = rotated;
+    if (sl == 0 && rotated_local) atomicOr(&rotated, big ? 3 : 1);
     __syncthreads();
-    if (tid == 0) rotated = 0;
+    const int flags = rotated;
     __syncthreads();
-    if (!any) break;
-  }
-  // singular values = column norms
-  for (int base = 0; base < m; base += nhw) {
-    const int col = base + hw;
-    double s = 0;
-    if (col < m)
-      for (int i = sl; i < m; i += 16) s += G[(size_t)col * m + i] * G[(size_t)col * m + i];
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (col < m && sl == 0) svs[col] = sqrt(s);
-  }
-  __syncthreads();
-  for (int base = 0; base < m; base += nhw) {
-    const int col = base + hw;
-    if (col < m) {
-      const double sv = svs[col];
-      int rank = 0;
-      for (int o = 0; o < m; ++o) rank += (svs[o] > sv) || (svs[o] == sv && o < col);
-      const double inv = sv > 0 ? 1.0 / sv : 0.0;
-      for (int i = sl; i < m; i += 16) {
-        Su[(size_t)rank * m + i] = G[(size_t)col * m + i] * inv;
-        Sv[(size_t)rank * m + i] = Vr[(size_t)col * m + i];
-      }
-      if (sl == 0) svout[rank] = sv;
+    // no rotation at all, or every cosine seen in this sweep was below 1e-8 (quadratic convergence:
+    // the rotations of this sweep already took them below 1e-15)
+    if ((flags & 2) == 0) {
+      ++sweeps;
+      break;
     }
   }
+  // singular values = exact column norms; rank by descending value (ties: column order)
+  for (int base = 0; base < m; base += NGRP) {
+    const int col = base + grp;
+    double sq = 0;
+    if (col < m)
+      for (int i = sl; i < m; i += LANES) sq = fma(G[(size_t)col * m + i], G[(size_t)col * m + i], sq);
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if (col < m && sl == 0) nrm[col] = sqrt(sq);
+  }
+  __syncthreads();
+  for (int col = tid; col < m; col += blockDim.x) {
+    const double sv = nrm[col];
+    int rank = 0;
+    for (int o = 0; o < m; ++o) rank += (nrm[o] > sv) || (nrm[o] == sv && o < col);
+    rankof[col] = rank;
+    inv[col] = sv > 0 ? 1.0 / sv : 0.0;
+    svout[rank] = sv;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < m * m; idx += blockDim.x) {  // U = G diag(1/sv), kept in shared memory too
+    const int col = idx / m, row = idx - col * m;
+    const double u = G[idx] * inv[col];
+    G[idx] = u;
+    Su[(size_t)rankof[col] * m + row] = u;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < m * m; idx += blockDim.x) {  // Vr = B^T U diag(1/sv)
+    const int col = idx / m, i = idx - col * m;
+    const double* u = G + (size_t)col * m;
+    double a = 0;
+#pragma unroll 4
+    for (int r = 0; r < m; ++r) a = fma(__ldg(B + (size_t)r * m + i), u[r], a);
+    Sv[(size_t)rankof[col] * m + i] = a * inv[col];
+  }
   if (tid == 0) info[2] = sweeps;
+}
+
+typedef void (*jacobi_fn)(const double*, int, double*, double*, double*, int*);
+constexpr int JLANES = 16;
+static jacobi_fn jacobi_for(int m) {
+  switch ((m + 2 * JLANES - 1) / (2 * JLANES)) {  // R rounded up to even
+    case 0:
+    case 1: return jacobi_svd<JLANES, 2>;
+    case 2: return jacobi_svd<JLANES, 4>;
+    case 3: return jacobi_svd<JLANES, 6>;
+    case 4: return jacobi_svd<JLANES, 8>;
+    case 5: return jacobi_svd<JLANES, 10>;
+    case 6: return jacobi_svd<JLANES, 12>;
+    case 7: return jacobi_svd<JLANES, 14>;
+    default: return jacobi_svd<JLANES, 16>;
+  }
 }
 
 // ---- residuals, convergence count and the next k (irlb.py:225-234) ------------------------------
@@ -379,32 +456,66 @@ __global__ void conv_check(const double* __restrict__ Su, const double* __restri
 }
 
 // ---- Q[:, :kc] <- Q[:, :m] S[:, :kc]  (irlb.py:238, 246, 249-250); S column-major m x m ----------
+// Tall-skinny fp64 GEMM, row-local, in place.  One thread per row: a 64-row tile of Q is staged
+// transposed in shared memory ([i][row], conflict-free column reads), S sits in shared memory as
+// [i][kcp] and is read as warp-wide broadcasts of 8 consecutive columns (4 x LDS.128), so the inner
+// loop is 5 shared loads per 8 DFMA -- the kernel runs at the SM's fp64 rate, not its LDS rate.
+// Warp w: rows (w & 1) * 32 + lane of the tile, column chunks (w >> 1), (w >> 1) + 4, ...
+constexpr int RB_ROWS = 64;
+constexpr int RB_QP = RB_ROWS + 1;
 __global__ void __launch_bounds__(256) rotate_basis(double* __restrict__ Q, int ld, i64 rows, const double* __restrict__ S,
                                                     int m, int kc, double* __restrict__ out, int ldo,
                                                     const double* __restrict__ colscale) {
-  extern __shared__ double sm[];
-  double* Ssm = sm;                                     // [m][kc]
-  double* rowbuf = sm + (size_t)m * kc + (threadIdx.x >> 5) * m;  // per warp [m]
-  for (int idx = threadIdx.x; idx < m * kc; idx += blockDim.x) {
-    const int c = idx / m, i = idx - c * m;
-    Ssm[(size_t)i * kc + c] = S[(size_t)c * m + i];
+  extern __shared__ __align__(16) double sm[];
+  const int kcp = (kc + 7) & ~7;
+  double* Ssm = sm;                          // [m][kcp]
+  double* Qs = sm + (size_t)m * kcp;         // [m][RB_QP]
+  for (int idx = threadIdx.x; idx < m * kcp; idx += blockDim.x) {
+    const int i = idx / kcp, c = idx - i * kcp;
+    Ssm[idx] = (c < kc) ? S[(size_t)c * m + i] : 0.0;
   }
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const i64 warps = ((i64)gridDim.x * blockDim.x) >> 5;
-  for (i64 r = (((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < rows; r += warps) {
-    double* qr = Q + (size_t)r * ld;
-    for (int i = lane; i < m; i += 32) rowbuf[i] = qr[i];
-    __syncwarp();
-    for (int c = lane; c < kc; c += 32) {
-      double a = 0;
-      for (int i = 0; i < m; ++i) a += rowbuf[i] * Ssm[(size_t)i * kc + c];
-      if (out)
-        out[(size_t)r * ldo + c] = colscale ? a * colscale[c] : a;
-      else
-        qr[c] = a;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = (warp & 1) * 32 + lane, cg = warp >> 1;
+  const int nchunks = kcp >> 3;
+  const i64 ntiles = (rows + RB_ROWS - 1) / RB_ROWS;
+  for (i64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const i64 row0 = t * RB_ROWS;
+    __syncthreads();  // previous tile fully consumed (and Ssm written, first time round)
+    for (int idx = threadIdx.x; idx < RB_ROWS * m; idx += blockDim.x) {
+      const int r = idx / m, i = idx - r * m;
+      Qs[(size_t)i * RB_QP + r] = (row0 + r < rows) ? Q[(size_t)(row0 + r) * ld + i] : 0.0;
     }
-    __syncwarp();
+    __syncthreads();
+    const bool live = row0 + row < rows;
+    for (int ch = cg; ch < nchunks; ch += 4) {
+      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      const double* sp = Ssm + ch * 8;
+      const double* qp = Qs + row;
+#pragma unroll 4
+      for (int i = 0; i < m; ++i) {
+        const double x = qp[(size_t)i * RB_QP];
+        const double2 s0 = *reinterpret_cast<const double2*>(sp + (size_t)i * kcp);
+        const double2 s1 = *reinterpret_cast<const double2*>(sp + (size_t)i * kcp + 2);
+        const double2 s2 = *reinterpret_cast<const double2*>(sp + (size_t)i * kcp + 4);
+        const double2 s3 = *reinterpret_cast<const double2*>(sp + (size_t)i * kcp + 6);
+        acc[0] = fma(x, s0.x, acc[0]);
+        acc[1] = fma(x, s0.y, acc[1]);
+        acc[2] = fma(x, s1.x, acc[2]);
+        acc[3] = fma(x, s1.y, acc[3]);
+        acc[4] = fma(x, s2.x, acc[4]);
+        acc[5] = fma(x, s2.y, acc[5]);
+        acc[6] = fma(x, s3.x, acc[6]);
+        acc[7] = fma(x, s3.y, acc[7]);
+      }
+      if (live) {
+        double* dst = out ? out + (size_t)(row0 + row) * ldo : Q + (size_t)(row0 + row) * ld;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int col = ch * 8 + c;
+          if (col < kc) dst[col] = colscale ? acc[c] * colscale[col] : acc[c];
+        }
+      }
+    }
   }
 }
 
@@ -428,13 +539,43 @@ __global__ void mul_vec(const double* a, const double* b, double* out, int n) {
   if (i < n) out[i] = a[i] * b[i];
 }
 
-static unsigned row_blocks(adobo_ctx* c, i64 rows) {
-  i64 b = (rows + 7) / 8;
-  i64 cap = (i64)c->sm_count * 4;
+static unsigned row_blocks(adobo_ctx* c, i64 rows) {  // rotate_basis: 64-row tiles, at most one CTA per SM
+  i64 b = (rows + RB_ROWS - 1) / RB_ROWS;
+  i64 cap = (i64)c->sm_count;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (unsigned)b;
 }
+
+static unsigned red_blocks(adobo_ctx* c, i64 rows) {  // 1024-thread CTAs of the reducing row kernels
+  i64 b = (rows + RT_WARPS - 1) / RT_WARPS;
+  if (b > c->sm_count) b = c->sm_count;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+// Workspace of the Lanczos driver.  It lives in the context across calls so that (a) repeated PCA
+// calls on same-shaped data do not re-allocate and (b) the CUDA graphs of one outer iteration --
+// keyed by (first iteration?, k) -- stay valid and are replayed: one graph launch and one 16-byte
+// read-back per restart instead of ~150 kernel launches.
+struct IrlbWs {
+  const void* sig_ptr[8] = {};
+  i64 sig_n = -1;
+  int sig_i[5] = {};
+  double sig_tol = 0;
+  DevBuf<double> V, W, B, sc, tbuf, ybuf_h, ybuf_n, fbuf, xs, wcur, cvec, partials, Su, Sv, svd_s, R, murs;
+  DevBuf<unsigned> counter;
+  DevBuf<int> info;
+  std::map<int, cudaGraphExec_t> graphs;
+  std::map<int, i64> graph_launches;
+  void clear_graphs() {
+    for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+    graphs.clear();
+    graph_launches.clear();
+  }
+  ~IrlbWs() { clear_graphs(); }
+};
+static void free_irlb_ws(void* p) { delete (IrlbWs*)p; }
 
 template <typename VT>
 IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const double* rs, int nu, double tol,
@@ -453,48 +594,69 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   const bool centered = (mu != nullptr);
   cudaStream_t st = c->stream;
 
-  DevBuf<double> V, W, B, sc, tbuf, ybuf_h, ybuf_n, fbuf, xs, wcur, cvec, partials, Su, Sv, svd_s, R, murs, vglob;
-  DevBuf<unsigned> counter;
-  DevBuf<int> info;
-  V.ensure((size_t)h * ld);
-  W.ensure((size_t)std::max<i64>(n, 1) * ld);
-  B.ensure((size_t)m_b * m_b);
-  sc.ensure(SC_COUNT);
-  tbuf.ensure((size_t)h);
-  ybuf_h.ensure((size_t)h);
-  ybuf_n.ensure((size_t)std::max<i64>(n, 1));
-  fbuf.ensure((size_t)h);
-  xs.ensure((size_t)h);
-  wcur.ensure((size_t)std::max<i64>(n, 1));
-  cvec.ensure(MAXB);
-  const unsigned gb_n = row_blocks(c, n), gb_h = row_blocks(c, h);
-  partials.ensure((size_t)std::max(gb_n, gb_h) * MAXB);
-  Su.ensure((size_t)m_b * m_b);
-  Sv.ensure((size_t)m_b * m_b);
-  svd_s.ensure((size_t)m_b);
-  R.ensure((size_t)m_b);
-  counter.ensure(1);
-  info.ensure(4);
+  if (!c->irlb_ws) {
+    c->irlb_ws = new IrlbWs();
+    c->irlb_ws_free = free_irlb_ws;
+  }
+  IrlbWs& ws = *(IrlbWs*)c->irlb_ws;
+  {
+    const void* sp[8] = {A.rptr.p, A.cidx.p, A.rval.p, A.cptr.p, A.ridx.p, A.cval.p, mu, rs};
+    const int si[5] = {h, nu, m_b, c->world, (int)sizeof(VT)};
+    bool same = ws.sig_n == n && ws.sig_tol == tol;
+    for (int q = 0; q < 8; ++q) same = same && ws.sig_ptr[q] == sp[q];
+    for (int q = 0; q < 5; ++q) same = same && ws.sig_i[q] == si[q];
+    if (!same) {
+      ws.clear_graphs();
+      for (int q = 0; q < 8; ++q) ws.sig_ptr[q] = sp[q];
+      for (int q = 0; q < 5; ++q) ws.sig_i[q] = si[q];
+      ws.sig_n = n;
+      ws.sig_tol = tol;
+    }
+  }
+  DevBuf<double>&V = ws.V, &W = ws.W, &B = ws.B, &sc = ws.sc, &tbuf = ws.tbuf, &ybuf_h = ws.ybuf_h, &ybuf_n = ws.ybuf_n,
+  &fbuf = ws.fbuf, &xs = ws.xs, &wcur = ws.wcur, &cvec = ws.cvec, &partials = ws.partials, &Su = ws.Su, &Sv = ws.Sv,
+  &svd_s = ws.svd_s, &R = ws.R, &murs = ws.murs;
+  DevBuf<unsigned>& counter = ws.counter;
+  DevBuf<int>& info = ws.info;
+  {
+    // a re-allocation moves a buffer: graphs that captured the old pointer must go
+    const double* before[4] = {V.p, W.p, partials.p, murs.p};
+    V.ensure((size_t)h * ld);
+    W.ensure((size_t)std::max<i64>(n, 1) * ld);
+    B.ensure((size_t)MAXB * MAXB);
+    sc.ensure(SC_COUNT);
+    tbuf.ensure((size_t)h);
+    ybuf_h.ensure((size_t)h);
+    ybuf_n.ensure((size_t)std::max<i64>(n, 1));
+    fbuf.ensure((size_t)h);
+    xs.ensure((size_t)h);
+    wcur.ensure((size_t)std::max<i64>(n, 1));
+    cvec.ensure(MAXB);
+    partials.ensure((size_t)c->sm_count * MAXB);
+    Su.ensure((size_t)MAXB * MAXB);
+    Sv.ensure((size_t)MAXB * MAXB);
+    svd_s.ensure((size_t)MAXB);
+    R.ensure((size_t)MAXB);
+    counter.ensure(1);
+    info.ensure(4);
+    murs.ensure((size_t)h);
+    const double* after[4] = {V.p, W.p, partials.p, murs.p};
+    for (int q = 0; q < 4; ++q)
+      if (before[q] != after[q]) ws.clear_graphs();
+  }
+  const unsigned gb_n = red_blocks(c, n), gb_h = red_blocks(c, h);
   CUDA_CHECK(cudaMemsetAsync(V.p, 0, sizeof(double) * (size_t)h * ld, st));
   CUDA_CHECK(cudaMemsetAsync(W.p, 0, sizeof(double) * (size_t)std::max<i64>(n, 1) * ld, st));
   CUDA_CHECK(cudaMemsetAsync(B.p, 0, sizeof(double) * m_b * m_b, st));
   CUDA_CHECK(cudaMemsetAsync(sc.p, 0, sizeof(double) * SC_COUNT, st));
   CUDA_CHECK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned), st));
   CUDA_CHECK(cudaMemsetAsync(cvec.p, 0, sizeof(double) * MAXB, st));
-  if (centered) {
-    murs.ensure((size_t)h);
-    LAUNCH(c, "mul_vec", (mul_vec<<<(h + 255) / 256, 256, 0, st>>>(mu, rs, murs.p, h)));
-  }
+  if (centered) LAUNCH(c, "mul_vec", (mul_vec<<<(h + 255) / 256, 256, 0, st>>>(mu, rs, murs.p, h)));
   // SVD kernel resources
-  size_t svd_smem = sizeof(double) * 2 * (size_t)m_b * m_b;
-  double* vg = nullptr;
-  if (svd_smem > 200 * 1024) {
-    vglob.ensure((size_t)m_b * m_b);
-    vg = vglob.p;
-    svd_smem = sizeof(double) * (size_t)m_b * m_b;
-  }
-  CUDA_CHECK(cudaFuncSetAttribute(jacobi_svd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem));
-  const size_t rot_smem = sizeof(double) * ((size_t)m_b * m_b + 8 * (size_t)m_b);
+  const size_t svd_smem = sizeof(double) * ((size_t)m_b * m_b + 256);
+  jacobi_fn jacobi = jacobi_for(m_b);
+  CUDA_CHECK(cudaFuncSetAttribute(jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem));
+  const size_t rot_smem = sizeof(double) * ((size_t)m_b * ((m_b + 7) & ~7) + (size_t)m_b * RB_QP);
   CUDA_CHECK(cudaFuncSetAttribute(rotate_basis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rot_smem));
 
   const unsigned fin_h = (unsigned)((h + 255) / 256), fin_n = (unsigned)std::max<i64>(1, (n + 255) / 256);
@@ -502,7 +664,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
 
   // ---- start vector (irlb.py:151-153): V[:,0] = v0 / ||v0|| ----
   CUDA_CHECK(cudaMemcpyAsync(ybuf_h.p, v0_host, sizeof(double) * h, cudaMemcpyHostToDevice, st));
-  LAUNCH(c, "update_norm", (update_norm<<<gb_h, 256, 0, st>>>(V.p, ld, 0, cvec.p, ybuf_h.p,
+  LAUNCH(c, "update_norm", (update_norm<<<gb_h, RT_THREADS, 0, st>>>(V.p, ld, 0, cvec.p, ybuf_h.p,
                                                             centered ? murs.p : nullptr, h, partials.p,
                                                             sc.p + SC_NRM2, counter.p)));
   LAUNCH(c, "v_finish", (v_finish<<<fin_h, 256, 0, st>>>(ybuf_h.p, rs, sc.p, V.p, ld, 0, m_b, h, fbuf.p, xs.p, B.p, -1,
@@ -511,49 +673,17 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   auto w_column = [&](int jprev, int nd, int jn) {
     // W[:, jn] = normalise( orthog( A_s x - fn W[:, jprev], W[:, :nd] ) )
     WORK(c, (double)A.nnz * (4.0 + sizeof(VT)) + 8.0 * (n + 1) + 8.0 * n * (nd + (jprev >= 0 ? 1 : 0) + 1) + 8.0 * h);
-    LAUNCH(c, "spmv_dots", (spmv_dots<VT><<<gb_n, 256, 0, st>>>(A.rptr.p, A.cidx.p, A.rval.p, xs.p, sc.p, W.p, ld, jprev,
+    LAUNCH(c, "spmv_dots", (spmv_dots<VT><<<gb_n, RT_THREADS, 0, st>>>(A.rptr.p, A.cidx.p, A.rval.p, xs.p, sc.p, W.p, ld, jprev,
                                                               nd, n, ybuf_n.p, partials.p, cvec.p, counter.p)));
     if (nd > 0) allreduce_sum_f64(c, cvec.p, (size_t)nd);
     WORK(c, 8.0 * n * (nd + 2));
-    LAUNCH(c, "update_norm", (update_norm<<<gb_n, 256, 0, st>>>(W.p, ld, nd, cvec.p, ybuf_n.p, nullptr, n, partials.p,
+    LAUNCH(c, "update_norm", (update_norm<<<gb_n, RT_THREADS, 0, st>>>(W.p, ld, nd, cvec.p, ybuf_n.p, nullptr, n, partials.p,
                                                               sc.p + SC_NRM2, counter.p)));
     allreduce_sum_f64(c, sc.p + SC_NRM2, 2);
     LAUNCH(c, "w_finish", (w_finish<<<fin_n, 256, 0, st>>>(ybuf_n.p, sc.p, W.p, ld, jn, n, wcur.p)));
   };
-
-  IrlbResult res;
-  int it = 0, k = nu, nmult = 0;
-  while (it < maxit) {
-    int j = (it > 0) ? k : 0;
-    w_column(-1, j, j);
-    ++nmult;
-    while (j < m_b) {
-      WORK(c, (double)A.nnz * (4.0 + sizeof(VT)) + 8.0 * (h + 1) + 8.0 * h + 8.0 * n);
-      LAUNCH(c, "spmvT_csc", (spmvT_csc<VT><<<h, 256, 0, st>>>(A.cptr.p, A.ridx.p, A.cval.p, wcur.p, tbuf.p)));
-      ++nmult;
-      allreduce_sum_f64(c, tbuf.p, (size_t)h);
-      WORK(c, 8.0 * h * (j + 1 + 4));
-      LAUNCH(c, "v_prep_dots", (v_prep_dots<<<gb_h, 256, 0, st>>>(tbuf.p, mu, rs, sc.p, V.p, ld, j, j + 1, h, ybuf_h.p,
-                                                                partials.p, cvec.p, counter.p)));
-      WORK(c, 8.0 * h * (j + 1 + 3));
-      LAUNCH(c, "update_norm_v", (update_norm<<<gb_h, 256, 0, st>>>(V.p, ld, j + 1, cvec.p, ybuf_h.p,
-                                                                centered ? murs.p : nullptr, h, partials.p,
-                                                                sc.p + SC_NRM2, counter.p)));
-      LAUNCH(c, "v_finish", (v_finish<<<fin_h, 256, 0, st>>>(ybuf_h.p, rs, sc.p, V.p, ld, j + 1, m_b, h, fbuf.p, xs.p,
-                                                           B.p, j, centered ? 1 : 0)));
-      if (j < m_b - 1) {
-        w_column(j, j + 1, j + 1);
-        ++nmult;
-      }
-      ++j;
-    }
-    LAUNCH(c, "jacobi_svd", (jacobi_svd<<<1, 1024, svd_smem, st>>>(B.p, m_b, Su.p, svd_s.p, Sv.p, vg, info.p)));
-    LAUNCH(c, "conv_check", (conv_check<<<1, 128, 0, st>>>(Su.p, svd_s.p, sc.p, m_b, nu, k, it, tol, R.p, info.p)));
-    CUDA_CHECK(cudaMemcpyAsync(h_info, info.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    const int conv = h_info[0];
-    if (conv >= nu) break;  // irlb.py:232-236
-    k = h_info[1];
+  // restart update (irlb.py:238-246): Ritz vectors into the leading k columns, V[:,k] = F, new B
+  auto restart_update = [&](int k) {
     LAUNCH(c, "rotate_basis", (rotate_basis<<<row_blocks(c, h), 256, rot_smem, st>>>(V.p, ld, h, Sv.p, m_b, k, nullptr, 0,
                                                                                  nullptr)));
     LAUNCH(c, "set_restart", (set_restart<<<(std::max(h, m_b * m_b) + 255) / 256, 256, 0, st>>>(V.p, ld, h, fbuf.p, B.p,
@@ -561,8 +691,83 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     WORK(c, 8.0 * n * (m_b + k));
     LAUNCH(c, "rotate_basis", (rotate_basis<<<row_blocks(c, n), 256, rot_smem, st>>>(W.p, ld, n, Su.p, m_b, k, nullptr, 0,
                                                                                  nullptr)));
+  };
+  // one outer iteration (irlb.py:155-231) up to the convergence read-back
+  auto enqueue_iteration = [&](bool first, int k) {
+    if (!first) restart_update(k);
+    int j = first ? 0 : k;
+    w_column(-1, j, j);
+    while (j < m_b) {
+      WORK(c, (double)A.nnz * (4.0 + sizeof(VT)) + 8.0 * (h + 1) + 8.0 * h + 8.0 * n);
+      LAUNCH(c, "spmvT_csc", (spmvT_csc<VT><<<h, 256, 0, st>>>(A.cptr.p, A.ridx.p, A.cval.p, wcur.p, tbuf.p)));
+      allreduce_sum_f64(c, tbuf.p, (size_t)h);
+      WORK(c, 8.0 * h * (j + 1 + 4));
+      LAUNCH(c, "v_prep_dots", (v_prep_dots<<<gb_h, RT_THREADS, 0, st>>>(tbuf.p, mu, rs, sc.p, V.p, ld, j, j + 1, h, ybuf_h.p,
+                                                                partials.p, cvec.p, counter.p)));
+      WORK(c, 8.0 * h * (j + 1 + 3));
+      LAUNCH(c, "update_norm_v", (update_norm<<<gb_h, RT_THREADS, 0, st>>>(V.p, ld, j + 1, cvec.p, ybuf_h.p,
+                                                                centered ? murs.p : nullptr, h, partials.p,
+                                                                sc.p + SC_NRM2, counter.p)));
+      LAUNCH(c, "v_finish", (v_finish<<<fin_h, 256, 0, st>>>(ybuf_h.p, rs, sc.p, V.p, ld, j + 1, m_b, h, fbuf.p, xs.p,
+                                                           B.p, j, centered ? 1 : 0)));
+      if (j < m_b - 1) w_column(j, j + 1, j + 1);
+      ++j;
+    }
+    LAUNCH(c, "jacobi_svd", (jacobi<<<1, 64 * JLANES, svd_smem, st>>>(B.p, m_b, Su.p, svd_s.p, Sv.p, info.p)));
+    LAUNCH(c, "conv_check", (conv_check<<<1, 128, 0, st>>>(Su.p, svd_s.p, sc.p, m_b, nu, k, first ? 0 : 1, tol, R.p, info.p)));
+    CUDA_CHECK(cudaMemcpyAsync(h_info, info.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+  };
+  const bool use_graphs = !c->profiling && getenv("ADOBO_B200_NO_GRAPH") == nullptr;
+  auto run_iteration = [&](bool first, int k) {
+    if (!use_graphs) {
+      enqueue_iteration(first, k);
+      return;
+    }
+    const int key = k | (first ? (1 << 16) : 0);
+    auto it = ws.graphs.find(key);
+    if (it == ws.graphs.end()) {
+      const i64 l0 = c->launches;
+      cudaGraph_t graph = nullptr;
+      CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      try {
+        enqueue_iteration(first, k);
+      } catch (...) {
+        cudaStreamEndCapture(st, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      CUDA_CHECK(cudaStreamEndCapture(st, &graph));
+      cudaGraphExec_t exec = nullptr;
+      cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) {
+        set_error("cudaGraphInstantiate -> %s", cudaGetErrorString(e));
+        throw Fail{ADOBO_ERR_CUDA};
+      }
+      ws.graph_launches[key] = c->launches - l0;
+      c->launches = l0;
+      it = ws.graphs.emplace(key, exec).first;
+    }
+    CUDA_CHECK(cudaGraphLaunch(it->second, st));
+    c->launches += ws.graph_launches[key];
+  };
+
+  IrlbResult res;
+  int it = 0, k = nu, nmult = 0;
+  bool converged = false;
+  while (it < maxit) {
+    run_iteration(it == 0, k);
+    nmult += 2 * (m_b - (it == 0 ? 0 : k));  // 1 + sum over j of (1 + [j < m_b-1]) mat-vecs
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (h_info[0] >= nu) {  // irlb.py:232-236
+      converged = true;
+      break;
+    }
+    k = h_info[1];
     ++it;
   }
+  // the reference applies the restart update before `it` reaches maxit (irlb.py:238-247)
+  if (!converged && it > 0) restart_update(k);
   // ---- U = W Su[:, :nu] (x diag(s) when var_weigh), V = V Sv[:, :nu]  (irlb.py:249-250, dr.py:164-168) ----
   outU.ensure((size_t)std::max<i64>(n, 1) * nu);
   outV.ensure((size_t)h * nu);
