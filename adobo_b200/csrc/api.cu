@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <mutex>
 #include <numeric>
 
 #include "common.cuh"
@@ -23,6 +24,75 @@ void set_error(const char* fmt, ...) {
 }
 
 void upload_normalized_values(adobo_ctx* c, const double* values);  // normalize.cu
+
+// ---- caching device allocator ---------------------------------------------------------------------
+namespace {
+struct Pool {
+  std::mutex mu;
+  std::map<int, std::multimap<size_t, void*>> free_blocks;  // device -> size -> block
+  std::map<void*, std::pair<int, size_t>> live;             // block -> (device, size)
+};
+Pool& pool() {
+  static Pool* p = new Pool();  // leaked on purpose: DevBufs may outlive static destruction order
+  return *p;
+}
+}  // namespace
+
+void* pool_alloc(size_t bytes) {
+  const size_t size = (bytes + 511) & ~(size_t)511;
+  int dev = 0;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  Pool& P = pool();
+  {
+    std::lock_guard<std::mutex> g(P.mu);
+    auto& fl = P.free_blocks[dev];
+    auto it = fl.lower_bound(size);
+    if (it != fl.end() && it->first <= size + size / 4 + 4096) {  // reuse when at most 25 % larger
+      void* p = it->second;
+      const size_t sz = it->first;
+      fl.erase(it);
+      P.live[p] = std::make_pair(dev, sz);
+      return p;
+    }
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, size);
+  if (e != cudaSuccess) {  // out of memory: drop the cache and retry once
+    cudaGetLastError();
+    pool_trim();
+    e = cudaMalloc(&p, size);
+  }
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%zu bytes) -> %s", size, cudaGetErrorString(e));
+    throw Fail{ADOBO_ERR_CUDA};
+  }
+  std::lock_guard<std::mutex> g(P.mu);
+  P.live[p] = std::make_pair(dev, size);
+  return p;
+}
+
+void pool_free(void* p) {
+  if (!p) return;
+  Pool& P = pool();
+  std::lock_guard<std::mutex> g(P.mu);
+  auto it = P.live.find(p);
+  if (it == P.live.end()) return;
+  P.free_blocks[it->second.first].insert(std::make_pair(it->second.second, p));
+  P.live.erase(it);
+}
+
+void pool_trim() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  Pool& P = pool();
+  std::vector<void*> blocks;
+  {
+    std::lock_guard<std::mutex> g(P.mu);
+    for (auto& kv : P.free_blocks[dev]) blocks.push_back(kv.second);
+    P.free_blocks[dev].clear();
+  }
+  for (void* b : blocks) cudaFree(b);
+}
 
 // ---- NCCL, resolved at run time so that single-GPU use does not need the library -------------
 struct NcclApi {
@@ -291,6 +361,7 @@ void adobo_ctx_destroy(adobo_ctx* c) {
   cudaStream_t st = c->stream;
   delete c;
   cudaStreamDestroy(st);
+  pool_trim();
 }
 
 int adobo_sync(adobo_ctx* c) {

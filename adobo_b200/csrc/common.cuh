@@ -37,7 +37,14 @@ struct Fail {
     }                               \
   } while (0)
 
-// ---- device buffer ------------------------------------------------------------------------
+// ---- device memory ------------------------------------------------------------------------
+// Caching allocator (api.cu): blocks released by DevBuf go back to a per-device free list instead
+// of cudaFree, so a steady-state pass of the hot path performs no cudaMalloc / cudaFree at all
+// (both serialise with the device and cost anywhere from microseconds to milliseconds).
+void* pool_alloc(size_t bytes);
+void pool_free(void* p);
+void pool_trim();  // cudaFree every cached block of the current device
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -46,11 +53,11 @@ struct DevBuf {
     if (n <= cap && p) return;
     release();
     size_t want = n ? n : 1;
-    CUDA_CHECK(cudaMalloc((void**)&p, want * sizeof(T)));
+    p = (T*)pool_alloc(want * sizeof(T));
     cap = want;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) pool_free(p);
     p = nullptr;
     cap = 0;
   }
