@@ -249,130 +249,244 @@ __global__ void w_finish(const double* __restrict__ ybuf, double* __restrict__ s
 }
 
 // ---- one-sided Jacobi SVD of B (m x m, row-major, m <= 128) in one CTA ---------------------------
-// G = B (column-major in shared memory).  Columns are rotated pairwise -- round-robin ordering, all
-// m/2 disjoint pairs of a round at once, LANES lanes per pair with the two columns in registers
-// (R = ceil(m / LANES) rows per lane) -- until mutually orthogonal: B Vr = U diag(sv).  The kernel
-// is bound by the fp64 rate of ONE SM, so the arithmetic is trimmed: column norms are cached
-// (refreshed exactly every sweep), the rotation comes from two rsqrt, and the right vectors are
-// not accumulated but recovered at the end as Vr = B^T U diag(1/sv) (one small GEMM; accurate for
-// the leading columns, which are the only ones the restart uses: k <= m - 3).
-// Outputs column-major, singular values descending.
-template <int LANES, int R>
-__global__ void __launch_bounds__(64 * LANES, 1) jacobi_svd(const double* __restrict__ B, int m, double* __restrict__ Su,
-                                                            double* __restrict__ svout, double* __restrict__ Sv,
-                                                            int* __restrict__ info) {
-  extern __shared__ double smem[];
-  double* G = smem;                       // [m][m] column-major
-  double* nrm = smem + (size_t)m * m;     // [m] squared column norms
-  double* inv = nrm + 128;                // [m] 1 / sv
+// G = B, column-major in shared memory (column stride LD = 16 R rows, zero padded; an extra zero
+// column when m is odd).  Columns are orthogonalised by plane rotations until B Vr = U diag(sv).
+// The kernel is bound by the issue rate and the shared-memory bandwidth of ONE SM -- a round of the
+// classic parallel ordering streams all of G through the register file for one rotation per column
+// -- so the ordering is BLOCKED: columns are grouped in blocks of two, the round-robin tournament
+// runs over blocks, and the 16 lanes that own a block pair (P, Q) load the four columns once
+// (128-bit LDS, bank-conflict free), apply the four cross rotations (a0,b0) (a1,b1) (a0,b1) (a1,b0)
+// in registers and store them once: half the shared-memory traffic and half the barriers per
+// sweep.  The intra-block pairs (a0,a1) are rotated at the start of each sweep.  Further trims: no
+// bounds predicates (padding), cached column norms (refreshed exactly every sweep), rotation angle
+// in fp32 with an exactly orthogonal fp64 (c, s), no accumulation of the right vectors:
+// Vr = B^T U diag(1/sv) is one small GEMM at the end (accurate for the leading columns, the only
+// ones the restart uses: k <= m - 3).  Outputs column-major, singular values descending.
+constexpr int JL = 16;        // lanes per block pair
+constexpr int JTHREADS = 512; // 32 groups >= 128 / 4 block pairs
+
+// (c, s) of the Jacobi rotation that orthogonalises two columns with squared norms nx, ny and inner
+// product ga; identity when the pair is already orthogonal to 1e-15.  The angle comes from fp32
+// arithmetic (the fp64 test decides when to stop, so fp32 only costs an occasional extra rotation);
+// (c, s) is then renormalised in fp64 so that the rotation is orthogonal to working precision.
+// Straight-line code: two independent calls interleave in the instruction stream.
+__device__ __forceinline__ int jacobi_angle(double ga, double nx, double ny, double& cs, double& sn) {
+  const double g2 = ga * ga, ab = nx * ny;
+  const bool rot = g2 > 1e-30 * ab;
+  const float d32 = (float)(ny - nx), g32 = (float)ga;
+  const float rh = rsqrtf(fmaf(d32, d32, 4.0f * g32 * g32));  // 1 / hypot(d, 2 gamma)
+  const float c2 = fmaf(0.5f * fabsf(d32), rh, 0.5f);          // cos^2 of the rotation angle
+  const float rc = rsqrtf(c2);
+  const float c32 = c2 * rc;
+  const float s32 = (d32 >= 0.0f ? g32 : -g32) * rh * rc;
+  double c = (double)c32, s_ = (double)s32;
+  const bool ok32 = isfinite(rh) && rh > 0.0f;
+  if (rot && !ok32) {  // fp32 range exhausted (columns of wildly different norm): all-fp64 angle
+    const double d = ny - nx;
+    const double rhd = rsqrt(fma(d, d, 4.0 * g2));
+    const double c2d = fma(0.5 * fabs(d), rhd, 0.5);
+    const double rcd = rsqrt(c2d);
+    c = c2d * rcd;
+    s_ = (d >= 0 ? ga : -ga) * rhd * rcd;
+  }
+  // renormalise: y = rsqrt(c^2 + s^2), two Newton steps from 1 (c^2 + s^2 = 1 +- 1e-6)
+  const double w = fma(c, c, s_ * s_);
+  double y = fma(-0.5, w, 1.5);
+  y = y * fma(-0.5 * w, y * y, 1.5);
+  cs = rot ? c * y : 1.0;
+  sn = rot ? s_ * y : 0.0;
+  return rot ? ((g2 > 1e-16 * ab) ? 3 : 1) : 0;
+}
+
+// two independent rotations (x0,y0) and (x1,y1), interleaved; columns are H double2 per lane, the
+// cached squared norms are updated in place; returns the OR of the convergence flags
+template <int H>
+__device__ __forceinline__ int jacobi_rotate2(double2 (&x0)[H], double2 (&y0)[H], double& nx0, double& ny0,
+                                              double2 (&x1)[H], double2 (&y1)[H], double& nx1, double& ny1) {
+  double p0 = 0, p1 = 0, q0 = 0, q1 = 0;
+#pragma unroll
+  for (int r = 0; r < H; ++r) {
+    p0 = fma(x0[r].x, y0[r].x, p0);
+    p1 = fma(x0[r].y, y0[r].y, p1);
+    q0 = fma(x1[r].x, y1[r].x, q0);
+    q1 = fma(x1[r].y, y1[r].y, q1);
+  }
+  double ga = p0 + p1, gb = q0 + q1;
+#pragma unroll
+  for (int o = JL / 2; o > 0; o >>= 1) {
+    ga += __shfl_xor_sync(0xffffffffu, ga, o);
+    gb += __shfl_xor_sync(0xffffffffu, gb, o);
+  }
+  double ca, sa, cb, sb;
+  const int fa = jacobi_angle(ga, nx0, ny0, ca, sa);
+  const int fb = jacobi_angle(gb, nx1, ny1, cb, sb);
+#pragma unroll
+  for (int r = 0; r < H; ++r) {
+    const double2 a = x0[r], b = y0[r], c = x1[r], d = y1[r];
+    x0[r].x = ca * a.x - sa * b.x;
+    x0[r].y = ca * a.y - sa * b.y;
+    y0[r].x = sa * a.x + ca * b.x;
+    y0[r].y = sa * a.y + ca * b.y;
+    x1[r].x = cb * c.x - sb * d.x;
+    x1[r].y = cb * c.y - sb * d.y;
+    y1[r].x = sb * c.x + cb * d.x;
+    y1[r].y = sb * c.y + cb * d.y;
+  }
+  {
+    const double c2 = ca * ca, s2 = sa * sa, xx = 2.0 * ca * sa * ga;
+    const double n = c2 * nx0 - xx + s2 * ny0;
+    ny0 = s2 * nx0 + xx + c2 * ny0;
+    nx0 = n;
+  }
+  {
+    const double c2 = cb * cb, s2 = sb * sb, xx = 2.0 * cb * sb * gb;
+    const double n = c2 * nx1 - xx + s2 * ny1;
+    ny1 = s2 * nx1 + xx + c2 * ny1;
+    nx1 = n;
+  }
+  return fa | fb;
+}
+
+template <int R>  // rows per lane (even); LD = JL * R >= m
+__global__ void __launch_bounds__(JTHREADS, 1) jacobi_svd(const double* __restrict__ B, int m, double* __restrict__ Su,
+                                                          double* __restrict__ svout, double* __restrict__ Sv,
+                                                          int* __restrict__ info) {
+  constexpr int LD = JL * R;
+  constexpr int H = R / 2;  // double2 per lane and column
+  constexpr int NGRP = JTHREADS / JL;
+  extern __shared__ __align__(16) double smem[];
+  const int nb = (m + 1) >> 1;             // column blocks (the last one is half empty when m is odd)
+  const int mc = 2 * nb;                   // columns held (column m is all zero when m is odd)
+  double* G = smem;                        // [mc][LD] column-major, rows >= m are zero
+  double* nrm = smem + (size_t)mc * LD;    // [mc] squared column norms
+  double* inv = nrm + 130;                 // [m] 1 / sv
   __shared__ int rotated;
   __shared__ int rankof[128];
   const int tid = threadIdx.x;
-  const int grp = tid / LANES, sl = tid % LANES;
-  constexpr int NGRP = 64;
-  for (int idx = tid; idx < m * m; idx += blockDim.x) {
-    const int col = idx / m, row = idx - col * m;
-    G[idx] = B[(size_t)row * m + col];
+  const int grp = tid / JL, sl = tid % JL;
+  for (int idx = tid; idx < mc * LD; idx += blockDim.x) {
+    const int col = idx / LD, row = idx - col * LD;
+    G[idx] = (row < m && col < m) ? B[(size_t)row * m + col] : 0.0;
   }
   __syncthreads();
-  const int np = m + (m & 1);
-  const int npairs = np >> 1;  // <= 64: one pair per group
+  const int nbp = nb + (nb & 1);           // players of the block tournament (dummy block when nb is odd)
+  const int nbpairs = nbp >> 1;            // <= 32 = NGRP
+  const bool warp_live = ((tid >> 5) * (32 / JL)) < nbpairs;
   int sweeps = 0;
   for (; sweeps < 60; ++sweeps) {
     // exact column norms at the start of every sweep
-    for (int base = 0; base < m; base += NGRP) {  // warp-uniform trip count (shuffles inside)
+    for (int base = 0; base < mc; base += NGRP) {  // warp-uniform trip count (shuffles inside)
       const int col = base + grp;
       double sq = 0;
-      if (col < m)
-        for (int i = sl; i < m; i += LANES) sq = fma(G[(size_t)col * m + i], G[(size_t)col * m + i], sq);
+      if (col < mc) {
+        const double* g = G + (size_t)col * LD;
 #pragma unroll
-      for (int o = LANES / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-      if (col < m && sl == 0) nrm[col] = sq;
+        for (int r = 0; r < R; ++r) sq = fma(g[sl + JL * r], g[sl + JL * r], sq);
+      }
+#pragma unroll
+      for (int o = JL / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      if (col < mc && sl == 0) nrm[col] = sq;
     }
     if (tid == 0) rotated = 0;
-    bool rotated_local = false;
     __syncthreads();
-    // round-robin schedule, kept incrementally: slot i of round rd holds player 1 + (i-1-rd) mod (np-1)
-    // (slot 0 holds player 0), pairs are slots (g, np-1-g); going to the next round moves every player
-    // >= 1 one step down the circle (1 wraps to np-1) -- no integer division in the loop.
-    int pa = (grp == 0) ? 0 : grp, pb = np - 1 - grp;
-    bool big = false;
-    for (int rd = 0; rd < np - 1; ++rd) {
-      const int p = min(pa, pb), q = max(pa, pb);
-      const bool act = (grp < npairs) && (q < m);
-      double* gpp = G + (size_t)(act ? p : 0) * m;
-      double* gqp = G + (size_t)(act ? q : 0) * m;
-      double gp[R], gq[R];
-      double ga0 = 0, ga1 = 0;
+    int flags = 0;
+    // ---- pairs inside a block: each group takes two blocks per pass ----
+    for (int base = 0; base < nb; base += 2 * NGRP) {  // warp-uniform
+      const int blk0 = base + 2 * grp, blk1 = blk0 + 1;
+      const bool act0 = blk0 < nb, act1 = blk1 < nb;
+      double2* c0 = reinterpret_cast<double2*>(G + (size_t)(act0 ? 2 * blk0 : 0) * LD) + sl;
+      double2* c1 = c0 + LD / 2;
+      double2* d0 = reinterpret_cast<double2*>(G + (size_t)(act1 ? 2 * blk1 : 0) * LD) + sl;
+      double2* d1 = d0 + LD / 2;
+      double2 x0[H], y0[H], x1[H], y1[H];
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int i = sl + LANES * r;
-        const bool ok = act && i < m;
-        gp[r] = ok ? gpp[i] : 0.0;
-        gq[r] = ok ? gqp[i] : 0.0;
+      for (int r = 0; r < H; ++r) {
+        x0[r] = act0 ? c0[JL * r] : make_double2(0.0, 0.0);  // idle slots rotate zeros: no flags
+        y0[r] = act0 ? c1[JL * r] : make_double2(0.0, 0.0);
+        x1[r] = act1 ? d0[JL * r] : make_double2(0.0, 0.0);
+        y1[r] = act1 ? d1[JL * r] : make_double2(0.0, 0.0);
       }
+      double nx0 = act0 ? nrm[2 * blk0] : 0.0, ny0 = act0 ? nrm[2 * blk0 + 1] : 0.0;
+      double nx1 = act1 ? nrm[2 * blk1] : 0.0, ny1 = act1 ? nrm[2 * blk1 + 1] : 0.0;
+      const int f = jacobi_rotate2<H>(x0, y0, nx0, ny0, x1, y1, nx1, ny1);
+      if (act0) {
 #pragma unroll
-      for (int r = 0; r < R; r += 2) {
-        ga0 = fma(gp[r], gq[r], ga0);
-        ga1 = fma(gp[r + 1], gq[r + 1], ga1);
-      }
-      double ga = ga0 + ga1;
-#pragma unroll
-      for (int o = LANES / 2; o > 0; o >>= 1) ga += __shfl_xor_sync(0xffffffffu, ga, o);
-      if (act) {
-        const double al = nrm[p], be = nrm[q];
-        const double g2 = ga * ga, ab = al * be;
-        if (g2 > 1e-30 * ab) {
-          // Rotation angle in fp32 (tan of the Jacobi angle; the fp64 convergence test above decides
-          // when to stop, so fp32 here only costs an occasional extra rotation), then an exactly
-          // orthogonal (c, s) in fp64: c = rsqrt(1 + t^2) by two Newton steps from the fp32 seed.
-          const float d32 = (float)(be - al), g32 = (float)ga;
-          const float z = __fdividef(d32, 2.0f * g32);
-          const float t32 = __fdividef(copysignf(1.0f, z), fabsf(z) + sqrtf(fmaf(z, z, 1.0f)));
-          double cs, sn;
-          if (t32 != 0.0f && isfinite(t32)) {
-            const double t = (double)t32;
-            const double w = fma(t, t, 1.0);
-            cs = (double)rsqrtf((float)w);
-            cs = cs * fma(-0.5 * w, cs * cs, 1.5);
-            cs = cs * fma(-0.5 * w, cs * cs, 1.5);
-            sn = cs * t;
-          } else {  // fp32 range exhausted (columns of wildly different norm): all-fp64 angle
-            const double d = be - al;
-            const double rh = rsqrt(fma(d, d, 4.0 * g2));
-            const double c2 = fma(0.5 * fabs(d), rh, 0.5);
-            const double rc = rsqrt(c2);
-            cs = c2 * rc;
-            sn = (d >= 0 ? ga : -ga) * rh * rc;
-          }
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const int i = sl + LANES * r;
-            if (i < m) {
-              gpp[i] = cs * gp[r] - sn * gq[r];
-              gqp[i] = sn * gp[r] + cs * gq[r];
-            }
-          }
-          if (sl == 0) {
-            const double c2 = cs * cs, s2 = sn * sn, x = 2.0 * cs * sn * ga;
-            nrm[p] = c2 * al - x + s2 * be;
-            nrm[q] = s2 * al + x + c2 * be;
-          }
-          big = big || (g2 > 1e-16 * ab);
-          rotated_local = true;
+        for (int r = 0; r < H; ++r) {
+          c0[JL * r] = x0[r];
+          c1[JL * r] = y0[r];
+        }
+        if (sl == 0) {
+          nrm[2 * blk0] = nx0;
+          nrm[2 * blk0 + 1] = ny0;
         }
       }
-      if (pa > 0) pa = (pa == 1) ? np - 1 : pa - 1;
-      pb = (pb == 1) ? np - 1 : pb - 1;
+      if (act1) {
+#pragma unroll
+        for (int r = 0; r < H; ++r) {
+          d0[JL * r] = x1[r];
+          d1[JL * r] = y1[r];
+        }
+        if (sl == 0) {
+          nrm[2 * blk1] = nx1;
+          nrm[2 * blk1 + 1] = ny1;
+        }
+      }
+      flags |= f;
+    }
+    __syncthreads();
+    // ---- round-robin over blocks, kept incrementally: slot i of round rd holds block
+    // 1 + (i-1-rd) mod (nbp-1) (slot 0 holds block 0), pairs are slots (g, nbp-1-g); the next round
+    // moves every block >= 1 one step down the circle (1 wraps to nbp-1).
+    int pa = (grp < nbpairs) ? grp : 0, pb = (grp < nbpairs) ? nbp - 1 - grp : 1;
+    for (int rd = 0; rd < nbp - 1; ++rd) {
+      if (warp_live) {
+        const int P = min(pa, pb), Q = max(pa, pb);
+        const bool act = (grp < nbpairs) && (Q < nb);
+        const int Qs = act ? Q : P;  // idle groups read block P twice and store nothing
+        double2* a0p = reinterpret_cast<double2*>(G + (size_t)(2 * P) * LD) + sl;
+        double2* a1p = a0p + LD / 2;
+        double2* b0p = reinterpret_cast<double2*>(G + (size_t)(2 * Qs) * LD) + sl;
+        double2* b1p = b0p + LD / 2;
+        double2 a0[H], a1[H], b0[H], b1[H];
+#pragma unroll
+        for (int r = 0; r < H; ++r) {
+          a0[r] = a0p[JL * r];
+          a1[r] = a1p[JL * r];
+          b0[r] = b0p[JL * r];
+          b1[r] = b1p[JL * r];
+        }
+        double na0 = nrm[2 * P], na1 = nrm[2 * P + 1], nb0 = nrm[2 * Qs], nb1 = nrm[2 * Qs + 1];
+        if (!act) nb0 = nb1 = 0.0;  // zero norm -> no rotation
+        int f = jacobi_rotate2<H>(a0, b0, na0, nb0, a1, b1, na1, nb1);
+        f |= jacobi_rotate2<H>(a0, b1, na0, nb1, a1, b0, na1, nb0);
+        if (act) {
+#pragma unroll
+          for (int r = 0; r < H; ++r) {
+            a0p[JL * r] = a0[r];
+            a1p[JL * r] = a1[r];
+            b0p[JL * r] = b0[r];
+            b1p[JL * r] = b1[r];
+          }
+          if (sl == 0) {
+            nrm[2 * P] = na0;
+            nrm[2 * P + 1] = na1;
+            nrm[2 * Q] = nb0;
+            nrm[2 * Q + 1] = nb1;
+          }
+          flags |= f;
+        }
+        if (pa > 0) pa = (pa == 1) ? nbp - 1 : pa - 1;
+        pb = (pb == 1) ? nbp - 1 : pb - 1;
+      }
       __syncthreads();
     }
-    if (sl == 0 && rotated_local) atomicOr(&rotated, big ? 3 : 1);
+    if (sl == 0 && flags) atomicOr(&rotated, flags);
     __syncthreads();
-    const int flags = rotated;
+    const int all_flags = rotated;
     __syncthreads();
     // no rotation at all, or every cosine seen in this sweep was below 1e-8 (quadratic convergence:
     // the rotations of this sweep already took them below 1e-15)
-    if ((flags & 2) == 0) {
+    if ((all_flags & 2) == 0) {
       ++sweeps;
       break;
     }
@@ -381,10 +495,13 @@ __global__ void __launch_bounds__(64 * LANES, 1) jacobi_svd(const double* __rest
   for (int base = 0; base < m; base += NGRP) {
     const int col = base + grp;
     double sq = 0;
-    if (col < m)
-      for (int i = sl; i < m; i += LANES) sq = fma(G[(size_t)col * m + i], G[(size_t)col * m + i], sq);
+    if (col < m) {
+      const double* g = G + (size_t)col * LD;
 #pragma unroll
-    for (int o = LANES / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      for (int r = 0; r < R; ++r) sq = fma(g[sl + JL * r], g[sl + JL * r], sq);
+    }
+#pragma unroll
+    for (int o = JL / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     if (col < m && sl == 0) nrm[col] = sqrt(sq);
   }
   __syncthreads();
@@ -399,14 +516,14 @@ __global__ void __launch_bounds__(64 * LANES, 1) jacobi_svd(const double* __rest
   __syncthreads();
   for (int idx = tid; idx < m * m; idx += blockDim.x) {  // U = G diag(1/sv), kept in shared memory too
     const int col = idx / m, row = idx - col * m;
-    const double u = G[idx] * inv[col];
-    G[idx] = u;
+    const double u = G[(size_t)col * LD + row] * inv[col];
+    G[(size_t)col * LD + row] = u;
     Su[(size_t)rankof[col] * m + row] = u;
   }
   __syncthreads();
   for (int idx = tid; idx < m * m; idx += blockDim.x) {  // Vr = B^T U diag(1/sv)
     const int col = idx / m, i = idx - col * m;
-    const double* u = G + (size_t)col * m;
+    const double* u = G + (size_t)col * LD;
     double a = 0;
 #pragma unroll 4
     for (int r = 0; r < m; ++r) a = fma(__ldg(B + (size_t)r * m + i), u[r], a);
@@ -416,18 +533,13 @@ __global__ void __launch_bounds__(64 * LANES, 1) jacobi_svd(const double* __rest
 }
 
 typedef void (*jacobi_fn)(const double*, int, double*, double*, double*, int*);
-constexpr int JLANES = 16;
+static int jacobi_rows_per_lane(int m) { return 2 * ((m + 2 * JL - 1) / (2 * JL)); }  // even R with 16 R >= m
 static jacobi_fn jacobi_for(int m) {
-  switch ((m + 2 * JLANES - 1) / (2 * JLANES)) {  // R rounded up to even
-    case 0:
-    case 1: return jacobi_svd<JLANES, 2>;
-    case 2: return jacobi_svd<JLANES, 4>;
-    case 3: return jacobi_svd<JLANES, 6>;
-    case 4: return jacobi_svd<JLANES, 8>;
-    case 5: return jacobi_svd<JLANES, 10>;
-    case 6: return jacobi_svd<JLANES, 12>;
-    case 7: return jacobi_svd<JLANES, 14>;
-    default: return jacobi_svd<JLANES, 16>;
+  switch (jacobi_rows_per_lane(m)) {
+    case 2: return jacobi_svd<2>;
+    case 4: return jacobi_svd<4>;
+    case 6: return jacobi_svd<6>;
+    default: return jacobi_svd<8>;
   }
 }
 
@@ -653,7 +765,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   CUDA_CHECK(cudaMemsetAsync(cvec.p, 0, sizeof(double) * MAXB, st));
   if (centered) LAUNCH(c, "mul_vec", (mul_vec<<<(h + 255) / 256, 256, 0, st>>>(mu, rs, murs.p, h)));
   // SVD kernel resources
-  const size_t svd_smem = sizeof(double) * ((size_t)m_b * m_b + 256);
+  const size_t svd_smem = sizeof(double) * ((size_t)(m_b + 1) * JL * jacobi_rows_per_lane(m_b) + 260);
   jacobi_fn jacobi = jacobi_for(m_b);
   CUDA_CHECK(cudaFuncSetAttribute(jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem));
   const size_t rot_smem = sizeof(double) * ((size_t)m_b * ((m_b + 7) & ~7) + (size_t)m_b * RB_QP);
@@ -713,7 +825,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
       if (j < m_b - 1) w_column(j, j + 1, j + 1);
       ++j;
     }
-    LAUNCH(c, "jacobi_svd", (jacobi<<<1, 64 * JLANES, svd_smem, st>>>(B.p, m_b, Su.p, svd_s.p, Sv.p, info.p)));
+    LAUNCH(c, "jacobi_svd", (jacobi<<<1, JTHREADS, svd_smem, st>>>(B.p, m_b, Su.p, svd_s.p, Sv.p, info.p)));
     LAUNCH(c, "conv_check", (conv_check<<<1, 128, 0, st>>>(Su.p, svd_s.p, sc.p, m_b, nu, k, first ? 0 : 1, tol, R.p, info.p)));
     CUDA_CHECK(cudaMemcpyAsync(h_info, info.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
   };
