@@ -270,18 +270,21 @@ constexpr int JTHREADS = 512; // 32 groups >= 128 / 4 block pairs
 // arithmetic (the fp64 test decides when to stop, so fp32 only costs an occasional extra rotation);
 // (c, s) is then renormalised in fp64 so that the rotation is orthogonal to working precision.
 // Straight-line code: two independent calls interleave in the instruction stream.
+__device__ __forceinline__ float rsqrt_approx(float x) {  // one MUFU.RSQ, no denormal fix-up
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ int jacobi_angle(double ga, double nx, double ny, double& cs, double& sn) {
   const double g2 = ga * ga, ab = nx * ny;
   const bool rot = g2 > 1e-30 * ab;
   const float d32 = (float)(ny - nx), g32 = (float)ga;
-  const float rh = rsqrtf(fmaf(d32, d32, 4.0f * g32 * g32));  // 1 / hypot(d, 2 gamma)
+  const float h2 = fmaf(d32, d32, 4.0f * g32 * g32);
+  const float rh = rsqrt_approx(h2);                           // 1 / hypot(d, 2 gamma)
   const float c2 = fmaf(0.5f * fabsf(d32), rh, 0.5f);          // cos^2 of the rotation angle
-  const float rc = rsqrtf(c2);
-  const float c32 = c2 * rc;
-  const float s32 = (d32 >= 0.0f ? g32 : -g32) * rh * rc;
-  double c = (double)c32, s_ = (double)s32;
-  const bool ok32 = isfinite(rh) && rh > 0.0f;
-  if (rot && !ok32) {  // fp32 range exhausted (columns of wildly different norm): all-fp64 angle
+  const float rc = rsqrt_approx(c2);
+  double c = (double)(c2 * rc), s_ = (double)((d32 >= 0.0f ? g32 : -g32) * rh * rc);
+  if (rot && !(h2 > 1e-30f && h2 < 1e30f)) {  // fp32 range exhausted (wildly different norms): fp64 angle
     const double d = ny - nx;
     const double rhd = rsqrt(fma(d, d, 4.0 * g2));
     const double c2d = fma(0.5 * fabs(d), rhd, 0.5);
@@ -568,67 +571,104 @@ __global__ void conv_check(const double* __restrict__ Su, const double* __restri
 }
 
 // ---- Q[:, :kc] <- Q[:, :m] S[:, :kc]  (irlb.py:238, 246, 249-250); S column-major m x m ----------
-// Tall-skinny fp64 GEMM, row-local, in place.  One thread per row: a 64-row tile of Q is staged
-// transposed in shared memory ([i][row], conflict-free column reads), S sits in shared memory as
-// [i][kcp] and is read as warp-wide broadcasts of 8 consecutive columns (4 x LDS.128), so the inner
-// loop is 5 shared loads per 8 DFMA -- the kernel runs at the SM's fp64 rate, not its LDS rate.
-// Warp w: rows (w & 1) * 32 + lane of the tile, column chunks (w >> 1), (w >> 1) + 4, ...
+// Tall-skinny fp64 GEMM, row-local, in place.  transpose_s lays S out as [i][kcp] (kcp = kc rounded
+// up to 8, zero filled) once; rotate_basis keeps it in shared memory and streams 64-row tiles of Q
+// through a double buffer filled with 8-byte cp.async (transposed to [i][row]: conflict-free column
+// reads).  Warp w owns output columns 8w .. 8w+7, each lane two rows of the tile: per inner step
+// 2 shared loads of Q + 4 broadcast LDS.128 of S feed 16 DFMA, so the loop runs at the SM's fp64
+// rate rather than its shared-memory rate.  blockDim = 32 * kcp / 8.
 constexpr int RB_ROWS = 64;
 constexpr int RB_QP = RB_ROWS + 1;
-__global__ void __launch_bounds__(256) rotate_basis(double* __restrict__ Q, int ld, i64 rows, const double* __restrict__ S,
-                                                    int m, int kc, double* __restrict__ out, int ldo,
+
+__global__ void transpose_s(const double* __restrict__ S, int m, int kc, int kcp, double* __restrict__ St) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= m * kcp) return;
+  const int i = idx / kcp, c = idx - i * kcp;
+  St[idx] = (c < kc) ? S[(size_t)c * m + i] : 0.0;
+}
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__global__ void __launch_bounds__(512) rotate_basis(double* __restrict__ Q, int ld, i64 rows, const double* __restrict__ St,
+                                                    int m, int kc, int nbuf, double* __restrict__ out, int ldo,
                                                     const double* __restrict__ colscale) {
   extern __shared__ __align__(16) double sm[];
   const int kcp = (kc + 7) & ~7;
-  double* Ssm = sm;                          // [m][kcp]
-  double* Qs = sm + (size_t)m * kcp;         // [m][RB_QP]
-  for (int idx = threadIdx.x; idx < m * kcp; idx += blockDim.x) {
-    const int i = idx / kcp, c = idx - i * kcp;
-    Ssm[idx] = (c < kc) ? S[(size_t)c * m + i] : 0.0;
-  }
+  double* Ssm = sm;                   // [m][kcp]
+  double* Qs = sm + (size_t)m * kcp;  // [nbuf][m][RB_QP]
+  const size_t qstride = (size_t)m * RB_QP;
+  for (int idx = threadIdx.x; idx < m * kcp; idx += blockDim.x) Ssm[idx] = St[idx];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int row = (warp & 1) * 32 + lane, cg = warp >> 1;
-  const int nchunks = kcp >> 3;
   const i64 ntiles = (rows + RB_ROWS - 1) / RB_ROWS;
-  for (i64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
+  auto fetch = [&](i64 t, int buf) {
     const i64 row0 = t * RB_ROWS;
-    __syncthreads();  // previous tile fully consumed (and Ssm written, first time round)
+    double* dst = Qs + buf * qstride;
     for (int idx = threadIdx.x; idx < RB_ROWS * m; idx += blockDim.x) {
       const int r = idx / m, i = idx - r * m;
-      Qs[(size_t)i * RB_QP + r] = (row0 + r < rows) ? Q[(size_t)(row0 + r) * ld + i] : 0.0;
+      if (row0 + r < rows) cp_async8(dst + (size_t)i * RB_QP + r, Q + (size_t)(row0 + r) * ld + i);
     }
-    __syncthreads();
-    const bool live = row0 + row < rows;
-    for (int ch = cg; ch < nchunks; ch += 4) {
-      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      const double* sp = Ssm + ch * 8;
-      const double* qp = Qs + row;
-#pragma unroll 4
-      for (int i = 0; i < m; ++i) {
-        const double x = qp[(size_t)i * RB_QP];
-        const double2 s0 = *reinterpret_cast<const double2*>(sp + (size_t)i * kcp);
-        const double2 s1 = *reinterpret_cast<const double2*>(sp + (size_t)i * kcp + 2);
-        const double2 s2 = *reinterpret_cast<const double2*>(sp + (size_t)i * kcp + 4);
-        const double2 s3 = *reinterpret_cast<const double2*>(sp + (size_t)i * kcp + 6);
-        acc[0] = fma(x, s0.x, acc[0]);
-        acc[1] = fma(x, s0.y, acc[1]);
-        acc[2] = fma(x, s1.x, acc[2]);
-        acc[3] = fma(x, s1.y, acc[3]);
-        acc[4] = fma(x, s2.x, acc[4]);
-        acc[5] = fma(x, s2.y, acc[5]);
-        acc[6] = fma(x, s3.x, acc[6]);
-        acc[7] = fma(x, s3.y, acc[7]);
-      }
-      if (live) {
-        double* dst = out ? out + (size_t)(row0 + row) * ldo : Q + (size_t)(row0 + row) * ld;
+    cp_async_commit();
+  };
+  int buf = 0;
+  if ((i64)blockIdx.x < ntiles) fetch(blockIdx.x, 0);
+  for (i64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    cp_async_wait_all();
+    __syncthreads();  // tile t landed (and Ssm written); everybody is done with the other buffer
+    const i64 tn = t + gridDim.x;
+    if (nbuf == 2 && tn < ntiles) fetch(tn, buf ^ 1);
+    const i64 row0 = t * RB_ROWS;
+    const double* qp = Qs + buf * qstride + lane;
+    const double* sp = Ssm + warp * 8;
+    double a0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 2
+    for (int i = 0; i < m; ++i) {
+      const double x0 = qp[(size_t)i * RB_QP], x1 = qp[(size_t)i * RB_QP + 32];
+      const double2 s0 = *reinterpret_cast<const double2*>(sp + (size_t)i * kcp);
+      const double2 s1 = *reinterpret_cast<const double2*>(sp + (size_t)i * kcp + 2);
+      const double2 s2 = *reinterpret_cast<const double2*>(sp + (size_t)i * kcp + 4);
+      const double2 s3 = *reinterpret_cast<const double2*>(sp + (size_t)i * kcp + 6);
+      a0[0] = fma(x0, s0.x, a0[0]);
+      a0[1] = fma(x0, s0.y, a0[1]);
+      a0[2] = fma(x0, s1.x, a0[2]);
+      a0[3] = fma(x0, s1.y, a0[3]);
+      a0[4] = fma(x0, s2.x, a0[4]);
+      a0[5] = fma(x0, s2.y, a0[5]);
+      a0[6] = fma(x0, s3.x, a0[6]);
+      a0[7] = fma(x0, s3.y, a0[7]);
+      a1[0] = fma(x1, s0.x, a1[0]);
+      a1[1] = fma(x1, s0.y, a1[1]);
+      a1[2] = fma(x1, s1.x, a1[2]);
+      a1[3] = fma(x1, s1.y, a1[3]);
+      a1[4] = fma(x1, s2.x, a1[4]);
+      a1[5] = fma(x1, s2.y, a1[5]);
+      a1[6] = fma(x1, s3.x, a1[6]);
+      a1[7] = fma(x1, s3.y, a1[7]);
+    }
+    if (nbuf == 1) {
+      __syncthreads();  // single buffer: everybody is done reading before it is refilled
+      if (tn < ntiles) fetch(tn, 0);
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const i64 r = row0 + lane + 32 * half;
+      if (r < rows) {
+        double* dst = out ? out + (size_t)r * ldo : Q + (size_t)r * ld;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          const int col = ch * 8 + c;
-          if (col < kc) dst[col] = colscale ? acc[c] * colscale[col] : acc[c];
+          const int col = warp * 8 + c;
+          const double v = half ? a1[c] : a0[c];
+          if (col < kc) dst[col] = colscale ? v * colscale[col] : v;
         }
       }
     }
+    if (nbuf == 2) buf ^= 1;
   }
+  cp_async_wait_all();
 }
 
 // ---- V[:,k] = F ; B = diag(sv[:k]) + R[:k] in column k  (irlb.py:239-244) ------------------------
@@ -675,7 +715,7 @@ struct IrlbWs {
   i64 sig_n = -1;
   int sig_i[5] = {};
   double sig_tol = 0;
-  DevBuf<double> V, W, B, sc, tbuf, ybuf_h, ybuf_n, fbuf, xs, wcur, cvec, partials, Su, Sv, svd_s, R, murs;
+  DevBuf<double> V, W, B, sc, tbuf, ybuf_h, ybuf_n, fbuf, xs, wcur, cvec, partials, Su, Sv, svd_s, R, murs, St;
   DevBuf<unsigned> counter;
   DevBuf<int> info;
   std::map<int, cudaGraphExec_t> graphs;
@@ -768,8 +808,21 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   const size_t svd_smem = sizeof(double) * ((size_t)(m_b + 1) * JL * jacobi_rows_per_lane(m_b) + 260);
   jacobi_fn jacobi = jacobi_for(m_b);
   CUDA_CHECK(cudaFuncSetAttribute(jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem));
-  const size_t rot_smem = sizeof(double) * ((size_t)m_b * ((m_b + 7) & ~7) + (size_t)m_b * RB_QP);
+  // rotate_basis: S tile + one or two Q tiles in shared memory (two when they fit in 227 KB)
+  const size_t rot_s = sizeof(double) * (size_t)m_b * ((m_b + 7) & ~7), rot_q = sizeof(double) * (size_t)m_b * RB_QP;
+  const int rot_nbuf = (rot_s + 2 * rot_q <= 225 * 1024) ? 2 : 1;
+  const size_t rot_smem = rot_s + rot_nbuf * rot_q;
   CUDA_CHECK(cudaFuncSetAttribute(rotate_basis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rot_smem));
+  ws.St.ensure((size_t)MAXB * MAXB);
+  DevBuf<double>& St = ws.St;
+  // Qm[:, :kc] (or out) = Qm[:, :m_b] S[:, :kc]
+  auto rotate = [&](double* Qm, i64 nrows, const double* Smat, int kc, double* outp, int ldo, const double* scale) {
+    const int kcp = (kc + 7) & ~7;
+    LAUNCH(c, "transpose_s", (transpose_s<<<(m_b * kcp + 255) / 256, 256, 0, st>>>(Smat, m_b, kc, kcp, St.p)));
+    WORK(c, 8.0 * nrows * (m_b + kc));
+    LAUNCH(c, "rotate_basis", (rotate_basis<<<row_blocks(c, nrows), 32 * (kcp / 8), rot_smem, st>>>(
+                                  Qm, ld, nrows, St.p, m_b, kc, rot_nbuf, outp, ldo, scale)));
+  };
 
   const unsigned fin_h = (unsigned)((h + 255) / 256), fin_n = (unsigned)std::max<i64>(1, (n + 255) / 256);
   int* h_info = (int*)c->pinned;
@@ -796,13 +849,10 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   };
   // restart update (irlb.py:238-246): Ritz vectors into the leading k columns, V[:,k] = F, new B
   auto restart_update = [&](int k) {
-    LAUNCH(c, "rotate_basis", (rotate_basis<<<row_blocks(c, h), 256, rot_smem, st>>>(V.p, ld, h, Sv.p, m_b, k, nullptr, 0,
-                                                                                 nullptr)));
+    rotate(V.p, h, Sv.p, k, nullptr, 0, nullptr);
     LAUNCH(c, "set_restart", (set_restart<<<(std::max(h, m_b * m_b) + 255) / 256, 256, 0, st>>>(V.p, ld, h, fbuf.p, B.p,
                                                                                             m_b, k, svd_s.p, R.p)));
-    WORK(c, 8.0 * n * (m_b + k));
-    LAUNCH(c, "rotate_basis", (rotate_basis<<<row_blocks(c, n), 256, rot_smem, st>>>(W.p, ld, n, Su.p, m_b, k, nullptr, 0,
-                                                                                 nullptr)));
+    rotate(W.p, n, Su.p, k, nullptr, 0, nullptr);
   };
   // one outer iteration (irlb.py:155-231) up to the convergence read-back
   auto enqueue_iteration = [&](bool first, int k) {
@@ -884,10 +934,8 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   outU.ensure((size_t)std::max<i64>(n, 1) * nu);
   outV.ensure((size_t)h * nu);
   outS.ensure((size_t)nu);
-  LAUNCH(c, "rotate_basis", (rotate_basis<<<row_blocks(c, n), 256, rot_smem, st>>>(W.p, ld, n, Su.p, m_b, nu, outU.p, nu,
-                                                                               var_weigh ? svd_s.p : nullptr)));
-  LAUNCH(c, "rotate_basis", (rotate_basis<<<row_blocks(c, h), 256, rot_smem, st>>>(V.p, ld, h, Sv.p, m_b, nu, outV.p, nu,
-                                                                               nullptr)));
+  rotate(W.p, n, Su.p, nu, outU.p, nu, var_weigh ? svd_s.p : nullptr);
+  rotate(V.p, h, Sv.p, nu, outV.p, nu, nullptr);
   CUDA_CHECK(cudaMemcpyAsync(outS.p, svd_s.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));
   CUDA_CHECK(cudaStreamSynchronize(st));
   res.steps = it;
