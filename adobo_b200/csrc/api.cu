@@ -345,6 +345,9 @@ void adobo_ctx_destroy(adobo_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  // graphs that captured NCCL kernels must be gone before the communicator is destroyed
+  if (c->irlb_ws && c->irlb_ws_free) c->irlb_ws_free(c->irlb_ws);
+  c->irlb_ws = nullptr;
   if (c->comm) {
     if (c->comm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm->comm);
     delete c->comm;
@@ -356,7 +359,6 @@ void adobo_ctx_destroy(adobo_ctx* c) {
     cudaEventDestroy(pe.b);
   }
   for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
-  if (c->irlb_ws && c->irlb_ws_free) c->irlb_ws_free(c->irlb_ws);
   if (c->pinned) cudaFreeHost(c->pinned);
   cudaStream_t st = c->stream;
   delete c;

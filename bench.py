@@ -285,6 +285,8 @@ def main():
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
+    eng.close()                                          # graphs + NCCL communicator go before torch's group
+    if dist is not None:
         dist.destroy_process_group()
 
 
