@@ -14,61 +14,17 @@
 //   3. knn_exact_rows fp64 brute force for flagged queries only (duplicates / massive ties).
 // There is no approximate result: a query is either certified or recomputed exactly.
 #include <cfloat>
+#include <cstdlib>
 #include <climits>
 
 #include "common.cuh"
+#include "knn_common.cuh"
 
 namespace adobo {
 
 constexpr int QT = 64;    // queries per CTA
 constexpr int RT = 128;   // references per shared-memory tile
 constexpr int MAXP = 128; // embedding dimensions supported
-
-struct Cand {
-  float key;
-  int idx;
-};
-__device__ __forceinline__ bool cand_less(float ka, int ia, float kb, int ib) {
-  return ka < kb || (ka == kb && ia < ib);
-}
-__device__ __forceinline__ bool cand_less(double ka, int ia, double kb, int ib) {
-  return ka < kb || (ka == kb && ia < ib);
-}
-
-// Sorted list of 32*E (key, idx) held E per lane (lane l owns global slots l*E .. l*E+E-1).
-template <typename KT, int E>
-__device__ __forceinline__ void list_insert(KT (&key)[E], int (&idx)[E], KT nk, int ni, int lane) {
-  // skip when not better than the current worst
-  const KT wk = __shfl_sync(0xffffffffu, key[E - 1], 31);
-  const int wi = __shfl_sync(0xffffffffu, idx[E - 1], 31);
-  if (!cand_less(nk, ni, wk, wi)) return;
-  int less = 0;
-#pragma unroll
-  for (int e = 0; e < E; ++e) less += cand_less(key[e], idx[e], nk, ni) ? 1 : 0;
-  const int pos = __reduce_add_sync(0xffffffffu, less);
-  KT pk = __shfl_up_sync(0xffffffffu, key[E - 1], 1);
-  int pi = __shfl_up_sync(0xffffffffu, idx[E - 1], 1);
-  KT ok[E];
-  int oi[E];
-#pragma unroll
-  for (int e = 0; e < E; ++e) {
-    ok[e] = key[e];
-    oi[e] = idx[e];
-  }
-#pragma unroll
-  for (int e = 0; e < E; ++e) {
-    const int gi = lane * E + e;
-    const KT prevk = (e == 0) ? pk : ok[e - 1];
-    const int previ = (e == 0) ? pi : oi[e - 1];
-    if (gi == pos) {
-      key[e] = nk;
-      idx[e] = ni;
-    } else if (gi > pos) {
-      key[e] = prevk;
-      idx[e] = previ;
-    }
-  }
-}
 
 // ---- preparation ------------------------------------------------------------------------------
 // centre = column mean of the first `m` rows (any fixed vector works; it only tightens eps)
@@ -265,7 +221,7 @@ template <int E>
 __global__ void __launch_bounds__(256) knn_rerank(const double* __restrict__ x, int p, const float* __restrict__ sk,
                                                   const int* __restrict__ si, const float* __restrict__ norms,
                                                   const unsigned* __restrict__ maxnorm_bits, i64 q_begin, i64 nq,
-                                                  int k, i64* __restrict__ out1, int* __restrict__ nn0,
+                                                  i64 n, int k, i64* __restrict__ out1, int* __restrict__ nn0,
                                                   int* __restrict__ flagged, int* __restrict__ nflag) {
   constexpr int KP = 32 * E;
   const int lane = threadIdx.x & 31;
@@ -278,6 +234,7 @@ __global__ void __launch_bounds__(256) knn_rerank(const double* __restrict__ x, 
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       id[e] = si[(size_t)ql * KP + lane * E + e];
+      if (id[e] >= n) id[e] = INT_MAX;  // padding rows of the last reference tile (only when n < KP)
       if (id[e] == INT_MAX) {
         d[e] = INFINITY;
       } else {
@@ -296,7 +253,7 @@ __global__ void __launch_bounds__(256) knn_rerank(const double* __restrict__ x, 
     const float lastkey = __shfl_sync(0xffffffffu, sk[(size_t)ql * KP + 31 * E + (E - 1)], 0);
     const double qn = (double)norms[q];
     const double T32 = (double)lastkey + qn;
-    const double eps = (2.0 * p + 16.0) * 5.9604644775390625e-08 * (qn + (double)__uint_as_float(*maxnorm_bits));
+    const double eps = (3.0 * p + 16.0) * 5.9604644775390625e-08 * (qn + (double)__uint_as_float(*maxnorm_bits));
     const bool ok = (lastkey == INFINITY) || (kth < T32 - eps);
     if (!ok && lane == 0) flagged[atomicAdd(nflag, 1)] = (int)ql;
   }
@@ -367,6 +324,10 @@ __global__ void __launch_bounds__(256) knn_exact_rows(const double* __restrict__
   }
 }
 
+bool knn_tc_supported(int p);  // knn_tc.cu
+void run_knn_shortlist_tc(adobo_ctx* c, const double* x, i64 n, int p, const double* ctr, i64 q_begin, i64 q_end, int E,
+                          float* skey, int* sidx, DevBuf<float>& norms, unsigned* maxnorm);
+
 // comp_local: this rank's rows (n_local x p, device, fp64).  Leaves c->nn (n_local x k, 0-based global ids).
 void run_knn(adobo_ctx* c, const double* comp_local, i64 n_local, int p, int k) {
   REQUIRE(p >= 1 && p <= MAXP, ADOBO_ERR_LIMIT, "knn: %d dimensions (supported: 1..%d)", p, MAXP);
@@ -400,14 +361,13 @@ void run_knn(adobo_ctx* c, const double* comp_local, i64 n_local, int p, int k) 
   DevBuf<float> refT, norms, skey;
   DevBuf<int> sidx, flagged, nflag;
   DevBuf<unsigned> maxnorm;
+  // The shortlist comes from the tcgen05 kernel (knn_tc.cu) whenever its resident A' operand fits in
+  // shared memory (p <= 126); wider embeddings use the CUDA-core tile kernel above.
+  const bool use_tc = knn_tc_supported(p) && getenv("ADOBO_B200_KNN_SIMT") == nullptr;
   ctr.ensure(MAXP);
-  refT.ensure((size_t)npad * P);
-  norms.ensure((size_t)npad);
   maxnorm.ensure(1);
   CUDA_CHECK(cudaMemsetAsync(maxnorm.p, 0, sizeof(unsigned), st));
   LAUNCH(c, "knn_center", (knn_center<<<1, 1024, 0, st>>>(x, std::min<i64>(n, 4096), p, ctr.p)));
-  LAUNCH(c, "knn_prep", (knn_prep<<<(unsigned)((npad + 127) / 128), 128, 0, st>>>(x, n, npad, p, P, ctr.p, refT.p,
-                                                                               norms.p, maxnorm.p)));
   skey.ensure((size_t)std::max<i64>(n_local, 1) * KP);
   sidx.ensure((size_t)std::max<i64>(n_local, 1) * KP);
   const i64 q_end = q_begin + n_local;
@@ -415,19 +375,26 @@ void run_knn(adobo_ctx* c, const double* comp_local, i64 n_local, int p, int k) 
   c->k = k;
   c->knn_n = n_local;
   if (n_local > 0) {
-    const i64 qt0 = q_begin / QT, qt1 = (q_end + QT - 1) / QT;
-    const size_t smem = sizeof(float) * ((size_t)P * RT + (size_t)P * QT + RT + QT) + sizeof(int) * QT +
-                        sizeof(Cand) * ((size_t)QT * RT + (size_t)QT * KP);
-    WORK(c, 2.0 * (double)(qt1 - qt0) * QT * (double)npad * P);  // flops
-    if (E == 1) {
-      CUDA_CHECK(cudaFuncSetAttribute(knn_shortlist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      LAUNCH(c, "knn_shortlist", (knn_shortlist<1><<<(unsigned)(qt1 - qt0), 256, smem, st>>>(
-                                     refT.p, norms.p, npad, P, qt0, skey.p, sidx.p, q_begin, q_end)));
+    if (use_tc) {
+      run_knn_shortlist_tc(c, x, n, p, ctr.p, q_begin, q_end, E, skey.p, sidx.p, norms, maxnorm.p);
     } else {
-      WORK(c, 2.0 * (double)(qt1 - qt0) * QT * (double)npad * P);
-      CUDA_CHECK(cudaFuncSetAttribute(knn_shortlist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      LAUNCH(c, "knn_shortlist", (knn_shortlist<2><<<(unsigned)(qt1 - qt0), 256, smem, st>>>(
-                                     refT.p, norms.p, npad, P, qt0, skey.p, sidx.p, q_begin, q_end)));
+      refT.ensure((size_t)npad * P);
+      norms.ensure((size_t)npad);
+      LAUNCH(c, "knn_prep", (knn_prep<<<(unsigned)((npad + 127) / 128), 128, 0, st>>>(x, n, npad, p, P, ctr.p, refT.p,
+                                                                                   norms.p, maxnorm.p)));
+      const i64 qt0 = q_begin / QT, qt1 = (q_end + QT - 1) / QT;
+      const size_t smem = sizeof(float) * ((size_t)P * RT + (size_t)P * QT + RT + QT) + sizeof(int) * QT +
+                          sizeof(Cand) * ((size_t)QT * RT + (size_t)QT * KP);
+      WORK(c, 2.0 * (double)(qt1 - qt0) * QT * (double)npad * P);  // flops
+      if (E == 1) {
+        CUDA_CHECK(cudaFuncSetAttribute(knn_shortlist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LAUNCH(c, "knn_shortlist", (knn_shortlist<1><<<(unsigned)(qt1 - qt0), 256, smem, st>>>(
+                                       refT.p, norms.p, npad, P, qt0, skey.p, sidx.p, q_begin, q_end)));
+      } else {
+        CUDA_CHECK(cudaFuncSetAttribute(knn_shortlist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LAUNCH(c, "knn_shortlist", (knn_shortlist<2><<<(unsigned)(qt1 - qt0), 256, smem, st>>>(
+                                       refT.p, norms.p, npad, P, qt0, skey.p, sidx.p, q_begin, q_end)));
+      }
     }
     flagged.ensure((size_t)n_local);
     nflag.ensure(1);
@@ -435,13 +402,14 @@ void run_knn(adobo_ctx* c, const double* comp_local, i64 n_local, int p, int k) 
     const unsigned rb = (unsigned)std::min<i64>((n_local + 7) / 8, (i64)c->sm_count * 8);
     if (E == 1)
       LAUNCH(c, "knn_rerank", (knn_rerank<1><<<rb, 256, 0, st>>>(x, p, skey.p, sidx.p, norms.p, maxnorm.p, q_begin,
-                                                               n_local, k, nullptr, c->nn.p, flagged.p, nflag.p)));
+                                                               n_local, n, k, nullptr, c->nn.p, flagged.p, nflag.p)));
     else
       LAUNCH(c, "knn_rerank", (knn_rerank<2><<<rb, 256, 0, st>>>(x, p, skey.p, sidx.p, norms.p, maxnorm.p, q_begin,
-                                                               n_local, k, nullptr, c->nn.p, flagged.p, nflag.p)));
+                                                               n_local, n, k, nullptr, c->nn.p, flagged.p, nflag.p)));
     int nf = 0;
     CUDA_CHECK(cudaMemcpyAsync(&nf, nflag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
+    if (getenv("ADOBO_B200_DEBUG")) fprintf(stderr, "[adobo_b200] knn: %d of %lld queries failed the fp32 certificate\n", nf, (long long)n_local);
     if (nf > 0)
       LAUNCH(c, "knn_exact_rows",
              (knn_exact_rows<<<(unsigned)nf, 256, 0, st>>>(x, n, p, flagged.p, q_begin, k, nullptr, c->nn.p)));

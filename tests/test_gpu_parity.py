@@ -206,3 +206,16 @@ def test_api_drop_in(eng):
         ad.hvg.find_hvg(ad.data.dataset.from_csr(case['counts_csr']))
     with pytest.raises(ValueError):
         ad.dr.pca(exp, genes=5)
+
+
+def test_knn_blobs_30k_tensor_core_path(eng):
+    """C5-shaped input (Gaussian blobs, 50 dims) at 30,000 points: many reference tiles per query tile,
+    exercising the TMA ring / TMEM double buffer of the tcgen05 shortlist; exact vs the oracle."""
+    from oracle import adobo_oracle as O
+    from adobo_b200.synth import synth_embedding
+    x = synth_embedding(30000, 50, seed=5)
+    for k in (10, 30):
+        nn = eng.knn(x, k)
+        ref = O.knn(x, k, block=512)
+        P.assert_knn_equal(nn, ref, x)
+        assert np.array_equal(nn[:, 0], np.arange(1, 30001))
