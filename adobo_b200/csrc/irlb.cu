@@ -320,6 +320,10 @@ __device__ __forceinline__ int jacobi_rotate2(double2 (&x0)[H], double2 (&y0)[H]
     ga += __shfl_xor_sync(0xffffffffu, ga, o);
     gb += __shfl_xor_sync(0xffffffffu, gb, o);
   }
+  // late sweeps: most pairs are already orthogonal -- when no pair of this warp needs a rotation the
+  // whole warp skips the angle / update / store work (warp-uniform branch, no divergence)
+  const bool need = (ga * ga > 1e-30 * (nx0 * ny0)) || (gb * gb > 1e-30 * (nx1 * ny1));
+  if (!__any_sync(0xffffffffu, need)) return 0;
   double ca, sa, cb, sb;
   const int fa = jacobi_angle(ga, nx0, ny0, ca, sa);
   const int fb = jacobi_angle(gb, nx1, ny1, cb, sb);
@@ -455,14 +459,14 @@ __global__ void __launch_bounds__(JTHREADS, 1) jacobi_svd(const double* __restri
         for (int r = 0; r < H; ++r) {
           a0[r] = a0p[JL * r];
           a1[r] = a1p[JL * r];
-          b0[r] = b0p[JL * r];
-          b1[r] = b1p[JL * r];
+          b0[r] = act ? b0p[JL * r] : make_double2(0.0, 0.0);  // idle groups rotate against zeros: no-op
+          b1[r] = act ? b1p[JL * r] : make_double2(0.0, 0.0);
         }
         double na0 = nrm[2 * P], na1 = nrm[2 * P + 1], nb0 = nrm[2 * Qs], nb1 = nrm[2 * Qs + 1];
         if (!act) nb0 = nb1 = 0.0;  // zero norm -> no rotation
         int f = jacobi_rotate2<H>(a0, b0, na0, nb0, a1, b1, na1, nb1);
         f |= jacobi_rotate2<H>(a0, b1, na0, nb1, a1, b0, na1, nb0);
-        if (act) {
+        if (act && f) {
 #pragma unroll
           for (int r = 0; r < H; ++r) {
             a0p[JL * r] = a0[r];
