@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libadobo_b200.so')
-SOURCES = ['api.cu', 'normalize.cu', 'moments.cu', 'gather.cu', 'irlb.cu', 'knn.cu', 'knn_tc.cu', 'snn.cu']
+SOURCES = ['api.cu', 'normalize.cu', 'moments.cu', 'gather.cu', 'irlb.cu', 'svd_arrow.cu', 'knn.cu', 'knn_tc.cu', 'snn.cu']
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr',
          '-Xptxas', '-v']

@@ -188,7 +188,7 @@ void run_seurat_host(adobo_ctx* c, int ngenes, int num_bins, std::vector<int>& o
 void run_gather_subset(adobo_ctx* c, const std::vector<int>& genes_sorted, bool scale);
 
 struct IrlbResult {
-  int steps = 0, nmult = 0;
+  int steps = 0, nmult = 0, svd_fallbacks = 0;
 };
 // generic driver on a SparsePair; mu/rs may be null (no centring / scaling)
 template <typename VT>

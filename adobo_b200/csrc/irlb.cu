@@ -19,6 +19,11 @@
 
 namespace adobo {
 
+// svd_arrow.cu: structured SVD of the restarted B (diag + spike + bidiagonal tail)
+bool svd_arrow_supported(int m, int k);
+void svd_arrow_prepare(int m);
+void launch_svd_arrow(adobo_ctx* c, const double* B, int m, int k, double* Su, double* sv, double* Sv, int* info);
+
 enum { SC_S = 0, SC_FN, SC_FNINV, SC_SU, SC_MVS, SC_SMAX, SC_NRM2, SC_AUX, SC_COUNT = 16 };
 constexpr int MAXB = 128;  // widest basis the dot kernels handle (4 columns per lane)
 constexpr double EPS2 = 2.0 * 2.220446049250313e-16;
@@ -552,8 +557,16 @@ static jacobi_fn jacobi_for(int m) {
 
 // ---- residuals, convergence count and the next k (irlb.py:225-234) ------------------------------
 __global__ void conv_check(const double* __restrict__ Su, const double* __restrict__ sv, double* __restrict__ sc,
-                           int m, int nu, int k, int it, double tol, double* __restrict__ R, int* __restrict__ info) {
+                           int m, int nu, int k, int it, double tol, double* __restrict__ R, int* __restrict__ info,
+                           int honour_flag) {
   __shared__ int cnt;
+  if (honour_flag && info[3] == 0) {  // svd_arrow rejected its own result: the host re-runs jacobi_svd
+    if (threadIdx.x == 0) {
+      info[0] = -1;
+      info[1] = k;
+    }
+    return;
+  }
   if (threadIdx.x == 0) cnt = 0;
   __syncthreads();
   const double fn = sc[SC_FN];
@@ -807,6 +820,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   CUDA_CHECK(cudaMemsetAsync(sc.p, 0, sizeof(double) * SC_COUNT, st));
   CUDA_CHECK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned), st));
   CUDA_CHECK(cudaMemsetAsync(cvec.p, 0, sizeof(double) * MAXB, st));
+  CUDA_CHECK(cudaMemsetAsync(info.p, 0, sizeof(int) * 4, st));
   if (centered) LAUNCH(c, "mul_vec", (mul_vec<<<(h + 255) / 256, 256, 0, st>>>(mu, rs, murs.p, h)));
   // SVD kernel resources
   const size_t svd_smem = sizeof(double) * ((size_t)(m_b + 1) * JL * jacobi_rows_per_lane(m_b) + 260);
@@ -828,6 +842,9 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
                                   Qm, ld, nrows, St.p, m_b, kc, rot_nbuf, outp, ldo, scale)));
   };
 
+  const bool use_arrow = getenv("ADOBO_B200_SVD_JACOBI") == nullptr;
+  const bool force_fallback = getenv("ADOBO_B200_SVD_FORCE_FALLBACK") != nullptr;  // test hook
+  if (use_arrow) svd_arrow_prepare(m_b);
   const unsigned fin_h = (unsigned)((h + 255) / 256), fin_n = (unsigned)std::max<i64>(1, (n + 255) / 256);
   int* h_info = (int*)c->pinned;
 
@@ -879,9 +896,24 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
       if (j < m_b - 1) w_column(j, j + 1, j + 1);
       ++j;
     }
-    LAUNCH(c, "jacobi_svd", (jacobi<<<1, JTHREADS, svd_smem, st>>>(B.p, m_b, Su.p, svd_s.p, Sv.p, info.p)));
-    LAUNCH(c, "conv_check", (conv_check<<<1, 128, 0, st>>>(Su.p, svd_s.p, sc.p, m_b, nu, k, first ? 0 : 1, tol, R.p, info.p)));
+    // SVD of B (irlb.py:224): restarts have the diag + spike + bidiagonal-tail structure (svd_arrow),
+    // the first iteration is a plain bidiagonal matrix (Jacobi)
+    const bool arrow = !first && use_arrow && svd_arrow_supported(m_b, k);
+    if (arrow)
+      launch_svd_arrow(c, B.p, m_b, k, Su.p, svd_s.p, Sv.p, info.p);
+    else
+      LAUNCH(c, "jacobi_svd", (jacobi<<<1, JTHREADS, svd_smem, st>>>(B.p, m_b, Su.p, svd_s.p, Sv.p, info.p)));
+    LAUNCH(c, "conv_check", (conv_check<<<1, 128, 0, st>>>(Su.p, svd_s.p, sc.p, m_b, nu, k, first ? 0 : 1, tol, R.p,
+                                                         info.p, arrow ? 1 : 0)));
     CUDA_CHECK(cudaMemcpyAsync(h_info, info.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+  };
+  // fallback when svd_arrow rejected its own result: generic Jacobi SVD of the same B
+  auto svd_fallback = [&](bool first, int k) {
+    LAUNCH(c, "jacobi_svd", (jacobi<<<1, JTHREADS, svd_smem, st>>>(B.p, m_b, Su.p, svd_s.p, Sv.p, info.p)));
+    LAUNCH(c, "conv_check", (conv_check<<<1, 128, 0, st>>>(Su.p, svd_s.p, sc.p, m_b, nu, k, first ? 0 : 1, tol, R.p,
+                                                         info.p, 0)));
+    CUDA_CHECK(cudaMemcpyAsync(h_info, info.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
   };
   const bool use_graphs = !c->profiling && getenv("ADOBO_B200_NO_GRAPH") == nullptr;
   auto run_iteration = [&](bool first, int k) {
@@ -925,6 +957,10 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     run_iteration(it == 0, k);
     nmult += 2 * (m_b - (it == 0 ? 0 : k));  // 1 + sum over j of (1 + [j < m_b-1]) mat-vecs
     CUDA_CHECK(cudaStreamSynchronize(st));
+    if (h_info[0] < 0 || (force_fallback && it > 0)) {  // structured SVD failed its self-check (kept for safety)
+      svd_fallback(it == 0, k);
+      ++res.svd_fallbacks;
+    }
     if (h_info[0] >= nu) {  // irlb.py:232-236
       converged = true;
       break;
@@ -944,6 +980,8 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   CUDA_CHECK(cudaStreamSynchronize(st));
   res.steps = it;
   res.nmult = nmult;
+  if (getenv("ADOBO_B200_DEBUG"))
+    fprintf(stderr, "[adobo_b200] irlb: %d restarts, %d mat-vecs, %d structured-SVD fallbacks\n", it, nmult, res.svd_fallbacks);
   return res;
 }
 

@@ -219,3 +219,19 @@ def test_knn_blobs_30k_tensor_core_path(eng):
         ref = O.knn(x, k, block=512)
         P.assert_knn_equal(nn, ref, x)
         assert np.array_equal(nn[:, 0], np.arange(1, 30001))
+
+
+@pytest.mark.parametrize('env', ['ADOBO_B200_SVD_JACOBI', 'ADOBO_B200_SVD_FORCE_FALLBACK', 'ADOBO_B200_NO_GRAPH'])
+def test_irlb_alternative_svd_paths(eng, env, monkeypatch):
+    """The generic Jacobi SVD of B (first iteration / fallback of the structured solver) and the
+    non-graph launch path must give the same PCA as the default path."""
+    case = P.load_case('medium')
+    eng.upload_normalized(case['norm_csr'])
+    base = eng.irlb(case['hvg_ordered'], ncomp=case['ncomp'], seed=42)
+    monkeypatch.setenv(env, '1')
+    eng.upload_normalized(case['norm_csr'])
+    alt = eng.irlb(case['hvg_ordered'], ncomp=case['ncomp'], seed=42)
+    ex_comp, ex_contr, _ = P.exact_pca(case['norm_csr'], case['hvg_ordered'], case['ncomp'])
+    P.assert_pca_close(alt['comp'], alt['contr'], case['comp'], case['contr'], ex_comp, ex_contr)
+    np.testing.assert_allclose(alt['s'], base['s'], rtol=1e-9)
+    assert np.max(P.component_err(alt['comp'], base['comp'])[:case['ncomp'] - 8]) < 1e-6
