@@ -442,6 +442,7 @@ void svd_arrow_prepare(int m) {
 }
 
 void launch_svd_arrow(adobo_ctx* c, const double* B, int m, int k, double* Su, double* sv, double* Sv, int* info) {
+  WORK(c, 24.0 * m * m);
   LAUNCH(c, "svd_arrow", (svd_arrow<<<1, SA_THREADS, svd_arrow_smem(m), c->stream>>>(B, m, k, Su, sv, Sv, info)));
 }
 
