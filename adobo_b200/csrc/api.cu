@@ -6,6 +6,7 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <climits>
 #include <mutex>
 #include <numeric>
@@ -222,6 +223,45 @@ static void prof_collect(adobo_ctx* c) {
   c->pending.clear();
 }
 
+// Mailboxes of the fused all-reduce: one cudaMalloc per rank, handles exchanged over NCCL, peers mapped
+// with CUDA IPC (one process per GPU on one node).
+static void setup_peer(adobo_ctx* c) {
+  const int W = c->world;
+  const size_t data_bytes = sizeof(double) * 2 * (size_t)W * PEER_SLOT;
+  const size_t flag_bytes = sizeof(unsigned) * 2 * (size_t)W * 32;
+  const size_t bytes = data_bytes + flag_bytes + 256;
+  void* mb = nullptr;
+  CUDA_CHECK(cudaMalloc(&mb, bytes));
+  CUDA_CHECK(cudaMemset(mb, 0, bytes));
+  c->peer_mailbox = mb;
+  cudaIpcMemHandle_t mine;
+  CUDA_CHECK(cudaIpcGetMemHandle(&mine, mb));
+  DevBuf<char> hbuf;
+  hbuf.ensure(sizeof(cudaIpcMemHandle_t) * (size_t)(W + 1));
+  CUDA_CHECK(cudaMemcpyAsync(hbuf.p + sizeof(mine) * W, &mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream));
+  NCCL_CHECK(g_nccl.AllGather(hbuf.p + sizeof(mine) * W, hbuf.p, sizeof(mine), ncclChar, c->comm->comm, c->stream));
+  std::vector<cudaIpcMemHandle_t> all(W);
+  CUDA_CHECK(cudaMemcpyAsync(all.data(), hbuf.p, sizeof(mine) * W, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  PeerComm pc;
+  pc.world = W;
+  pc.rank = c->rank;
+  for (int r = 0; r < W; ++r) {
+    void* ptr = mb;
+    if (r != c->rank) CUDA_CHECK(cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess));
+    pc.data[r] = (double*)ptr;
+    pc.flags[r] = (unsigned*)((char*)ptr + data_bytes);
+  }
+  pc.seq = (unsigned*)((char*)mb + data_bytes + flag_bytes);
+  // nobody may write into a mailbox before every rank has zeroed and mapped it
+  DevBuf<double> one;
+  one.ensure(1);
+  CUDA_CHECK(cudaMemsetAsync(one.p, 0, sizeof(double), c->stream));
+  NCCL_CHECK(g_nccl.AllReduce(one.p, one.p, 1, ncclFloat64, ncclSum, c->comm->comm, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  c->peer = pc;
+}
+
 static void refresh_partition(adobo_ctx* c) {
   std::vector<i64> all;
   allgather_i64_host(c, c->n, all);
@@ -348,6 +388,12 @@ void adobo_ctx_destroy(adobo_ctx* c) {
   // graphs that captured NCCL kernels must be gone before the communicator is destroyed
   if (c->irlb_ws && c->irlb_ws_free) c->irlb_ws_free(c->irlb_ws);
   c->irlb_ws = nullptr;
+  if (c->peer_mailbox) {
+    for (int r = 0; r < c->peer.world; ++r)
+      if (r != c->peer.rank && c->peer.data[r]) cudaIpcCloseMemHandle(c->peer.data[r]);
+    cudaFree(c->peer_mailbox);
+    c->peer_mailbox = nullptr;
+  }
   if (c->comm) {
     if (c->comm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm->comm);
     delete c->comm;
@@ -396,6 +442,7 @@ int adobo_comm_init(adobo_ctx* c, int world, int rank, const void* id128) {
   }
   c->world = world;
   c->rank = rank;
+  if (world > 1 && world <= PEER_MAX && getenv("ADOBO_B200_NO_PEER") == nullptr) setup_peer(c);
   if (c->have_counts || c->have_norm) refresh_partition(c);
   API_END
 }

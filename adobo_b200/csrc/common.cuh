@@ -95,6 +95,21 @@ struct SparsePair {
 
 struct Comm;  // NCCL wrapper, api.cu
 
+// One-shot all-reduce over NVLink peer memory (api.cu sets it up with CUDA IPC when world > 1).
+// Every rank owns a mailbox data[parity][rank][PEER_SLOT] + flags[parity][rank]; a reducing kernel's
+// last CTA writes its vector into ITS slot of EVERY peer's mailbox, releases a sequence flag, waits for
+// the flags of all ranks in its own mailbox and sums the slots in rank order -- the result is bitwise
+// identical on all ranks, and the exchange is part of the kernel that produced the partial sums
+// (no separate collective launch; ~3 of these per Lanczos step replace three ncclAllReduce calls).
+constexpr int PEER_MAX = 8;
+constexpr int PEER_SLOT = 4096;  // doubles per rank slot: larger vectors go through NCCL
+struct PeerComm {
+  int world = 1, rank = 0;
+  double* data[PEER_MAX] = {};     // mailbox of every rank (peer pointers through CUDA IPC)
+  unsigned* flags[PEER_MAX] = {};  // [2][world] sequence flags, 128 bytes apart
+  unsigned* seq = nullptr;         // this rank's sequence counter (device)
+};
+
 }  // namespace adobo
 
 struct adobo_ctx {
@@ -137,6 +152,8 @@ struct adobo_ctx {
   // ---- plumbing ----
   adobo::Comm* comm = nullptr;
   int world = 1, rank = 0;
+  adobo::PeerComm peer;         // world == 1 unless the peer-memory all-reduce is set up
+  void* peer_mailbox = nullptr;
   cudaEvent_t events[64] = {};
   bool profiling = false;
   std::map<std::string, adobo::ProfItem> prof;
@@ -227,6 +244,44 @@ __device__ __forceinline__ int warp_sum(int v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// ---- fused all-reduce over peer memory: called by ALL threads of ONE CTA; vec is in global memory ----
+__device__ __forceinline__ void peer_allreduce_block(const PeerComm& pc, double* vec, int count) {
+  __shared__ unsigned s_seq;
+  const int W = pc.world, me = pc.rank;
+  if (threadIdx.x == 0) s_seq = *pc.seq + 1u;
+  __syncthreads();
+  const unsigned seq = s_seq;
+  const int par = (int)(seq & 1u);
+  // phase 1: my vector into my slot of every rank's mailbox (NVLink stores), then release the flag
+  for (int r = 0; r < W; ++r) {
+    double* dst = pc.data[r] + ((size_t)(par * W + me)) * PEER_SLOT;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = __ldcg(vec + i);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < W) {
+    unsigned* f = pc.flags[threadIdx.x] + (size_t)(par * W + me) * 32;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(seq) : "memory");
+  }
+  // phase 2: wait for every rank's contribution in MY mailbox, sum in rank order
+  if ((int)threadIdx.x < W) {
+    const unsigned* f = pc.flags[me] + (size_t)(par * W + threadIdx.x) * 32;
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    } while (v != seq);
+  }
+  __syncthreads();
+  const double* mine = pc.data[me] + (size_t)(par * W) * PEER_SLOT;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    double s = 0;
+    for (int r = 0; r < W; ++r) s += __ldcv(mine + (size_t)r * PEER_SLOT + i);
+    vec[i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *pc.seq = seq;
+}
+
 // streaming 128-bit loads/stores that do not pollute L1
 __device__ __forceinline__ int4 ld_stream(const int4* p) {
   int4 r;

@@ -36,7 +36,8 @@ constexpr int RT_WARPS = RT_THREADS / 32;
 
 // vector of nd (<= 128) sums; acc[t] is this lane's partial for column lane + 32 t
 __device__ __forceinline__ void reduce_vec_blocks(double (&acc)[4], int nd, double* __restrict__ partials,
-                                                  double* __restrict__ out, unsigned* __restrict__ counter) {
+                                                  double* __restrict__ out, unsigned* __restrict__ counter,
+                                                  const PeerComm& pc) {
   __shared__ double sh[RT_WARPS][MAXB];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -62,12 +63,17 @@ __device__ __forceinline__ void reduce_vec_blocks(double (&acc)[4], int nd, doub
       if (lane == 0) out[col] = s;
     }
     if (threadIdx.x == 0) *counter = 0;
+    if (pc.world > 1) {  // sum over ranks, fused: this CTA exchanges the vector over NVLink peer memory
+      __syncthreads();
+      peer_allreduce_block(pc, out, nd);
+    }
   }
 }
 
 // two scalars
 __device__ __forceinline__ void reduce_two_blocks(double a, double b, double* __restrict__ partials,
-                                                  double* __restrict__ out, unsigned* __restrict__ counter) {
+                                                  double* __restrict__ out, unsigned* __restrict__ counter,
+                                                  const PeerComm& pc) {
   __shared__ double sh2[RT_WARPS][2];
   __shared__ bool is_last2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -86,18 +92,24 @@ __device__ __forceinline__ void reduce_two_blocks(double a, double b, double* __
   __syncthreads();
   if (threadIdx.x == 0) is_last2 = (atomicAdd(counter, 1u) == gridDim.x - 1);
   __syncthreads();
-  if (is_last2 && warp == 0) {
-    double s0 = 0, s1 = 0;
-    for (unsigned bb = lane; bb < gridDim.x; bb += 32) {
-      s0 += __ldcg(partials + (size_t)bb * 2);
-      s1 += __ldcg(partials + (size_t)bb * 2 + 1);
+  if (is_last2) {
+    if (warp == 0) {
+      double s0 = 0, s1 = 0;
+      for (unsigned bb = lane; bb < gridDim.x; bb += 32) {
+        s0 += __ldcg(partials + (size_t)bb * 2);
+        s1 += __ldcg(partials + (size_t)bb * 2 + 1);
+      }
+      s0 = warp_sum(s0);
+      s1 = warp_sum(s1);
+      if (lane == 0) {
+        out[0] = s0;
+        out[1] = s1;
+        *counter = 0;
+      }
     }
-    s0 = warp_sum(s0);
-    s1 = warp_sum(s1);
-    if (lane == 0) {
-      out[0] = s0;
-      out[1] = s1;
-      *counter = 0;
+    if (pc.world > 1) {
+      __syncthreads();
+      peer_allreduce_block(pc, out, 2);
     }
   }
 }
@@ -106,8 +118,10 @@ __device__ __forceinline__ void reduce_two_blocks(double a, double b, double* __
 template <typename VT>
 __global__ void __launch_bounds__(256) spmvT_csc(const i64* __restrict__ cptr, const int* __restrict__ ridx,
                                                  const VT* __restrict__ cval, const double* __restrict__ u,
-                                                 double* __restrict__ t) {
+                                                 double* __restrict__ t, int h, unsigned* __restrict__ counter,
+                                                 const PeerComm pc) {
   __shared__ double red[8];
+  __shared__ bool last_cta;
   const int col = blockIdx.x;
   const i64 b = cptr[col], e1 = cptr[col + 1];
   double s = 0;
@@ -122,6 +136,17 @@ __global__ void __launch_bounds__(256) spmvT_csc(const i64* __restrict__ cptr, c
     for (int w = 0; w < 8; ++w) tt += red[w];
     t[col] = tt;
   }
+  if (pc.world > 1) {  // the last column CTA to finish sums t over ranks (fused NVLink exchange)
+    if (threadIdx.x == 0) {
+      __threadfence();
+      last_cta = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last_cta) {
+      peer_allreduce_block(pc, t, h);
+      if (threadIdx.x == 0) *counter = 0;
+    }
+  }
 }
 
 // ---- F = A_s^T w - s V[:,j]  and  c = V[:, :nd]^T F  (irlb.py:182-190, first half of orthog) ----
@@ -132,6 +157,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) v_prep_dots(const double* __res
                                                    double* __restrict__ cvec, unsigned* __restrict__ counter) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
+  const PeerComm nopeer;  // V is replicated: no exchange
   const double s = sc[SC_S], su = sc[SC_SU];
   double acc[4] = {0, 0, 0, 0};
   for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < h; r += warps) {
@@ -146,7 +172,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) v_prep_dots(const double* __res
       if (col < nd) acc[q] += vr[col] * f;
     }
   }
-  reduce_vec_blocks(acc, nd, partials, cvec, counter);
+  reduce_vec_blocks(acc, nd, partials, cvec, counter, nopeer);
 }
 
 // ---- K4  w = A_s x - fn W[:,jprev]  and  c = W[:, :nd]^T w  (irlb.py:165 / 204-216) -------------
@@ -156,7 +182,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) spmv_dots(const i64* __restrict
                                                  const double* __restrict__ sc, const double* __restrict__ W,
                                                  int ldw, int jprev, int nd, i64 n, double* __restrict__ ybuf,
                                                  double* __restrict__ partials, double* __restrict__ cvec,
-                                                 unsigned* __restrict__ counter) {
+                                                 unsigned* __restrict__ counter, const PeerComm pc) {
   const int lane = threadIdx.x & 31;
   const i64 warps = ((i64)gridDim.x * blockDim.x) >> 5;
   const double mvs = sc[SC_MVS], fn = sc[SC_FN];
@@ -177,7 +203,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) spmv_dots(const i64* __restrict
       if (col < nd) acc[q] += wr[col] * w;
     }
   }
-  if (nd > 0) reduce_vec_blocks(acc, nd, partials, cvec, counter);
+  if (nd > 0) reduce_vec_blocks(acc, nd, partials, cvec, counter, pc);
 }
 
 // ---- y -= Q[:, :nd] c ;  nrm2 = y.y ;  aux = coef.y  (second half of orthog + the norm) ---------
@@ -185,7 +211,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) update_norm(const double* __res
                                                    const double* __restrict__ cvec, double* __restrict__ ybuf,
                                                    const double* __restrict__ coef, i64 rows,
                                                    double* __restrict__ partials, double* __restrict__ out2,
-                                                   unsigned* __restrict__ counter) {
+                                                   unsigned* __restrict__ counter, const PeerComm pc) {
   const int lane = threadIdx.x & 31;
   const i64 warps = ((i64)gridDim.x * blockDim.x) >> 5;
   double creg[4];
@@ -209,7 +235,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) update_norm(const double* __res
     n2 += y * y;
     ax += (coef ? coef[r] : 1.0) * y;
   }
-  reduce_two_blocks(n2, ax, partials, out2, counter);
+  reduce_two_blocks(n2, ax, partials, out2, counter, pc);
 }
 
 // ---- normalise F, store V[:, jn], prepare x = F / sigma and mu.x, write B[j,j], B[j,j+1] ---------
@@ -806,7 +832,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     Sv.ensure((size_t)MAXB * MAXB);
     svd_s.ensure((size_t)MAXB);
     R.ensure((size_t)MAXB);
-    counter.ensure(1);
+    counter.ensure(2);
     info.ensure(4);
     murs.ensure((size_t)h);
     const double* after[4] = {V.p, W.p, partials.p, murs.p};
@@ -818,7 +844,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   CUDA_CHECK(cudaMemsetAsync(W.p, 0, sizeof(double) * (size_t)std::max<i64>(n, 1) * ld, st));
   CUDA_CHECK(cudaMemsetAsync(B.p, 0, sizeof(double) * m_b * m_b, st));
   CUDA_CHECK(cudaMemsetAsync(sc.p, 0, sizeof(double) * SC_COUNT, st));
-  CUDA_CHECK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned), st));
+  CUDA_CHECK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned) * 2, st));
   CUDA_CHECK(cudaMemsetAsync(cvec.p, 0, sizeof(double) * MAXB, st));
   CUDA_CHECK(cudaMemsetAsync(info.p, 0, sizeof(int) * 4, st));
   if (centered) LAUNCH(c, "mul_vec", (mul_vec<<<(h + 255) / 256, 256, 0, st>>>(mu, rs, murs.p, h)));
@@ -850,9 +876,14 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
 
   // ---- start vector (irlb.py:151-153): V[:,0] = v0 / ||v0|| ----
   CUDA_CHECK(cudaMemcpyAsync(ybuf_h.p, v0_host, sizeof(double) * h, cudaMemcpyHostToDevice, st));
+  // fused NVLink all-reduce inside the reducing kernels (peer mailboxes); NCCL when it is unavailable
+  const bool fused = c->world > 1 && c->peer.world == c->world;
+  const PeerComm pcw = fused ? c->peer : PeerComm();
+  const PeerComm pc1;  // replicated (V-side) reductions
+  const bool fused_t = fused && h <= PEER_SLOT;
   LAUNCH(c, "update_norm", (update_norm<<<gb_h, RT_THREADS, 0, st>>>(V.p, ld, 0, cvec.p, ybuf_h.p,
                                                             centered ? murs.p : nullptr, h, partials.p,
-                                                            sc.p + SC_NRM2, counter.p)));
+                                                            sc.p + SC_NRM2, counter.p, pc1)));
   LAUNCH(c, "v_finish", (v_finish<<<fin_h, 256, 0, st>>>(ybuf_h.p, rs, sc.p, V.p, ld, 0, m_b, h, fbuf.p, xs.p, B.p, -1,
                                                        centered ? 1 : 0)));
 
@@ -860,12 +891,12 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     // W[:, jn] = normalise( orthog( A_s x - fn W[:, jprev], W[:, :nd] ) )
     WORK(c, (double)A.nnz * (4.0 + sizeof(VT)) + 8.0 * (n + 1) + 8.0 * n * (nd + (jprev >= 0 ? 1 : 0) + 1) + 8.0 * h);
     LAUNCH(c, "spmv_dots", (spmv_dots<VT><<<gb_n, RT_THREADS, 0, st>>>(A.rptr.p, A.cidx.p, A.rval.p, xs.p, sc.p, W.p, ld, jprev,
-                                                              nd, n, ybuf_n.p, partials.p, cvec.p, counter.p)));
-    if (nd > 0) allreduce_sum_f64(c, cvec.p, (size_t)nd);
+                                                              nd, n, ybuf_n.p, partials.p, cvec.p, counter.p, pcw)));
+    if (nd > 0 && !fused) allreduce_sum_f64(c, cvec.p, (size_t)nd);
     WORK(c, 8.0 * n * (nd + 2));
     LAUNCH(c, "update_norm", (update_norm<<<gb_n, RT_THREADS, 0, st>>>(W.p, ld, nd, cvec.p, ybuf_n.p, nullptr, n, partials.p,
-                                                              sc.p + SC_NRM2, counter.p)));
-    allreduce_sum_f64(c, sc.p + SC_NRM2, 2);
+                                                              sc.p + SC_NRM2, counter.p, pcw)));
+    if (!fused) allreduce_sum_f64(c, sc.p + SC_NRM2, 2);
     LAUNCH(c, "w_finish", (w_finish<<<fin_n, 256, 0, st>>>(ybuf_n.p, sc.p, W.p, ld, jn, n, wcur.p)));
   };
   // restart update (irlb.py:238-246): Ritz vectors into the leading k columns, V[:,k] = F, new B
@@ -882,15 +913,16 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     w_column(-1, j, j);
     while (j < m_b) {
       WORK(c, (double)A.nnz * (4.0 + sizeof(VT)) + 8.0 * (h + 1) + 8.0 * h + 8.0 * n);
-      LAUNCH(c, "spmvT_csc", (spmvT_csc<VT><<<h, 256, 0, st>>>(A.cptr.p, A.ridx.p, A.cval.p, wcur.p, tbuf.p)));
-      allreduce_sum_f64(c, tbuf.p, (size_t)h);
+      LAUNCH(c, "spmvT_csc", (spmvT_csc<VT><<<h, 256, 0, st>>>(A.cptr.p, A.ridx.p, A.cval.p, wcur.p, tbuf.p, h, counter.p + 1,
+                                                               fused_t ? pcw : pc1)));
+      if (!fused_t) allreduce_sum_f64(c, tbuf.p, (size_t)h);
       WORK(c, 8.0 * h * (j + 1 + 4));
       LAUNCH(c, "v_prep_dots", (v_prep_dots<<<gb_h, RT_THREADS, 0, st>>>(tbuf.p, mu, rs, sc.p, V.p, ld, j, j + 1, h, ybuf_h.p,
                                                                 partials.p, cvec.p, counter.p)));
       WORK(c, 8.0 * h * (j + 1 + 3));
       LAUNCH(c, "update_norm_v", (update_norm<<<gb_h, RT_THREADS, 0, st>>>(V.p, ld, j + 1, cvec.p, ybuf_h.p,
                                                                 centered ? murs.p : nullptr, h, partials.p,
-                                                                sc.p + SC_NRM2, counter.p)));
+                                                                sc.p + SC_NRM2, counter.p, pc1)));
       LAUNCH(c, "v_finish", (v_finish<<<fin_h, 256, 0, st>>>(ybuf_h.p, rs, sc.p, V.p, ld, j + 1, m_b, h, fbuf.p, xs.p,
                                                            B.p, j, centered ? 1 : 0)));
       if (j < m_b - 1) w_column(j, j + 1, j + 1);
