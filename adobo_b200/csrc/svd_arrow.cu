@@ -242,8 +242,8 @@ __global__ void __launch_bounds__(SA_THREADS, 1) svd_arrow(const double* __restr
     for (int it = 0; it < 60; ++it) {
       double psi = 0, dpsi = 0, phi = 0, dphi = 0, abst = 0;
       for (int i = lane; i < na; i += 32) {
-        const double r = (da[i] - org) - x;
-        const double q = w2a[i] / r, q2 = q / r;
+        const double ri = 1.0 / ((da[i] - org) - x);
+        const double q = w2a[i] * ri, q2 = q * ri;
         abst += fabs(q);
         if (i <= j) {
           psi += q;
@@ -306,15 +306,17 @@ __global__ void __launch_bounds__(SA_THREADS, 1) svd_arrow(const double* __restr
   __syncthreads();
 
   // ---- S6: Gu-Eisenstat weights: what_i^2 = prod_j (mu_j - d_i) / prod_{j != i} (d_j - d_i) ----
-  for (int i = tid; i < na; i += SA_THREADS) {
+  for (int i = warp; i < na; i += SA_WARPS) {  // one warp per weight, lanes over the roots
     const double di = da[i];
-    double p = (da[base[i]] - di) + tau[i];  // mu_i - d_i
-    for (int j = 0; j < na; ++j) {
-      if (j == i) continue;
-      p *= ((da[base[j]] - di) + tau[j]) / (da[j] - di);
+    double p = 1.0;
+    for (int j = lane; j < na; j += 32) {
+      const double num = (da[base[j]] - di) + tau[j];  // mu_j - d_i
+      p *= (j == i) ? num : num / (da[j] - di);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) p *= __shfl_xor_sync(0xffffffffu, p, o);
     const double v = sqrt(fabs(p));
-    what[i] = (wsa[i] >= 0) ? v : -v;
+    if (lane == 0) what[i] = (wsa[i] >= 0) ? v : -v;
   }
   // ---- S7: eigenvectors in ORIGINAL coordinates: X[:, js] for every sorted coordinate js ----
   for (int idx = tid; idx < m * m; idx += SA_THREADS) X[idx] = 0.0;
