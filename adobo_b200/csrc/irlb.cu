@@ -34,20 +34,45 @@ __device__ __forceinline__ double inv_or_zero(double x) { return x > EPS2 ? 1.0 
 constexpr int RT_THREADS = 1024;
 constexpr int RT_WARPS = RT_THREADS / 32;
 
-// vector of nd (<= 128) sums; acc[t] is this lane's partial for column lane + 32 t
-__device__ __forceinline__ void reduce_vec_blocks(double (&acc)[4], int nd, double* __restrict__ partials,
-                                                  double* __restrict__ out, unsigned* __restrict__ counter,
-                                                  const PeerComm& pc) {
+// vector of nd (<= 128) sums.  Every warp first deposits its partial vector in shared memory (deposit_*),
+// then reduce_vec_finish sums over warps, writes the CTA partial, and the last CTA to arrive sums the CTA
+// partials in a fixed order (and, when ranks > 1, exchanges the result over NVLink peer memory).
+__device__ __forceinline__ double (*vec_stage())[MAXB] {
   __shared__ double sh[RT_WARPS][MAXB];
-  __shared__ bool is_last;
+  return sh;
+}
+// acc[t] is this lane's partial for column lane + 32 t
+__device__ __forceinline__ void deposit_lane32(double (&acc)[4]) {
+  double(*sh)[MAXB] = vec_stage();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int t = 0; t < 4; ++t) sh[warp][lane + 32 * t] = acc[t];
+}
+// acc[q] is the partial for column (lane & 7) + 8 q, held by all four 8-lane groups of the warp
+template <int NQ>
+__device__ __forceinline__ void deposit_lane8(double (&acc)[NQ]) {
+  double(*sh)[MAXB] = vec_stage();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    double v = acc[q];
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    if (lane < 8) sh[warp][lane + 8 * q] = v;
+  }
+  if (NQ * 8 < MAXB)
+    for (int c = NQ * 8 + lane; c < MAXB; c += 32) sh[warp][c] = 0.0;
+}
+__device__ __forceinline__ void reduce_vec_finish(int nd, double* __restrict__ partials, double* __restrict__ out,
+                                                  unsigned* __restrict__ counter, const PeerComm& pc) {
+  double(*sh)[MAXB] = vec_stage();
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
   __syncthreads();
   if (threadIdx.x < nd) {
     double s = 0;
-#pragma unroll 8
-    for (int w = 0; w < RT_WARPS; ++w) s += sh[w][threadIdx.x];
+    for (int w = 0; w < nwarps; ++w) s += sh[w][threadIdx.x];
     partials[(size_t)blockIdx.x * MAXB + threadIdx.x] = s;
   }
   __threadfence();
@@ -55,8 +80,8 @@ __device__ __forceinline__ void reduce_vec_blocks(double (&acc)[4], int nd, doub
   if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
   __syncthreads();
   if (is_last) {
-    // warp w sums columns w, w+32, ...: lanes stride the CTA partials (fixed order -> deterministic)
-    for (int col = warp; col < nd; col += RT_WARPS) {
+    // warp w sums columns w, w + nwarps, ...: lanes stride the CTA partials (fixed order -> deterministic)
+    for (int col = warp; col < nd; col += nwarps) {
       double s = 0;
       for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + (size_t)b * MAXB + col);
       s = warp_sum(s);
@@ -68,6 +93,12 @@ __device__ __forceinline__ void reduce_vec_blocks(double (&acc)[4], int nd, doub
       peer_allreduce_block(pc, out, nd);
     }
   }
+}
+__device__ __forceinline__ void reduce_vec_blocks(double (&acc)[4], int nd, double* __restrict__ partials,
+                                                  double* __restrict__ out, unsigned* __restrict__ counter,
+                                                  const PeerComm& pc) {
+  deposit_lane32(acc);
+  reduce_vec_finish(nd, partials, out, counter, pc);
 }
 
 // two scalars
@@ -84,8 +115,8 @@ __device__ __forceinline__ void reduce_two_blocks(double a, double b, double* __
   __syncthreads();
   if (threadIdx.x < 2) {
     double s = 0;
-#pragma unroll 8
-    for (int w = 0; w < RT_WARPS; ++w) s += sh2[w][threadIdx.x];
+    const int nwarps = blockDim.x >> 5;
+    for (int w = 0; w < nwarps; ++w) s += sh2[w][threadIdx.x];
     partials[(size_t)blockIdx.x * 2 + threadIdx.x] = s;
   }
   __threadfence();
@@ -176,8 +207,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) v_prep_dots(const double* __res
 }
 
 // ---- K4  w = A_s x - fn W[:,jprev]  and  c = W[:, :nd]^T w  (irlb.py:165 / 204-216) -------------
+// One warp per row: lowest latency, used while the shard has few rows per resident warp (n < 64 k).
 template <typename VT>
-__global__ void __launch_bounds__(RT_THREADS, 1) spmv_dots(const i64* __restrict__ rptr, const int* __restrict__ cidx,
+__global__ void __launch_bounds__(RT_THREADS, 1) spmv_dots_w32(const i64* __restrict__ rptr, const int* __restrict__ cidx,
                                                  const VT* __restrict__ rval, const double* __restrict__ xs,
                                                  const double* __restrict__ sc, const double* __restrict__ W,
                                                  int ldw, int jprev, int nd, i64 n, double* __restrict__ ybuf,
@@ -206,8 +238,55 @@ __global__ void __launch_bounds__(RT_THREADS, 1) spmv_dots(const i64* __restrict
   if (nd > 0) reduce_vec_blocks(acc, nd, partials, cvec, counter, pc);
 }
 
+// Four rows per warp (8 lanes each), used for large shards: the subset holds ~50-100 non-zeros per cell, so a full warp per row
+// leaves lanes idle and only one dependent load chain (row pointer -> entries -> gather) in flight per warp.
+constexpr int SD_THREADS = 512;
+template <typename VT, int NQ>  // NQ = ceil(nd / 8) column slots per lane (12: basis <= 96 wide, 16: <= 128)
+__global__ void __launch_bounds__(SD_THREADS, 2) spmv_dots(const i64* __restrict__ rptr, const int* __restrict__ cidx,
+                                                 const VT* __restrict__ rval, const double* __restrict__ xs,
+                                                 const double* __restrict__ sc, const double* __restrict__ W,
+                                                 int ldw, int jprev, int nd, i64 n, double* __restrict__ ybuf,
+                                                 double* __restrict__ partials, double* __restrict__ cvec,
+                                                 unsigned* __restrict__ counter, const PeerComm pc) {
+  const int lane = threadIdx.x & 31, sub = lane >> 3, sl = lane & 7;
+  const i64 wg = (((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const i64 warps = ((i64)gridDim.x * blockDim.x) >> 5;
+  const double mvs = sc[SC_MVS], fn = sc[SC_FN];
+  double acc[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) acc[q] = 0.0;
+  for (i64 base = wg * 4; base < n; base += warps * 4) {  // warp-uniform trip count (shuffles inside)
+    const i64 r = base + sub;
+    const bool valid = r < n;
+    double a = 0;
+    if (valid) {
+      const i64 b = rptr[r], e1 = rptr[r + 1];
+#pragma unroll 4
+      for (i64 e = b + sl; e < e1; e += 8) a += (double)__ldg(rval + e) * xs[__ldg(cidx + e)];
+    }
+    a += __shfl_xor_sync(0xffffffffu, a, 4);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    if (valid) {
+      const double* wr = W + (size_t)r * ldw;
+      double w = a - mvs;
+      if (jprev >= 0) w -= fn * wr[jprev];
+      if (sl == 0) ybuf[r] = w;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int col = sl + 8 * q;
+        if (col < nd) acc[q] = fma(wr[col], w, acc[q]);
+      }
+    }
+  }
+  if (nd > 0) {
+    deposit_lane8<NQ>(acc);
+    reduce_vec_finish(nd, partials, cvec, counter, pc);
+  }
+}
+
 // ---- y -= Q[:, :nd] c ;  nrm2 = y.y ;  aux = coef.y  (second half of orthog + the norm) ---------
-__global__ void __launch_bounds__(RT_THREADS, 1) update_norm(const double* __restrict__ Q, int ld, int nd,
+__global__ void __launch_bounds__(RT_THREADS, 1) update_norm_w32(const double* __restrict__ Q, int ld, int nd,
                                                    const double* __restrict__ cvec, double* __restrict__ ybuf,
                                                    const double* __restrict__ coef, i64 rows,
                                                    double* __restrict__ partials, double* __restrict__ out2,
@@ -235,6 +314,48 @@ __global__ void __launch_bounds__(RT_THREADS, 1) update_norm(const double* __res
     n2 += y * y;
     ax += (coef ? coef[r] : 1.0) * y;
   }
+  reduce_two_blocks(n2, ax, partials, out2, counter, pc);
+}
+
+// same, four rows per warp (8 lanes each): more loads in flight, used for large row counts
+__global__ void __launch_bounds__(RT_THREADS, 1) update_norm(const double* __restrict__ Q, int ld, int nd,
+                                                   const double* __restrict__ cvec, double* __restrict__ ybuf,
+                                                   const double* __restrict__ coef, i64 rows,
+                                                   double* __restrict__ partials, double* __restrict__ out2,
+                                                   unsigned* __restrict__ counter, const PeerComm pc) {
+  __shared__ double csh[MAXB];
+  const int lane = threadIdx.x & 31, sub = lane >> 3, sl = lane & 7;
+  const i64 wg = (((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const i64 warps = ((i64)gridDim.x * blockDim.x) >> 5;
+  if (threadIdx.x < MAXB) csh[threadIdx.x] = (threadIdx.x < nd) ? cvec[threadIdx.x] : 0.0;
+  __syncthreads();
+  double n2 = 0, ax = 0;
+  for (i64 base = wg * 4; base < rows; base += warps * 4) {  // four rows per warp, 8 lanes each
+    const i64 r = base + sub;
+    const bool valid = r < rows;
+    double y = valid ? ybuf[r] : 0.0;
+    if (nd > 0) {
+      double p = 0;
+      if (valid) {
+        const double* qr = Q + (size_t)r * ld;
+        for (int col = sl; col < nd; col += 8) p = fma(qr[col], csh[col], p);
+      }
+      p += __shfl_xor_sync(0xffffffffu, p, 4);
+      p += __shfl_xor_sync(0xffffffffu, p, 2);
+      p += __shfl_xor_sync(0xffffffffu, p, 1);
+      y -= p;
+      if (valid && sl == 0) ybuf[r] = y;
+    }
+    if (valid && sl == 0) {
+      n2 = fma(y, y, n2);
+      ax = fma(coef ? coef[r] : 1.0, y, ax);
+    }
+  }
+  // leaders of the four row groups -> lane 0
+  n2 += __shfl_xor_sync(0xffffffffu, n2, 8);
+  n2 += __shfl_xor_sync(0xffffffffu, n2, 16);
+  ax += __shfl_xor_sync(0xffffffffu, ax, 8);
+  ax += __shfl_xor_sync(0xffffffffu, ax, 16);
   reduce_two_blocks(n2, ax, partials, out2, counter, pc);
 }
 
@@ -827,7 +948,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     xs.ensure((size_t)h);
     wcur.ensure((size_t)std::max<i64>(n, 1));
     cvec.ensure(MAXB);
-    partials.ensure((size_t)c->sm_count * MAXB);
+    partials.ensure((size_t)2 * c->sm_count * MAXB);
     Su.ensure((size_t)MAXB * MAXB);
     Sv.ensure((size_t)MAXB * MAXB);
     svd_s.ensure((size_t)MAXB);
@@ -840,6 +961,9 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
       if (before[q] != after[q]) ws.clear_graphs();
   }
   const unsigned gb_n = red_blocks(c, n), gb_h = red_blocks(c, h);
+  const bool wide_rows = n >= 65536;  // enough rows per resident warp to prefer throughput over latency
+  // spmv_dots (wide): 512-thread CTAs, two per SM, four rows per warp
+  const unsigned gb_sd = (unsigned)std::max<i64>(1, std::min<i64>((n + 63) / 64, 2 * (i64)c->sm_count));
   CUDA_CHECK(cudaMemsetAsync(V.p, 0, sizeof(double) * (size_t)h * ld, st));
   CUDA_CHECK(cudaMemsetAsync(W.p, 0, sizeof(double) * (size_t)std::max<i64>(n, 1) * ld, st));
   CUDA_CHECK(cudaMemsetAsync(B.p, 0, sizeof(double) * m_b * m_b, st));
@@ -881,7 +1005,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   const PeerComm pcw = fused ? c->peer : PeerComm();
   const PeerComm pc1;  // replicated (V-side) reductions
   const bool fused_t = fused && h <= PEER_SLOT;
-  LAUNCH(c, "update_norm", (update_norm<<<gb_h, RT_THREADS, 0, st>>>(V.p, ld, 0, cvec.p, ybuf_h.p,
+  LAUNCH(c, "update_norm", (update_norm_w32<<<gb_h, RT_THREADS, 0, st>>>(V.p, ld, 0, cvec.p, ybuf_h.p,
                                                             centered ? murs.p : nullptr, h, partials.p,
                                                             sc.p + SC_NRM2, counter.p, pc1)));
   LAUNCH(c, "v_finish", (v_finish<<<fin_h, 256, 0, st>>>(ybuf_h.p, rs, sc.p, V.p, ld, 0, m_b, h, fbuf.p, xs.p, B.p, -1,
@@ -890,12 +1014,26 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   auto w_column = [&](int jprev, int nd, int jn) {
     // W[:, jn] = normalise( orthog( A_s x - fn W[:, jprev], W[:, :nd] ) )
     WORK(c, (double)A.nnz * (4.0 + sizeof(VT)) + 8.0 * (n + 1) + 8.0 * n * (nd + (jprev >= 0 ? 1 : 0) + 1) + 8.0 * h);
-    LAUNCH(c, "spmv_dots", (spmv_dots<VT><<<gb_n, RT_THREADS, 0, st>>>(A.rptr.p, A.cidx.p, A.rval.p, xs.p, sc.p, W.p, ld, jprev,
-                                                              nd, n, ybuf_n.p, partials.p, cvec.p, counter.p, pcw)));
+    if (!wide_rows)
+      LAUNCH(c, "spmv_dots", (spmv_dots_w32<VT><<<gb_n, RT_THREADS, 0, st>>>(A.rptr.p, A.cidx.p, A.rval.p, xs.p, sc.p, W.p, ld,
+                                                                    jprev, nd, n, ybuf_n.p, partials.p, cvec.p,
+                                                                    counter.p, pcw)));
+    else if (m_b <= 96)
+      LAUNCH(c, "spmv_dots", (spmv_dots<VT, 12><<<gb_sd, SD_THREADS, 0, st>>>(A.rptr.p, A.cidx.p, A.rval.p, xs.p, sc.p, W.p, ld,
+                                                                     jprev, nd, n, ybuf_n.p, partials.p, cvec.p,
+                                                                     counter.p, pcw)));
+    else
+      LAUNCH(c, "spmv_dots", (spmv_dots<VT, 16><<<gb_sd, SD_THREADS, 0, st>>>(A.rptr.p, A.cidx.p, A.rval.p, xs.p, sc.p, W.p, ld,
+                                                                     jprev, nd, n, ybuf_n.p, partials.p, cvec.p,
+                                                                     counter.p, pcw)));
     if (nd > 0 && !fused) allreduce_sum_f64(c, cvec.p, (size_t)nd);
     WORK(c, 8.0 * n * (nd + 2));
-    LAUNCH(c, "update_norm", (update_norm<<<gb_n, RT_THREADS, 0, st>>>(W.p, ld, nd, cvec.p, ybuf_n.p, nullptr, n, partials.p,
-                                                              sc.p + SC_NRM2, counter.p, pcw)));
+    if (wide_rows)
+      LAUNCH(c, "update_norm", (update_norm<<<gb_n, RT_THREADS, 0, st>>>(W.p, ld, nd, cvec.p, ybuf_n.p, nullptr, n, partials.p,
+                                                                sc.p + SC_NRM2, counter.p, pcw)));
+    else
+      LAUNCH(c, "update_norm", (update_norm_w32<<<gb_n, RT_THREADS, 0, st>>>(W.p, ld, nd, cvec.p, ybuf_n.p, nullptr, n,
+                                                                    partials.p, sc.p + SC_NRM2, counter.p, pcw)));
     if (!fused) allreduce_sum_f64(c, sc.p + SC_NRM2, 2);
     LAUNCH(c, "w_finish", (w_finish<<<fin_n, 256, 0, st>>>(ybuf_n.p, sc.p, W.p, ld, jn, n, wcur.p)));
   };
@@ -920,7 +1058,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
       LAUNCH(c, "v_prep_dots", (v_prep_dots<<<gb_h, RT_THREADS, 0, st>>>(tbuf.p, mu, rs, sc.p, V.p, ld, j, j + 1, h, ybuf_h.p,
                                                                 partials.p, cvec.p, counter.p)));
       WORK(c, 8.0 * h * (j + 1 + 3));
-      LAUNCH(c, "update_norm_v", (update_norm<<<gb_h, RT_THREADS, 0, st>>>(V.p, ld, j + 1, cvec.p, ybuf_h.p,
+      LAUNCH(c, "update_norm_v", (update_norm_w32<<<gb_h, RT_THREADS, 0, st>>>(V.p, ld, j + 1, cvec.p, ybuf_h.p,
                                                                 centered ? murs.p : nullptr, h, partials.p,
                                                                 sc.p + SC_NRM2, counter.p, pc1)));
       LAUNCH(c, "v_finish", (v_finish<<<fin_h, 256, 0, st>>>(ybuf_h.p, rs, sc.p, V.p, ld, j + 1, m_b, h, fbuf.p, xs.p,
