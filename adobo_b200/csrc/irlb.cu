@@ -744,12 +744,27 @@ __global__ void conv_check(const double* __restrict__ Su, const double* __restri
 constexpr int RB_ROWS = 64;
 constexpr int RB_QP = RB_ROWS + 1;
 
-__global__ void transpose_s(const double* __restrict__ S, int m, int kc, int kcp, double* __restrict__ St) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= m * kcp) return;
+// both rotation matrices of a restart (Sv for V, Su for W) in one launch: St0 | St1
+__global__ void transpose_s(const double* __restrict__ S0, const double* __restrict__ S1, int m, int kc, int kcp,
+                            double* __restrict__ St) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = m * kcp;
+  if (idx >= 2 * per) return;
+  const double* S = (idx < per) ? S0 : S1;
+  double* dst = St + ((idx < per) ? 0 : per);
+  if (idx >= per) idx -= per;
   const int i = idx / kcp, c = idx - i * kcp;
-  St[idx] = (c < kc) ? S[(size_t)c * m + i] : 0.0;
+  dst[idx] = (c < kc) ? S[(size_t)c * m + i] : 0.0;
 }
+
+struct RotJob {
+  double* Q;               // rows x ld, row-major
+  i64 rows;
+  const double* St;        // [m][kcp] transposed rotation
+  double* out;             // nullptr: in place into Q[:, :kc]
+  int ldo;
+  const double* colscale;  // optional per-column factor (var_weigh)
+};
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -758,9 +773,20 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-__global__ void __launch_bounds__(512) rotate_basis(double* __restrict__ Q, int ld, i64 rows, const double* __restrict__ St,
-                                                    int m, int kc, int nbuf, double* __restrict__ out, int ldo,
-                                                    const double* __restrict__ colscale) {
+// The V (h rows, few tiles) and W (n rows) rotations of a restart run as ONE launch: CTAs [0, nba) take job a,
+// the rest job b, so the small V job no longer occupies a nearly empty GPU on its own.
+__global__ void __launch_bounds__(512) rotate_basis(const RotJob ja, const RotJob jb, int nba, int ld, int m, int kc,
+                                                    int nbuf) {
+  const bool second = (int)blockIdx.x >= nba;
+  const RotJob& job = second ? jb : ja;
+  double* __restrict__ Q = job.Q;
+  const i64 rows = job.rows;
+  const double* __restrict__ St = job.St;
+  double* __restrict__ out = job.out;
+  const int ldo = job.ldo;
+  const double* __restrict__ colscale = job.colscale;
+  const unsigned bid = second ? blockIdx.x - nba : blockIdx.x;
+  const unsigned nblk = second ? gridDim.x - nba : nba;
   extern __shared__ __align__(16) double sm[];
   const int kcp = (kc + 7) & ~7;
   double* Ssm = sm;                   // [m][kcp]
@@ -779,11 +805,11 @@ __global__ void __launch_bounds__(512) rotate_basis(double* __restrict__ Q, int 
     cp_async_commit();
   };
   int buf = 0;
-  if ((i64)blockIdx.x < ntiles) fetch(blockIdx.x, 0);
-  for (i64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
+  if ((i64)bid < ntiles) fetch(bid, 0);
+  for (i64 t = bid; t < ntiles; t += nblk) {
     cp_async_wait_all();
     __syncthreads();  // tile t landed (and Ssm written); everybody is done with the other buffer
-    const i64 tn = t + gridDim.x;
+    const i64 tn = t + nblk;
     if (nbuf == 2 && tn < ntiles) fetch(tn, buf ^ 1);
     const i64 row0 = t * RB_ROWS;
     const double* qp = Qs + buf * qstride + lane;
@@ -981,17 +1007,20 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   const int rot_nbuf = (rot_s + 2 * rot_q <= 225 * 1024) ? 2 : 1;
   const size_t rot_smem = rot_s + rot_nbuf * rot_q;
   CUDA_CHECK(cudaFuncSetAttribute(rotate_basis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rot_smem));
-  ws.St.ensure((size_t)MAXB * MAXB);
+  ws.St.ensure((size_t)2 * MAXB * MAXB);
   DevBuf<double>& St = ws.St;
-  // Qm[:, :kc] (or out) = Qm[:, :m_b] S[:, :kc]
-  auto rotate = [&](double* Qm, i64 nrows, const double* Smat, int kc, double* outp, int ldo, const double* scale) {
+  // V[:, :kc] (or outv) = V Sv[:, :kc]  and  W[:, :kc] (or outw) = W Su[:, :kc], one launch each for the
+  // transposes and for the two tall-skinny GEMMs
+  auto rotate2 = [&](int kc, double* outv, double* outw, int ldo, const double* scale_w) {
     const int kcp = (kc + 7) & ~7;
-    LAUNCH(c, "transpose_s", (transpose_s<<<(m_b * kcp + 255) / 256, 256, 0, st>>>(Smat, m_b, kc, kcp, St.p)));
-    WORK(c, 8.0 * nrows * (m_b + kc));
-    LAUNCH(c, "rotate_basis", (rotate_basis<<<row_blocks(c, nrows), 32 * (kcp / 8), rot_smem, st>>>(
-                                  Qm, ld, nrows, St.p, m_b, kc, rot_nbuf, outp, ldo, scale)));
+    LAUNCH(c, "transpose_s", (transpose_s<<<(2 * m_b * kcp + 255) / 256, 256, 0, st>>>(Sv.p, Su.p, m_b, kc, kcp, St.p)));
+    RotJob jv{V.p, (i64)h, St.p, outv, ldo, nullptr};
+    RotJob jw{W.p, n, St.p + (size_t)m_b * kcp, outw, ldo, scale_w};
+    const unsigned nbv = row_blocks(c, h), nbw = row_blocks(c, n);
+    WORK(c, 8.0 * (n + h) * (m_b + kc));
+    LAUNCH(c, "rotate_basis", (rotate_basis<<<nbv + nbw, 32 * (kcp / 8), rot_smem, st>>>(jv, jw, (int)nbv, ld, m_b, kc,
+                                                                                   rot_nbuf)));
   };
-
   const bool use_arrow = getenv("ADOBO_B200_SVD_JACOBI") == nullptr;
   const bool force_fallback = getenv("ADOBO_B200_SVD_FORCE_FALLBACK") != nullptr;  // test hook
   if (use_arrow) svd_arrow_prepare(m_b);
@@ -1039,10 +1068,9 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   };
   // restart update (irlb.py:238-246): Ritz vectors into the leading k columns, V[:,k] = F, new B
   auto restart_update = [&](int k) {
-    rotate(V.p, h, Sv.p, k, nullptr, 0, nullptr);
+    rotate2(k, nullptr, nullptr, 0, nullptr);
     LAUNCH(c, "set_restart", (set_restart<<<(std::max(h, m_b * m_b) + 255) / 256, 256, 0, st>>>(V.p, ld, h, fbuf.p, B.p,
                                                                                             m_b, k, svd_s.p, R.p)));
-    rotate(W.p, n, Su.p, k, nullptr, 0, nullptr);
   };
   // one outer iteration (irlb.py:155-231) up to the convergence read-back
   auto enqueue_iteration = [&](bool first, int k) {
@@ -1144,8 +1172,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   outU.ensure((size_t)std::max<i64>(n, 1) * nu);
   outV.ensure((size_t)h * nu);
   outS.ensure((size_t)nu);
-  rotate(W.p, n, Su.p, nu, outU.p, nu, var_weigh ? svd_s.p : nullptr);
-  rotate(V.p, h, Sv.p, nu, outV.p, nu, nullptr);
+  rotate2(nu, outV.p, outU.p, nu, var_weigh ? svd_s.p : nullptr);
   CUDA_CHECK(cudaMemcpyAsync(outS.p, svd_s.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));
   CUDA_CHECK(cudaStreamSynchronize(st));
   res.steps = it;
