@@ -102,7 +102,7 @@ __device__ __forceinline__ void reduce_vec_blocks(double (&acc)[4], int nd, doub
 }
 
 // two scalars
-__device__ __forceinline__ void reduce_two_blocks(double a, double b, double* __restrict__ partials,
+__device__ __forceinline__ bool reduce_two_blocks(double a, double b, double* __restrict__ partials,
                                                   double* __restrict__ out, unsigned* __restrict__ counter,
                                                   const PeerComm& pc) {
   __shared__ double sh2[RT_WARPS][2];
@@ -141,6 +141,54 @@ __device__ __forceinline__ void reduce_two_blocks(double a, double b, double* __
     if (pc.world > 1) {
       __syncthreads();
       peer_allreduce_block(pc, out, 2);
+    }
+  }
+  return is_last2;
+}
+
+// Epilogue of the norm reduction, run by the LAST CTA only (all its threads): normalise the vector and
+// store it -- the work of v_finish / w_finish without another kernel launch.  kind 1: F -> V[:, jn], x = F/sigma,
+// mu.x, B[j,j], B[j,j+1] (irlb.py:191-197, 221);  kind 2: w -> W[:, jn] and its contiguous copy (irlb.py:176-178, 217-219).
+struct Finish {
+  int kind = 0;  // 0: none (a separate finish kernel follows)
+  const double* rs = nullptr;
+  double* sc = nullptr;
+  double* M = nullptr;  // V or W
+  int ld = 0, jn = 0, m_b = 0, j = -1, centered = 0;
+  double* fbuf = nullptr;  // kind 1: normalised F;  kind 2: wcur
+  double* xs = nullptr;
+  double* B = nullptr;
+};
+__device__ __forceinline__ void finish_in_last_cta(const Finish& f, const double* __restrict__ ybuf, i64 rows) {
+  __syncthreads();  // out2 (written by lane 0 / the peer exchange) is visible to the whole CTA
+  const double nrm = sqrt(__ldcg(f.sc + SC_NRM2));
+  const double inv = inv_or_zero(nrm);
+  const double aux = __ldcg(f.sc + SC_AUX);
+  if (f.kind == 1) {
+    for (i64 r = threadIdx.x; r < rows; r += blockDim.x) {
+      const double v = inv * __ldcg(ybuf + r);
+      f.fbuf[r] = v;
+      if (f.jn < f.m_b) f.M[(size_t)r * f.ld + f.jn] = v;
+      f.xs[r] = f.rs ? v * f.rs[r] : v;
+    }
+    if (threadIdx.x == 0) {
+      f.sc[SC_FN] = nrm;
+      f.sc[SC_FNINV] = inv;
+      f.sc[SC_MVS] = f.centered ? inv * aux : 0.0;
+      if (f.j >= 0) {
+        f.B[(size_t)f.j * f.m_b + f.j] = f.sc[SC_S];
+        if (f.j < f.m_b - 1) f.B[(size_t)f.j * f.m_b + f.j + 1] = nrm;
+      }
+    }
+  } else {
+    for (i64 r = threadIdx.x; r < rows; r += blockDim.x) {
+      const double v = inv * __ldcg(ybuf + r);
+      f.M[(size_t)r * f.ld + f.jn] = v;
+      f.fbuf[r] = v;
+    }
+    if (threadIdx.x == 0) {
+      f.sc[SC_S] = nrm;
+      f.sc[SC_SU] = inv * aux;
     }
   }
 }
@@ -290,7 +338,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) update_norm_w32(const double* _
                                                    const double* __restrict__ cvec, double* __restrict__ ybuf,
                                                    const double* __restrict__ coef, i64 rows,
                                                    double* __restrict__ partials, double* __restrict__ out2,
-                                                   unsigned* __restrict__ counter, const PeerComm pc) {
+                                                   unsigned* __restrict__ counter, const PeerComm pc, const Finish fin) {
   const int lane = threadIdx.x & 31;
   const i64 warps = ((i64)gridDim.x * blockDim.x) >> 5;
   double creg[4];
@@ -314,7 +362,8 @@ __global__ void __launch_bounds__(RT_THREADS, 1) update_norm_w32(const double* _
     n2 += y * y;
     ax += (coef ? coef[r] : 1.0) * y;
   }
-  reduce_two_blocks(n2, ax, partials, out2, counter, pc);
+  const bool last = reduce_two_blocks(n2, ax, partials, out2, counter, pc);
+  if (last && fin.kind) finish_in_last_cta(fin, ybuf, rows);
 }
 
 // same, four rows per warp (8 lanes each): more loads in flight, used for large row counts
@@ -1016,7 +1065,12 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     LAUNCH(c, "transpose_s", (transpose_s<<<(2 * m_b * kcp + 255) / 256, 256, 0, st>>>(Sv.p, Su.p, m_b, kc, kcp, St.p)));
     RotJob jv{V.p, (i64)h, St.p, outv, ldo, nullptr};
     RotJob jw{W.p, n, St.p + (size_t)m_b * kcp, outw, ldo, scale_w};
-    const unsigned nbv = row_blocks(c, h), nbw = row_blocks(c, n);
+    // one wave: split the SMs between the two jobs in proportion to their 64-row tiles
+    const i64 tv = (h + RB_ROWS - 1) / RB_ROWS, tw = (n + RB_ROWS - 1) / RB_ROWS, sms = c->sm_count;
+    i64 bv = (tv * sms + (tv + tw) / 2) / (tv + tw);
+    bv = std::max<i64>(1, std::min<i64>(bv, tv));
+    const i64 bw = std::max<i64>(1, std::min<i64>(tw, sms - bv));
+    const unsigned nbv = (unsigned)bv, nbw = (unsigned)bw;
     WORK(c, 8.0 * (n + h) * (m_b + kc));
     LAUNCH(c, "rotate_basis", (rotate_basis<<<nbv + nbw, 32 * (kcp / 8), rot_smem, st>>>(jv, jw, (int)nbv, ld, m_b, kc,
                                                                                    rot_nbuf)));
@@ -1034,11 +1088,28 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   const PeerComm pcw = fused ? c->peer : PeerComm();
   const PeerComm pc1;  // replicated (V-side) reductions
   const bool fused_t = fused && h <= PEER_SLOT;
+  // the finish step (normalise + store) runs in the last CTA of the norm reduction when one CTA can do it
+  // in about a launch latency; larger vectors keep the separate grid-wide kernels
+  const bool fold_v = h <= 16384, fold_w = !wide_rows && n <= 8192 && !(c->world > 1 && !fused);
+  auto v_fin = [&](int jn, int j) {
+    Finish f;
+    if (!fold_v) return f;
+    f.kind = 1, f.rs = rs, f.sc = sc.p, f.M = V.p, f.ld = ld, f.jn = jn, f.m_b = m_b, f.j = j, f.centered = centered ? 1 : 0;
+    f.fbuf = fbuf.p, f.xs = xs.p, f.B = B.p;
+    return f;
+  };
+  auto w_fin = [&](int jn) {
+    Finish f;
+    if (!fold_w) return f;
+    f.kind = 2, f.sc = sc.p, f.M = W.p, f.ld = ld, f.jn = jn, f.fbuf = wcur.p;
+    return f;
+  };
   LAUNCH(c, "update_norm", (update_norm_w32<<<gb_h, RT_THREADS, 0, st>>>(V.p, ld, 0, cvec.p, ybuf_h.p,
                                                             centered ? murs.p : nullptr, h, partials.p,
-                                                            sc.p + SC_NRM2, counter.p, pc1)));
-  LAUNCH(c, "v_finish", (v_finish<<<fin_h, 256, 0, st>>>(ybuf_h.p, rs, sc.p, V.p, ld, 0, m_b, h, fbuf.p, xs.p, B.p, -1,
-                                                       centered ? 1 : 0)));
+                                                            sc.p + SC_NRM2, counter.p, pc1, v_fin(0, -1))));
+  if (!fold_v)
+    LAUNCH(c, "v_finish", (v_finish<<<fin_h, 256, 0, st>>>(ybuf_h.p, rs, sc.p, V.p, ld, 0, m_b, h, fbuf.p, xs.p, B.p, -1,
+                                                         centered ? 1 : 0)));
 
   auto w_column = [&](int jprev, int nd, int jn) {
     // W[:, jn] = normalise( orthog( A_s x - fn W[:, jprev], W[:, :nd] ) )
@@ -1062,9 +1133,10 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
                                                                 sc.p + SC_NRM2, counter.p, pcw)));
     else
       LAUNCH(c, "update_norm", (update_norm_w32<<<gb_n, RT_THREADS, 0, st>>>(W.p, ld, nd, cvec.p, ybuf_n.p, nullptr, n,
-                                                                    partials.p, sc.p + SC_NRM2, counter.p, pcw)));
+                                                                    partials.p, sc.p + SC_NRM2, counter.p, pcw,
+                                                                    w_fin(jn))));
     if (!fused) allreduce_sum_f64(c, sc.p + SC_NRM2, 2);
-    LAUNCH(c, "w_finish", (w_finish<<<fin_n, 256, 0, st>>>(ybuf_n.p, sc.p, W.p, ld, jn, n, wcur.p)));
+    if (wide_rows || !fold_w) LAUNCH(c, "w_finish", (w_finish<<<fin_n, 256, 0, st>>>(ybuf_n.p, sc.p, W.p, ld, jn, n, wcur.p)));
   };
   // restart update (irlb.py:238-246): Ritz vectors into the leading k columns, V[:,k] = F, new B
   auto restart_update = [&](int k) {
@@ -1088,9 +1160,10 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
       WORK(c, 8.0 * h * (j + 1 + 3));
       LAUNCH(c, "update_norm_v", (update_norm_w32<<<gb_h, RT_THREADS, 0, st>>>(V.p, ld, j + 1, cvec.p, ybuf_h.p,
                                                                 centered ? murs.p : nullptr, h, partials.p,
-                                                                sc.p + SC_NRM2, counter.p, pc1)));
-      LAUNCH(c, "v_finish", (v_finish<<<fin_h, 256, 0, st>>>(ybuf_h.p, rs, sc.p, V.p, ld, j + 1, m_b, h, fbuf.p, xs.p,
-                                                           B.p, j, centered ? 1 : 0)));
+                                                                sc.p + SC_NRM2, counter.p, pc1, v_fin(j + 1, j))));
+      if (!fold_v)
+        LAUNCH(c, "v_finish", (v_finish<<<fin_h, 256, 0, st>>>(ybuf_h.p, rs, sc.p, V.p, ld, j + 1, m_b, h, fbuf.p, xs.p,
+                                                             B.p, j, centered ? 1 : 0)));
       if (j < m_b - 1) w_column(j, j + 1, j + 1);
       ++j;
     }
