@@ -376,6 +376,9 @@ int adobo_ctx_create(int device, adobo_ctx** out) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming));
   CUDA_CHECK(cudaMallocHost(&c->pinned, 4096));
   *out = c;
   API_END
@@ -406,8 +409,11 @@ void adobo_ctx_destroy(adobo_ctx* c) {
   }
   for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
   if (c->pinned) cudaFreeHost(c->pinned);
-  cudaStream_t st = c->stream;
+  if (c->fork_ev) cudaEventDestroy(c->fork_ev);
+  if (c->join_ev) cudaEventDestroy(c->join_ev);
+  cudaStream_t st = c->stream, side = c->side;
   delete c;
+  if (side) cudaStreamDestroy(side);
   cudaStreamDestroy(st);
   pool_trim();
 }

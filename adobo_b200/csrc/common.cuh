@@ -116,6 +116,9 @@ struct adobo_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  // second stream + fork/join events: the small SVD of an IRLB restart runs beside the last Lanczos step
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
   // ---- count matrix shard (CSR cells x genes) ----
   i64 n = 0;        // local cells
   i64 n_total = 0;  // cells over all ranks

@@ -22,7 +22,8 @@ namespace adobo {
 // svd_arrow.cu: structured SVD of the restarted B (diag + spike + bidiagonal tail)
 bool svd_arrow_supported(int m, int k);
 void svd_arrow_prepare(int m);
-void launch_svd_arrow(adobo_ctx* c, const double* B, int m, int k, double* Su, double* sv, double* Sv, int* info);
+void launch_svd_arrow(adobo_ctx* c, const double* B, int m, int k, double* Su, double* sv, double* Sv, int* info,
+                      cudaStream_t st);
 
 enum { SC_S = 0, SC_FN, SC_FNINV, SC_SU, SC_MVS, SC_SMAX, SC_NRM2, SC_AUX, SC_COUNT = 16 };
 constexpr int MAXB = 128;  // widest basis the dot kernels handle (4 columns per lane)
@@ -154,7 +155,7 @@ struct Finish {
   const double* rs = nullptr;
   double* sc = nullptr;
   double* M = nullptr;  // V or W
-  int ld = 0, jn = 0, m_b = 0, j = -1, centered = 0;
+  int ld = 0, jn = 0, m_b = 0, j = -1, centered = 0;  // kind 2: m_b = row length of B
   double* fbuf = nullptr;  // kind 1: normalised F;  kind 2: wcur
   double* xs = nullptr;
   double* B = nullptr;
@@ -175,10 +176,7 @@ __device__ __forceinline__ void finish_in_last_cta(const Finish& f, const double
       f.sc[SC_FN] = nrm;
       f.sc[SC_FNINV] = inv;
       f.sc[SC_MVS] = f.centered ? inv * aux : 0.0;
-      if (f.j >= 0) {
-        f.B[(size_t)f.j * f.m_b + f.j] = f.sc[SC_S];
-        if (f.j < f.m_b - 1) f.B[(size_t)f.j * f.m_b + f.j + 1] = nrm;
-      }
+      if (f.j >= 0 && f.j < f.m_b - 1) f.B[(size_t)f.j * f.m_b + f.j + 1] = nrm;  // irlb.py:197
     }
   } else {
     for (i64 r = threadIdx.x; r < rows; r += blockDim.x) {
@@ -189,6 +187,7 @@ __device__ __forceinline__ void finish_in_last_cta(const Finish& f, const double
     if (threadIdx.x == 0) {
       f.sc[SC_S] = nrm;
       f.sc[SC_SU] = inv * aux;
+      f.B[(size_t)f.jn * f.m_b + f.jn] = nrm;  // irlb.py:196 / 221
     }
   }
 }
@@ -425,16 +424,14 @@ __global__ void v_finish(const double* __restrict__ ybuf, const double* __restri
     sc[SC_FN] = fn;
     sc[SC_FNINV] = fninv;
     sc[SC_MVS] = centered ? fninv * sc[SC_AUX] : 0.0;
-    if (j >= 0) {
-      B[(size_t)j * m_b + j] = sc[SC_S];               // irlb.py:196 / 221
-      if (j < m_b - 1) B[(size_t)j * m_b + j + 1] = fn;  // irlb.py:197
-    }
+    if (j >= 0 && j < m_b - 1) B[(size_t)j * m_b + j + 1] = fn;  // irlb.py:197
   }
 }
 
 // ---- normalise w, store W[:, jn] and the contiguous copy the next A^T u gathers from -----------
+// B[jn, jn] = ||w|| is complete here, so the SVD of B can start while the last F is still being computed
 __global__ void w_finish(const double* __restrict__ ybuf, double* __restrict__ sc, double* __restrict__ W, int ldw,
-                         int jn, i64 n, double* __restrict__ wcur) {
+                         int jn, i64 n, double* __restrict__ wcur, double* __restrict__ B, int m_b) {
   const double s = sqrt(sc[SC_NRM2]);
   const double sinv = inv_or_zero(s);
   const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -446,6 +443,7 @@ __global__ void w_finish(const double* __restrict__ ybuf, double* __restrict__ s
   if (r == 0) {
     sc[SC_S] = s;
     sc[SC_SU] = sinv * sc[SC_AUX];
+    B[(size_t)jn * m_b + jn] = s;  // irlb.py:196 / 221
   }
 }
 
@@ -1101,7 +1099,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   auto w_fin = [&](int jn) {
     Finish f;
     if (!fold_w) return f;
-    f.kind = 2, f.sc = sc.p, f.M = W.p, f.ld = ld, f.jn = jn, f.fbuf = wcur.p;
+    f.kind = 2, f.sc = sc.p, f.M = W.p, f.ld = ld, f.jn = jn, f.fbuf = wcur.p, f.B = B.p, f.m_b = m_b;
     return f;
   };
   LAUNCH(c, "update_norm", (update_norm_w32<<<gb_h, RT_THREADS, 0, st>>>(V.p, ld, 0, cvec.p, ybuf_h.p,
@@ -1136,7 +1134,8 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
                                                                     partials.p, sc.p + SC_NRM2, counter.p, pcw,
                                                                     w_fin(jn))));
     if (!fused) allreduce_sum_f64(c, sc.p + SC_NRM2, 2);
-    if (wide_rows || !fold_w) LAUNCH(c, "w_finish", (w_finish<<<fin_n, 256, 0, st>>>(ybuf_n.p, sc.p, W.p, ld, jn, n, wcur.p)));
+    if (wide_rows || !fold_w) LAUNCH(c, "w_finish", (w_finish<<<fin_n, 256, 0, st>>>(ybuf_n.p, sc.p, W.p, ld, jn, n, wcur.p, B.p,
+                                                                                       m_b)));
   };
   // restart update (irlb.py:238-246): Ritz vectors into the leading k columns, V[:,k] = F, new B
   auto restart_update = [&](int k) {
@@ -1145,11 +1144,28 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
                                                                                             m_b, k, svd_s.p, R.p)));
   };
   // one outer iteration (irlb.py:155-231) up to the convergence read-back
+  const bool use_graphs = !c->profiling && getenv("ADOBO_B200_NO_GRAPH") == nullptr;
+  // SVD of B (irlb.py:224): restarts have the diag + spike + bidiagonal-tail structure (svd_arrow), the first
+  // iteration is a plain bidiagonal matrix (Jacobi).  B is complete once the last column of W is normalised,
+  // so under graph capture the single-CTA SVD is forked onto the side stream and overlaps the last F.
+  auto enqueue_svd = [&](bool first, int k, cudaStream_t s) {
+    if (!first && use_arrow && svd_arrow_supported(m_b, k))
+      launch_svd_arrow(c, B.p, m_b, k, Su.p, svd_s.p, Sv.p, info.p, s);
+    else
+      LAUNCH(c, "jacobi_svd", (jacobi<<<1, JTHREADS, svd_smem, s>>>(B.p, m_b, Su.p, svd_s.p, Sv.p, info.p)));
+  };
+  const bool fork_svd = use_graphs && getenv("ADOBO_B200_NO_FORK") == nullptr;
   auto enqueue_iteration = [&](bool first, int k) {
     if (!first) restart_update(k);
     int j = first ? 0 : k;
     w_column(-1, j, j);
     while (j < m_b) {
+      if (j == m_b - 1 && fork_svd) {
+        CUDA_CHECK(cudaEventRecord(c->fork_ev, st));
+        CUDA_CHECK(cudaStreamWaitEvent(c->side, c->fork_ev, 0));
+        enqueue_svd(first, k, c->side);
+        CUDA_CHECK(cudaEventRecord(c->join_ev, c->side));
+      }
       WORK(c, (double)A.nnz * (4.0 + sizeof(VT)) + 8.0 * (h + 1) + 8.0 * h + 8.0 * n);
       LAUNCH(c, "spmvT_csc", (spmvT_csc<VT><<<h, 256, 0, st>>>(A.cptr.p, A.ridx.p, A.cval.p, wcur.p, tbuf.p, h, counter.p + 1,
                                                                fused_t ? pcw : pc1)));
@@ -1167,13 +1183,11 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
       if (j < m_b - 1) w_column(j, j + 1, j + 1);
       ++j;
     }
-    // SVD of B (irlb.py:224): restarts have the diag + spike + bidiagonal-tail structure (svd_arrow),
-    // the first iteration is a plain bidiagonal matrix (Jacobi)
     const bool arrow = !first && use_arrow && svd_arrow_supported(m_b, k);
-    if (arrow)
-      launch_svd_arrow(c, B.p, m_b, k, Su.p, svd_s.p, Sv.p, info.p);
+    if (fork_svd)
+      CUDA_CHECK(cudaStreamWaitEvent(st, c->join_ev, 0));
     else
-      LAUNCH(c, "jacobi_svd", (jacobi<<<1, JTHREADS, svd_smem, st>>>(B.p, m_b, Su.p, svd_s.p, Sv.p, info.p)));
+      enqueue_svd(first, k, st);
     LAUNCH(c, "conv_check", (conv_check<<<1, 128, 0, st>>>(Su.p, svd_s.p, sc.p, m_b, nu, k, first ? 0 : 1, tol, R.p,
                                                          info.p, arrow ? 1 : 0)));
     CUDA_CHECK(cudaMemcpyAsync(h_info, info.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
@@ -1186,7 +1200,6 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     CUDA_CHECK(cudaMemcpyAsync(h_info, info.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
   };
-  const bool use_graphs = !c->profiling && getenv("ADOBO_B200_NO_GRAPH") == nullptr;
   auto run_iteration = [&](bool first, int k) {
     if (!use_graphs) {
       enqueue_iteration(first, k);

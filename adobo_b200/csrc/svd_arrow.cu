@@ -443,9 +443,10 @@ void svd_arrow_prepare(int m) {
   }
 }
 
-void launch_svd_arrow(adobo_ctx* c, const double* B, int m, int k, double* Su, double* sv, double* Sv, int* info) {
+void launch_svd_arrow(adobo_ctx* c, const double* B, int m, int k, double* Su, double* sv, double* Sv, int* info,
+                      cudaStream_t st) {
   WORK(c, 24.0 * m * m);
-  LAUNCH(c, "svd_arrow", (svd_arrow<<<1, SA_THREADS, svd_arrow_smem(m), c->stream>>>(B, m, k, Su, sv, Sv, info)));
+  LAUNCH(c, "svd_arrow", (svd_arrow<<<1, SA_THREADS, svd_arrow_smem(m), st>>>(B, m, k, Su, sv, Sv, info)));
 }
 
 }  // namespace adobo
