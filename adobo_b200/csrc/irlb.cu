@@ -908,6 +908,129 @@ __global__ void __launch_bounds__(512) rotate_basis(const RotJob ja, const RotJo
   cp_async_wait_all();
 }
 
+// ---- rotate_rows<R>: the same product for shards of up to a few hundred rows per SM ---------------
+// At the C2 size a CTA owns ~140 rows: rotate_basis would run three 64-row tiles behind a serial prologue
+// (S, then the first tile).  Here a CTA takes its whole row range as tiles of 32 R rows (R rows per lane,
+// 8 R accumulators), and the loads of a tile are pipelined along the INNER dimension instead: S and Q are
+// fetched in four cp.async groups by ranges of i, and the FMA loop over the first range starts when that
+// group has landed while the other three are still in flight.  8 R DFMA per R + 4 shared loads.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+constexpr int RR_CHUNKS = 4;
+
+template <int R>
+__global__ void __launch_bounds__(512) rotate_rows(const RotJob ja, const RotJob jb, int nba, int ld, int m, int kc) {
+  const bool second = (int)blockIdx.x >= nba;
+  const RotJob& job = second ? jb : ja;
+  double* __restrict__ Q = job.Q;
+  const double* __restrict__ St = job.St;
+  double* __restrict__ out = job.out;
+  const int ldo = job.ldo;
+  const double* __restrict__ colscale = job.colscale;
+  const i64 bid = second ? blockIdx.x - nba : blockIdx.x;
+  const i64 nblk = second ? gridDim.x - nba : nba;
+  const i64 per = (job.rows + nblk - 1) / nblk;
+  const i64 lo = bid * per, hi = min(job.rows, lo + per);
+  constexpr int TR = 32 * R, RP = TR + 1;
+  extern __shared__ __align__(16) double sm[];
+  const int kcp = (kc + 7) & ~7;
+  double* Ssm = sm;                   // [m][kcp]
+  double* Qs = sm + (size_t)m * kcp;  // [m][RP], transposed tile
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nthr = blockDim.x;
+  bool s_loaded = false;
+  for (i64 row0 = lo; row0 < hi; row0 += TR) {
+    const int nrow = (int)min((i64)TR, hi - row0);
+    if (row0 != lo) __syncthreads();  // everybody is done with the previous tile
+#pragma unroll
+    for (int ch = 0; ch < RR_CHUNKS; ++ch) {
+      const int i0 = (m * ch) / RR_CHUNKS, w = (m * (ch + 1)) / RR_CHUNKS - i0;
+      if (!s_loaded)
+        for (int idx = threadIdx.x; idx < w * kcp / 2; idx += nthr)
+          cp_async16(Ssm + (size_t)i0 * kcp + 2 * idx, St + (size_t)i0 * kcp + 2 * idx);
+      for (int idx = threadIdx.x; idx < nrow * w; idx += nthr) {
+        const int r = idx / w, i = i0 + (idx - r * w);
+        cp_async8(Qs + (size_t)i * RP + r, Q + (size_t)(row0 + r) * ld + i);
+      }
+      cp_async_commit();
+    }
+    s_loaded = true;
+    double acc[R][8];
+#pragma unroll
+    for (int q = 0; q < R; ++q)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[q][c] = 0.0;
+    const double* qp = Qs + lane;
+    const double* sp = Ssm + warp * 8;
+#pragma unroll
+    for (int ch = 0; ch < RR_CHUNKS; ++ch) {
+      if (ch == 0) cp_async_wait<3>();
+      if (ch == 1) cp_async_wait<2>();
+      if (ch == 2) cp_async_wait<1>();
+      if (ch == 3) cp_async_wait<0>();
+      __syncthreads();
+      const int i0 = (m * ch) / RR_CHUNKS, i1 = (m * (ch + 1)) / RR_CHUNKS;
+#pragma unroll 2
+      for (int i = i0; i < i1; ++i) {
+        double x[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) x[q] = qp[(size_t)i * RP + 32 * q];
+        const double2 s0 = *reinterpret_cast<const double2*>(sp + (size_t)i * kcp);
+        const double2 s1 = *reinterpret_cast<const double2*>(sp + (size_t)i * kcp + 2);
+        const double2 s2 = *reinterpret_cast<const double2*>(sp + (size_t)i * kcp + 4);
+        const double2 s3 = *reinterpret_cast<const double2*>(sp + (size_t)i * kcp + 6);
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+          acc[q][0] = fma(x[q], s0.x, acc[q][0]);
+          acc[q][1] = fma(x[q], s0.y, acc[q][1]);
+          acc[q][2] = fma(x[q], s1.x, acc[q][2]);
+          acc[q][3] = fma(x[q], s1.y, acc[q][3]);
+          acc[q][4] = fma(x[q], s2.x, acc[q][4]);
+          acc[q][5] = fma(x[q], s2.y, acc[q][5]);
+          acc[q][6] = fma(x[q], s3.x, acc[q][6]);
+          acc[q][7] = fma(x[q], s3.y, acc[q][7]);
+        }
+      }
+    }
+    const bool vec = out == nullptr && warp * 8 + 8 <= kc;  // in place, full column group: 128-bit stores
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      const int r = lane + 32 * q;
+      if (r < nrow) {
+        if (vec) {
+          double2* dst = reinterpret_cast<double2*>(Q + (size_t)(row0 + r) * ld + warp * 8);
+          dst[0] = make_double2(acc[q][0], acc[q][1]);
+          dst[1] = make_double2(acc[q][2], acc[q][3]);
+          dst[2] = make_double2(acc[q][4], acc[q][5]);
+          dst[3] = make_double2(acc[q][6], acc[q][7]);
+        } else {
+          double* dst = out ? out + (size_t)(row0 + r) * ldo : Q + (size_t)(row0 + r) * ld;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int col = warp * 8 + c;
+            if (col < kc) dst[col] = colscale ? acc[q][c] * colscale[col] : acc[q][c];
+          }
+        }
+      }
+    }
+  }
+}
+using rotate_rows_fn = void (*)(const RotJob, const RotJob, int, int, int, int);
+static rotate_rows_fn rotate_rows_for(int R) {
+  switch (R) {
+    case 1: return rotate_rows<1>;
+    case 2: return rotate_rows<2>;
+    case 3: return rotate_rows<3>;
+    case 4: return rotate_rows<4>;
+    default: return rotate_rows<5>;
+  }
+}
+
 // ---- V[:,k] = F ; B = diag(sv[:k]) + R[:k] in column k  (irlb.py:239-244) ------------------------
 __global__ void set_restart(double* __restrict__ V, int ldv, int h, const double* __restrict__ fbuf,
                             double* __restrict__ B, int m, int k, const double* __restrict__ sv,
@@ -950,7 +1073,7 @@ static unsigned red_blocks(adobo_ctx* c, i64 rows) {  // 1024-thread CTAs of the
 struct IrlbWs {
   const void* sig_ptr[8] = {};
   i64 sig_n = -1;
-  int sig_i[5] = {};
+  int sig_i[6] = {};
   double sig_tol = 0;
   DevBuf<double> V, W, B, sc, tbuf, ybuf_h, ybuf_n, fbuf, xs, wcur, cvec, partials, Su, Sv, svd_s, R, murs, St;
   DevBuf<unsigned> counter;
@@ -990,14 +1113,17 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   IrlbWs& ws = *(IrlbWs*)c->irlb_ws;
   {
     const void* sp[8] = {A.rptr.p, A.cidx.p, A.rval.p, A.cptr.p, A.ridx.p, A.cval.p, mu, rs};
-    const int si[5] = {h, nu, m_b, c->world, (int)sizeof(VT)};
+    // test hooks read from the environment change what a captured iteration contains
+    const int hooks = (getenv("ADOBO_B200_SVD_JACOBI") ? 1 : 0) | (getenv("ADOBO_B200_NO_FORK") ? 2 : 0) |
+                      (getenv("ADOBO_B200_ROTATE_STREAMED") ? 4 : 0);
+    const int si[6] = {h, nu, m_b, c->world, (int)sizeof(VT), hooks};
     bool same = ws.sig_n == n && ws.sig_tol == tol;
     for (int q = 0; q < 8; ++q) same = same && ws.sig_ptr[q] == sp[q];
-    for (int q = 0; q < 5; ++q) same = same && ws.sig_i[q] == si[q];
+    for (int q = 0; q < 6; ++q) same = same && ws.sig_i[q] == si[q];
     if (!same) {
       ws.clear_graphs();
       for (int q = 0; q < 8; ++q) ws.sig_ptr[q] = sp[q];
-      for (int q = 0; q < 5; ++q) ws.sig_i[q] = si[q];
+      for (int q = 0; q < 6; ++q) ws.sig_i[q] = si[q];
       ws.sig_n = n;
       ws.sig_tol = tol;
     }
@@ -1058,6 +1184,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   DevBuf<double>& St = ws.St;
   // V[:, :kc] (or outv) = V Sv[:, :kc]  and  W[:, :kc] (or outw) = W Su[:, :kc], one launch each for the
   // transposes and for the two tall-skinny GEMMs
+  const bool rot_streamed = getenv("ADOBO_B200_ROTATE_STREAMED") != nullptr;  // test hook: force rotate_basis
   auto rotate2 = [&](int kc, double* outv, double* outw, int ldo, const double* scale_w) {
     const int kcp = (kc + 7) & ~7;
     LAUNCH(c, "transpose_s", (transpose_s<<<(2 * m_b * kcp + 255) / 256, 256, 0, st>>>(Sv.p, Su.p, m_b, kc, kcp, St.p)));
@@ -1070,8 +1197,22 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     const i64 bw = std::max<i64>(1, std::min<i64>(tw, sms - bv));
     const unsigned nbv = (unsigned)bv, nbw = (unsigned)bw;
     WORK(c, 8.0 * (n + h) * (m_b + kc));
-    LAUNCH(c, "rotate_basis", (rotate_basis<<<nbv + nbw, 32 * (kcp / 8), rot_smem, st>>>(jv, jw, (int)nbv, ld, m_b, kc,
-                                                                                   rot_nbuf)));
+    // few tiles per SM: rotate_rows (row range per CTA, loads pipelined along the inner dimension);
+    // long shards: rotate_basis (64-row tiles streamed through a double buffer)
+    const i64 per = std::max<i64>(((i64)h + bv - 1) / bv, (n + bw - 1) / bw);  // rows per CTA
+    const size_t s_bytes = sizeof(double) * (size_t)m_b * kcp;
+    const int r_fit = (int)std::min<i64>(5, (((i64)(225 * 1024 - s_bytes) / (8 * m_b)) - 1) / 32);
+    if (!rot_streamed && r_fit >= 1 && per <= 2 * 32 * r_fit) {
+      const i64 ntile = (per + 32 * r_fit - 1) / (32 * r_fit);
+      const int Rr = (int)std::min<i64>(r_fit, ((per + ntile - 1) / ntile + 31) / 32);
+      const size_t smem = s_bytes + sizeof(double) * (size_t)m_b * (32 * Rr + 1);
+      rotate_rows_fn fn = rotate_rows_for(Rr);
+      CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      LAUNCH(c, "rotate_basis", (fn<<<nbv + nbw, 32 * (kcp / 8), smem, st>>>(jv, jw, (int)nbv, ld, m_b, kc)));
+    } else {
+      LAUNCH(c, "rotate_basis", (rotate_basis<<<nbv + nbw, 32 * (kcp / 8), rot_smem, st>>>(jv, jw, (int)nbv, ld, m_b, kc,
+                                                                                     rot_nbuf)));
+    }
   };
   const bool use_arrow = getenv("ADOBO_B200_SVD_JACOBI") == nullptr;
   const bool force_fallback = getenv("ADOBO_B200_SVD_FORCE_FALLBACK") != nullptr;  // test hook
