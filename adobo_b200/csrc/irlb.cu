@@ -24,6 +24,7 @@ bool svd_arrow_supported(int m, int k);
 void svd_arrow_prepare(int m);
 void launch_svd_arrow(adobo_ctx* c, const double* B, int m, int k, double* Su, double* sv, double* Sv, int* info,
                       cudaStream_t st);
+int svd_arrow_cluster();
 
 enum { SC_S = 0, SC_FN, SC_FNINV, SC_SU, SC_MVS, SC_SMAX, SC_NRM2, SC_AUX, SC_COUNT = 16 };
 constexpr int MAXB = 128;  // widest basis the dot kernels handle (4 columns per lane)
@@ -463,42 +464,6 @@ __global__ void w_finish(const double* __restrict__ ybuf, double* __restrict__ s
 // ones the restart uses: k <= m - 3).  Outputs column-major, singular values descending.
 constexpr int JL = 16;        // lanes per block pair
 constexpr int JTHREADS = 512; // 32 groups >= 128 / 4 block pairs
-
-// (c, s) of the Jacobi rotation that orthogonalises two columns with squared norms nx, ny and inner
-// product ga; identity when the pair is already orthogonal to 1e-15.  The angle comes from fp32
-// arithmetic (the fp64 test decides when to stop, so fp32 only costs an occasional extra rotation);
-// (c, s) is then renormalised in fp64 so that the rotation is orthogonal to working precision.
-// Straight-line code: two independent calls interleave in the instruction stream.
-__device__ __forceinline__ float rsqrt_approx(float x) {  // one MUFU.RSQ, no denormal fix-up
-  float y;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ int jacobi_angle(double ga, double nx, double ny, double& cs, double& sn) {
-  const double g2 = ga * ga, ab = nx * ny;
-  const bool rot = g2 > 1e-30 * ab;
-  const float d32 = (float)(ny - nx), g32 = (float)ga;
-  const float h2 = fmaf(d32, d32, 4.0f * g32 * g32);
-  const float rh = rsqrt_approx(h2);                           // 1 / hypot(d, 2 gamma)
-  const float c2 = fmaf(0.5f * fabsf(d32), rh, 0.5f);          // cos^2 of the rotation angle
-  const float rc = rsqrt_approx(c2);
-  double c = (double)(c2 * rc), s_ = (double)((d32 >= 0.0f ? g32 : -g32) * rh * rc);
-  if (rot && !(h2 > 1e-30f && h2 < 1e30f)) {  // fp32 range exhausted (wildly different norms): fp64 angle
-    const double d = ny - nx;
-    const double rhd = rsqrt(fma(d, d, 4.0 * g2));
-    const double c2d = fma(0.5 * fabs(d), rhd, 0.5);
-    const double rcd = rsqrt(c2d);
-    c = c2d * rcd;
-    s_ = (d >= 0 ? ga : -ga) * rhd * rcd;
-  }
-  // renormalise: y = rsqrt(c^2 + s^2), two Newton steps from 1 (c^2 + s^2 = 1 +- 1e-6)
-  const double w = fma(c, c, s_ * s_);
-  double y = fma(-0.5, w, 1.5);
-  y = y * fma(-0.5 * w, y * y, 1.5);
-  cs = rot ? c * y : 1.0;
-  sn = rot ? s_ * y : 0.0;
-  return rot ? ((g2 > 1e-16 * ab) ? 3 : 1) : 0;
-}
 
 // two independent rotations (x0,y0) and (x1,y1), interleaved; columns are H double2 per lane, the
 // cached squared norms are updated in place; returns the OR of the convergence flags
@@ -1115,7 +1080,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     const void* sp[8] = {A.rptr.p, A.cidx.p, A.rval.p, A.cptr.p, A.ridx.p, A.cval.p, mu, rs};
     // test hooks read from the environment change what a captured iteration contains
     const int hooks = (getenv("ADOBO_B200_SVD_JACOBI") ? 1 : 0) | (getenv("ADOBO_B200_NO_FORK") ? 2 : 0) |
-                      (getenv("ADOBO_B200_ROTATE_STREAMED") ? 4 : 0);
+                      (getenv("ADOBO_B200_ROTATE_STREAMED") ? 4 : 0) | (svd_arrow_cluster() << 4);
     const int si[6] = {h, nu, m_b, c->world, (int)sizeof(VT), hooks};
     bool same = ws.sig_n == n && ws.sig_tol == tol;
     for (int q = 0; q < 8; ++q) same = same && ws.sig_ptr[q] == sp[q];
