@@ -13,11 +13,14 @@
 //
 // Reductions are two-stage and ordered (per-CTA partials, summed by the last CTA to finish), so
 // a given shard layout gives bit-identical results run to run.
+#include <cooperative_groups.h>
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
 
 namespace adobo {
+namespace cg = cooperative_groups;
 
 // svd_arrow.cu: structured SVD of the restarted B (diag + spike + bidiagonal tail)
 bool svd_arrow_supported(int m, int k);
@@ -194,15 +197,36 @@ __device__ __forceinline__ void finish_in_last_cta(const Finish& f, const double
 }
 
 // ---- K5  A^T u on the CSC copy: one CTA per gene column ---------------------------------------
+// With `wf.W != nullptr` the kernel also does the work of w_finish for the column of W it consumes: u = ybuf / ||w||
+// is applied as one factor on the finished sum (A^T is linear), and CTA `col` stores its slice of W[:, jn].
+struct WFinish {
+  double* W = nullptr;  // nullptr: u is already normalised (w_finish ran)
+  int ldw = 0, jn = 0, m_b = 0;
+  i64 n = 0;
+  double* sc = nullptr;
+  double* B = nullptr;
+};
 template <typename VT>
 __global__ void __launch_bounds__(256) spmvT_csc(const i64* __restrict__ cptr, const int* __restrict__ ridx,
                                                  const VT* __restrict__ cval, const double* __restrict__ u,
                                                  double* __restrict__ t, int h, unsigned* __restrict__ counter,
-                                                 const PeerComm pc) {
+                                                 const PeerComm pc, const WFinish wf) {
   __shared__ double red[8];
   __shared__ bool last_cta;
   const int col = blockIdx.x;
   const i64 b = cptr[col], e1 = cptr[col + 1];
+  double sinv = 1.0;
+  if (wf.W) {
+    const double nrm = sqrt(wf.sc[SC_NRM2]);
+    sinv = inv_or_zero(nrm);
+    const i64 chunk = (wf.n + gridDim.x - 1) / gridDim.x, lo = (i64)col * chunk, hi = min(wf.n, lo + chunk);
+    for (i64 r = lo + threadIdx.x; r < hi; r += 256) wf.W[(size_t)r * wf.ldw + wf.jn] = sinv * u[r];
+    if (col == 0 && threadIdx.x == 0) {
+      wf.sc[SC_S] = nrm;
+      wf.sc[SC_SU] = sinv * wf.sc[SC_AUX];
+      wf.B[(size_t)wf.jn * wf.m_b + wf.jn] = nrm;  // irlb.py:196 / 221
+    }
+  }
   double s = 0;
 #pragma unroll 4
   for (i64 e = b + threadIdx.x; e < e1; e += 256) s += (double)__ldg(cval + e) * u[__ldg(ridx + e)];
@@ -213,7 +237,7 @@ __global__ void __launch_bounds__(256) spmvT_csc(const i64* __restrict__ cptr, c
     double tt = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) tt += red[w];
-    t[col] = tt;
+    t[col] = tt * sinv;
   }
   if (pc.world > 1) {  // the last column CTA to finish sums t over ranks (fused NVLink exchange)
     if (threadIdx.x == 0) {
@@ -267,21 +291,37 @@ __global__ void __launch_bounds__(RT_THREADS, 1) spmv_dots_w32(const i64* __rest
   const i64 warps = ((i64)gridDim.x * blockDim.x) >> 5;
   const double mvs = sc[SC_MVS], fn = sc[SC_FN];
   double acc[4] = {0, 0, 0, 0};
-  for (i64 r = (((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < n; r += warps) {
-    const i64 b = rptr[r], e1 = rptr[r + 1];
+  // a warp takes ~4 rows one after the other and every row is a chain of dependent loads (row pointers ->
+  // entries -> gather): the next row's pointers and this row's slice of W are requested before the chain starts
+  i64 r = (((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  i64 b = 0, e1 = 0;
+  if (r < n) {
+    b = __ldg(rptr + r);
+    e1 = __ldg(rptr + r + 1);
+  }
+  for (; r < n; r += warps) {
+    const i64 rn = r + warps;
+    i64 nb = 0, ne = 0;
+    if (rn < n) {
+      nb = __ldg(rptr + rn);
+      ne = __ldg(rptr + rn + 1);
+    }
+    const double* wr = W + (size_t)r * ldw;
+    double wv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) wv[q] = (lane + 32 * q < nd) ? wr[lane + 32 * q] : 0.0;
+    const double wp = (jprev >= 0) ? wr[jprev] : 0.0;
     double a = 0;
 #pragma unroll 4
     for (i64 e = b + lane; e < e1; e += 32) a += (double)__ldg(rval + e) * xs[__ldg(cidx + e)];
     a = warp_sum(a);
-    const double* wr = W + (size_t)r * ldw;
     double w = a - mvs;
-    if (jprev >= 0) w -= fn * wr[jprev];
+    if (jprev >= 0) w -= fn * wp;
     if (lane == 0) ybuf[r] = w;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int col = lane + 32 * q;
-      if (col < nd) acc[q] += wr[col] * w;
-    }
+    for (int q = 0; q < 4; ++q) acc[q] += wv[q] * w;
+    b = nb;
+    e1 = ne;
   }
   if (nd > 0) reduce_vec_blocks(acc, nd, partials, cvec, counter, pc);
 }
@@ -345,22 +385,39 @@ __global__ void __launch_bounds__(RT_THREADS, 1) update_norm_w32(const double* _
 #pragma unroll
   for (int q = 0; q < 4; ++q) creg[q] = (lane + 32 * q < nd) ? cvec[lane + 32 * q] : 0.0;
   double n2 = 0, ax = 0;
-  for (i64 r = (((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < rows; r += warps) {
-    double y = ybuf[r];
+  // two rows per trip: their loads and the two warp reductions overlap (same summation order as one by one)
+  for (i64 r = (((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < rows; r += 2 * warps) {
+    const i64 r2 = r + warps;
+    const bool two = r2 < rows;
+    double y0 = ybuf[r], y1 = two ? ybuf[r2] : 0.0;
+    const double c0 = coef ? coef[r] : 1.0, c1 = (coef && two) ? coef[r2] : 1.0;
     if (nd > 0) {
-      const double* qr = Q + (size_t)r * ld;
-      double p = 0;
+      const double* q0 = Q + (size_t)r * ld;
+      const double* q1 = Q + (size_t)(two ? r2 : r) * ld;
+      double p0 = 0, p1 = 0;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int col = lane + 32 * q;
-        if (col < nd) p += qr[col] * creg[q];
+        if (col < nd) {
+          p0 += q0[col] * creg[q];
+          p1 += q1[col] * creg[q];
+        }
       }
-      p = warp_sum(p);
-      y -= p;
-      if (lane == 0) ybuf[r] = y;
+      p0 = warp_sum(p0);
+      p1 = warp_sum(p1);
+      y0 -= p0;
+      y1 -= p1;
+      if (lane == 0) {
+        ybuf[r] = y0;
+        if (two) ybuf[r2] = y1;
+      }
     }
-    n2 += y * y;
-    ax += (coef ? coef[r] : 1.0) * y;
+    n2 += y0 * y0;
+    ax += c0 * y0;
+    if (two) {
+      n2 += y1 * y1;
+      ax += c1 * y1;
+    }
   }
   const bool last = reduce_two_blocks(n2, ax, partials, out2, counter, pc);
   if (last && fin.kind) finish_in_last_cta(fin, ybuf, rows);
@@ -406,6 +463,145 @@ __global__ void __launch_bounds__(RT_THREADS, 1) update_norm(const double* __res
   ax += __shfl_xor_sync(0xffffffffu, ax, 8);
   ax += __shfl_xor_sync(0xffffffffu, ax, 16);
   reduce_two_blocks(n2, ax, partials, out2, counter, pc);
+}
+
+// ---- v_step: the whole V side of a Lanczos step in ONE launch on a thread-block cluster -----------
+// F = A_s^T w - s V[:, j]  (from t = A^T w),  c = V[:, :j+1]^T F,  F -= V c,  ||F||, mu.F,  V[:, j+1] = F / ||F||,
+// x = F / (||F|| sigma)   (irlb.py:185-197, 203-221).  V has only h ~ 1000 rows: v_prep_dots + update_norm + v_finish
+// spend their time in three launches and two cross-CTA reductions through global memory.  Here eight CTAs of a
+// cluster take h/8 rows each and reduce through DISTRIBUTED SHARED MEMORY: every CTA pushes its partial
+// dot products (then its two partial norms) into the shared memory of all eight, one cluster barrier, and every
+// CTA sums the eight partials in the same order -- bitwise the same c and ||F|| everywhere, no atomics.
+constexpr int VS_THREADS = 1024, VS_WARPS = VS_THREADS / 32, VS_CLUSTER = 8, VS_ROWS = 4;
+
+template <int NQ>  // columns per lane: 3 (m_b <= 96) or 4
+__global__ void __launch_bounds__(VS_THREADS, 1)
+    v_step(const double* __restrict__ t, const double* __restrict__ mu, const double* __restrict__ rs,
+           const double* __restrict__ murs, double* __restrict__ sc, double* __restrict__ V, int ldv, int j, int m_b, int h,
+           double* __restrict__ ybuf, double* __restrict__ fbuf, double* __restrict__ xs, double* __restrict__ B) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
+  cluster.barrier_arrive();  // matched below, before the first write into a neighbour's shared memory
+  __shared__ double wacc[VS_WARPS][MAXB];
+  __shared__ double call[VS_CLUSTER][MAXB];  // partial dot products of every CTA of the cluster
+  __shared__ double ctot[MAXB];
+  __shared__ double red2[VS_WARPS][2];
+  __shared__ double nall[VS_CLUSTER][2];  // partial (||F||^2, mu.F) of every CTA
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nd = j + 1;
+  const int per = (h + csize - 1) / csize;
+  const int r0 = crank * per, r1 = min(h, r0 + per);
+  const double s = sc[SC_S], su = sc[SC_SU];
+  // phase A: F = prep(t), partial c.  Rows go to warps in batches of VS_ROWS independent rows so that their
+  // loads (and, in phase B, their warp reductions) are in flight together.
+  double acc[NQ] = {};
+  for (int rb = r0 + warp; rb < r1; rb += VS_WARPS * VS_ROWS) {
+    double f[VS_ROWS], vj[VS_ROWS], vq[VS_ROWS][NQ];
+#pragma unroll
+    for (int i = 0; i < VS_ROWS; ++i) {
+      const int r = rb + i * VS_WARPS;
+      const bool ok = r < r1;
+      const double* vr = V + (size_t)(ok ? r : r0) * ldv;
+      f[i] = ok ? t[r] : 0.0;
+      if (mu) f[i] = ok ? (f[i] - mu[r] * su) * rs[r] : 0.0;
+      vj[i] = ok ? vr[j] : 0.0;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) vq[i][q] = (ok && lane + 32 * q < nd) ? vr[lane + 32 * q] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < VS_ROWS; ++i) {
+      const int r = rb + i * VS_WARPS;
+      f[i] -= s * vj[i];
+      if (lane == 0 && r < r1) ybuf[r] = f[i];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) acc[q] += vq[i][q] * f[i];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+    if (lane + 32 * q < MAXB) wacc[warp][lane + 32 * q] = acc[q];
+  __syncthreads();
+  cluster.barrier_wait();  // every CTA of the cluster is running
+  if (tid < nd) {
+    double p = 0;
+#pragma unroll 8
+    for (int w = 0; w < VS_WARPS; ++w) p += wacc[w][tid];
+    for (int q = 0; q < csize; ++q) cluster.map_shared_rank(&call[0][0], q)[crank * MAXB + tid] = p;
+  }
+  cluster.sync();
+  if (tid < nd) {
+    double p = 0;
+    for (int q = 0; q < csize; ++q) p += call[q][tid];
+    ctot[tid] = p;
+  }
+  __syncthreads();
+  // phase B: F -= V c, partial ||F||^2 and mu.F
+  double creg[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) creg[q] = (lane + 32 * q < nd) ? ctot[lane + 32 * q] : 0.0;
+  double n2 = 0, ax = 0;
+  for (int rb = r0 + warp; rb < r1; rb += VS_WARPS * VS_ROWS) {
+    double p[VS_ROWS], y[VS_ROWS], cf[VS_ROWS];
+#pragma unroll
+    for (int i = 0; i < VS_ROWS; ++i) {
+      const int r = rb + i * VS_WARPS;
+      const bool ok = r < r1;
+      const double* vr = V + (size_t)(ok ? r : r0) * ldv;
+      p[i] = 0;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int col = lane + 32 * q;
+        if (ok && col < nd) p[i] += vr[col] * creg[q];
+      }
+      y[i] = ok ? __ldcg(ybuf + r) : 0.0;
+      cf[i] = (ok && murs) ? murs[r] : (ok ? 1.0 : 0.0);
+    }
+#pragma unroll
+    for (int i = 0; i < VS_ROWS; ++i) p[i] = warp_sum(p[i]);
+#pragma unroll
+    for (int i = 0; i < VS_ROWS; ++i) {
+      const int r = rb + i * VS_WARPS;
+      y[i] -= p[i];
+      if (lane == 0 && r < r1) ybuf[r] = y[i];
+      n2 += y[i] * y[i];
+      ax += cf[i] * y[i];
+    }
+  }
+  if (lane == 0) {
+    red2[warp][0] = n2;
+    red2[warp][1] = ax;
+  }
+  __syncthreads();
+  if (tid < 2) {
+    double p = 0;
+#pragma unroll 8
+    for (int w = 0; w < VS_WARPS; ++w) p += red2[w][tid];
+    for (int q = 0; q < csize; ++q) cluster.map_shared_rank(&nall[0][0], q)[crank * 2 + tid] = p;
+  }
+  cluster.sync();  // also orders this CTA's ybuf writes before its own reads below
+  double tot0 = 0, tot1 = 0;
+  for (int q = 0; q < csize; ++q) {
+    tot0 += nall[q][0];
+    tot1 += nall[q][1];
+  }
+  // finish: V[:, j+1] = F / ||F||, x = F / (||F|| sigma)
+  const double nrm = sqrt(tot0);
+  const double inv = inv_or_zero(nrm);
+  const int jn = j + 1;
+  for (int r = r0 + tid; r < r1; r += VS_THREADS) {
+    const double v = inv * __ldcg(ybuf + r);
+    fbuf[r] = v;
+    if (jn < m_b) V[(size_t)r * ldv + jn] = v;
+    xs[r] = rs ? v * rs[r] : v;
+  }
+  if (crank == 0 && tid == 0) {
+    sc[SC_NRM2] = tot0;
+    sc[SC_AUX] = tot1;
+    sc[SC_FN] = nrm;
+    sc[SC_FNINV] = inv;
+    sc[SC_MVS] = murs ? inv * tot1 : 0.0;
+    if (j < m_b - 1) B[(size_t)j * m_b + j + 1] = nrm;  // irlb.py:197
+  }
 }
 
 // ---- normalise F, store V[:, jn], prepare x = F / sigma and mu.x, write B[j,j], B[j,j+1] ---------
@@ -1080,7 +1276,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     const void* sp[8] = {A.rptr.p, A.cidx.p, A.rval.p, A.cptr.p, A.ridx.p, A.cval.p, mu, rs};
     // test hooks read from the environment change what a captured iteration contains
     const int hooks = (getenv("ADOBO_B200_SVD_JACOBI") ? 1 : 0) | (getenv("ADOBO_B200_NO_FORK") ? 2 : 0) |
-                      (getenv("ADOBO_B200_ROTATE_STREAMED") ? 4 : 0) | (svd_arrow_cluster() << 4);
+                      (getenv("ADOBO_B200_ROTATE_STREAMED") ? 4 : 0) | (getenv("ADOBO_B200_NO_VSTEP") ? 8 : 0) | (getenv("ADOBO_B200_NO_WFOLD") ? 1024 : 0) | (svd_arrow_cluster() << 4);
     const int si[6] = {h, nu, m_b, c->world, (int)sizeof(VT), hooks};
     bool same = ws.sig_n == n && ws.sig_tol == tol;
     for (int q = 0; q < 8; ++q) same = same && ws.sig_ptr[q] == sp[q];
@@ -1195,6 +1391,9 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   // the finish step (normalise + store) runs in the last CTA of the norm reduction when one CTA can do it
   // in about a launch latency; larger vectors keep the separate grid-wide kernels
   const bool fold_v = h <= 16384, fold_w = !wide_rows && n <= 8192 && !(c->world > 1 && !fused);
+  // otherwise the W finish rides in the spmvT_csc that consumes the column -- except for the last column, whose
+  // norm completes B for the SVD that is forked off before that spmvT_csc
+  const bool fold_wt = !fold_w && getenv("ADOBO_B200_NO_WFOLD") == nullptr;
   auto v_fin = [&](int jn, int j) {
     Finish f;
     if (!fold_v) return f;
@@ -1240,7 +1439,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
                                                                     partials.p, sc.p + SC_NRM2, counter.p, pcw,
                                                                     w_fin(jn))));
     if (!fused) allreduce_sum_f64(c, sc.p + SC_NRM2, 2);
-    if (wide_rows || !fold_w) LAUNCH(c, "w_finish", (w_finish<<<fin_n, 256, 0, st>>>(ybuf_n.p, sc.p, W.p, ld, jn, n, wcur.p, B.p,
+    if ((wide_rows || !fold_w) && !(fold_wt && jn != m_b - 1)) LAUNCH(c, "w_finish", (w_finish<<<fin_n, 256, 0, st>>>(ybuf_n.p, sc.p, W.p, ld, jn, n, wcur.p, B.p,
                                                                                        m_b)));
   };
   // restart update (irlb.py:238-246): Ritz vectors into the leading k columns, V[:,k] = F, new B
@@ -1261,6 +1460,8 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
       LAUNCH(c, "jacobi_svd", (jacobi<<<1, JTHREADS, svd_smem, s>>>(B.p, m_b, Su.p, svd_s.p, Sv.p, info.p)));
   };
   const bool fork_svd = use_graphs && getenv("ADOBO_B200_NO_FORK") == nullptr;
+  // V side of a step as one cluster kernel (short V), or three grid-wide kernels (very long V)
+  const bool use_vstep = h <= 8192 && getenv("ADOBO_B200_NO_VSTEP") == nullptr;
   auto enqueue_iteration = [&](bool first, int k) {
     if (!first) restart_update(k);
     int j = first ? 0 : k;
@@ -1273,19 +1474,43 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
         CUDA_CHECK(cudaEventRecord(c->join_ev, c->side));
       }
       WORK(c, (double)A.nnz * (4.0 + sizeof(VT)) + 8.0 * (h + 1) + 8.0 * h + 8.0 * n);
-      LAUNCH(c, "spmvT_csc", (spmvT_csc<VT><<<h, 256, 0, st>>>(A.cptr.p, A.ridx.p, A.cval.p, wcur.p, tbuf.p, h, counter.p + 1,
-                                                               fused_t ? pcw : pc1)));
+      {
+        // column j of W arrives normalised (w_finish / folded finish) or as ybuf + ||w||^2 (finish folded in here)
+        WFinish wf;
+        const bool infold = fold_wt && j != m_b - 1;
+        if (infold) wf.W = W.p, wf.ldw = ld, wf.jn = j, wf.m_b = m_b, wf.n = n, wf.sc = sc.p, wf.B = B.p;
+        LAUNCH(c, "spmvT_csc", (spmvT_csc<VT><<<h, 256, 0, st>>>(A.cptr.p, A.ridx.p, A.cval.p, infold ? ybuf_n.p : wcur.p, tbuf.p,
+                                                                 h, counter.p + 1, fused_t ? pcw : pc1, wf)));
+      }
       if (!fused_t) allreduce_sum_f64(c, tbuf.p, (size_t)h);
-      WORK(c, 8.0 * h * (j + 1 + 4));
-      LAUNCH(c, "v_prep_dots", (v_prep_dots<<<gb_h, RT_THREADS, 0, st>>>(tbuf.p, mu, rs, sc.p, V.p, ld, j, j + 1, h, ybuf_h.p,
-                                                                partials.p, cvec.p, counter.p)));
-      WORK(c, 8.0 * h * (j + 1 + 3));
-      LAUNCH(c, "update_norm_v", (update_norm_w32<<<gb_h, RT_THREADS, 0, st>>>(V.p, ld, j + 1, cvec.p, ybuf_h.p,
-                                                                centered ? murs.p : nullptr, h, partials.p,
-                                                                sc.p + SC_NRM2, counter.p, pc1, v_fin(j + 1, j))));
-      if (!fold_v)
-        LAUNCH(c, "v_finish", (v_finish<<<fin_h, 256, 0, st>>>(ybuf_h.p, rs, sc.p, V.p, ld, j + 1, m_b, h, fbuf.p, xs.p,
-                                                             B.p, j, centered ? 1 : 0)));
+      if (use_vstep) {
+        WORK(c, 8.0 * h * (2.0 * (j + 1) + 8));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(VS_CLUSTER);
+        cfg.blockDim = dim3(VS_THREADS);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = VS_CLUSTER;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        LAUNCH(c, "v_step", CUDA_CHECK(cudaLaunchKernelEx(&cfg, m_b <= 96 ? v_step<3> : v_step<4>, (const double*)tbuf.p, mu, rs,
+                                                           (const double*)(centered ? murs.p : nullptr), sc.p, V.p, ld, j,
+                                                           m_b, h, ybuf_h.p, fbuf.p, xs.p, B.p)));
+      } else {
+        WORK(c, 8.0 * h * (j + 1 + 4));
+        LAUNCH(c, "v_prep_dots", (v_prep_dots<<<gb_h, RT_THREADS, 0, st>>>(tbuf.p, mu, rs, sc.p, V.p, ld, j, j + 1, h, ybuf_h.p,
+                                                                  partials.p, cvec.p, counter.p)));
+        WORK(c, 8.0 * h * (j + 1 + 3));
+        LAUNCH(c, "update_norm_v", (update_norm_w32<<<gb_h, RT_THREADS, 0, st>>>(V.p, ld, j + 1, cvec.p, ybuf_h.p,
+                                                                  centered ? murs.p : nullptr, h, partials.p,
+                                                                  sc.p + SC_NRM2, counter.p, pc1, v_fin(j + 1, j))));
+        if (!fold_v)
+          LAUNCH(c, "v_finish", (v_finish<<<fin_h, 256, 0, st>>>(ybuf_h.p, rs, sc.p, V.p, ld, j + 1, m_b, h, fbuf.p, xs.p,
+                                                               B.p, j, centered ? 1 : 0)));
+      }
       if (j < m_b - 1) w_column(j, j + 1, j + 1);
       ++j;
     }
@@ -1341,6 +1566,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   };
 
   IrlbResult res;
+  const bool trace = getenv("ADOBO_B200_IRLB_TRACE") != nullptr;  // diagnostic: one line per outer iteration
   int it = 0, k = nu, nmult = 0;
   bool converged = false;
   while (it < maxit) {
@@ -1351,6 +1577,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
       svd_fallback(it == 0, k);
       ++res.svd_fallbacks;
     }
+    if (trace) fprintf(stderr, "irlb it=%d k=%d conv=%d next_k=%d\n", it, k, h_info[0], h_info[1]);
     if (h_info[0] >= nu) {  // irlb.py:232-236
       converged = true;
       break;
