@@ -205,6 +205,7 @@ struct WFinish {
   i64 n = 0;
   double* sc = nullptr;
   double* B = nullptr;
+  const double* n2p = nullptr;  // (||w||^2, sum w) of the column: sc + SC_NRM2, or the tail of w_step's vector
 };
 template <typename VT>
 __global__ void __launch_bounds__(256) spmvT_csc(const i64* __restrict__ cptr, const int* __restrict__ ridx,
@@ -217,13 +218,13 @@ __global__ void __launch_bounds__(256) spmvT_csc(const i64* __restrict__ cptr, c
   const i64 b = cptr[col], e1 = cptr[col + 1];
   double sinv = 1.0;
   if (wf.W) {
-    const double nrm = sqrt(wf.sc[SC_NRM2]);
+    const double nrm = sqrt(wf.n2p[0]);
     sinv = inv_or_zero(nrm);
     const i64 chunk = (wf.n + gridDim.x - 1) / gridDim.x, lo = (i64)col * chunk, hi = min(wf.n, lo + chunk);
     for (i64 r = lo + threadIdx.x; r < hi; r += 256) wf.W[(size_t)r * wf.ldw + wf.jn] = sinv * u[r];
     if (col == 0 && threadIdx.x == 0) {
       wf.sc[SC_S] = nrm;
-      wf.sc[SC_SU] = sinv * wf.sc[SC_AUX];
+      wf.sc[SC_SU] = sinv * wf.n2p[1];
       wf.B[(size_t)wf.jn * wf.m_b + wf.jn] = nrm;  // irlb.py:196 / 221
     }
   }
@@ -465,6 +466,74 @@ __global__ void __launch_bounds__(RT_THREADS, 1) update_norm(const double* __res
   reduce_two_blocks(n2, ax, partials, out2, counter, pc);
 }
 
+// ---- w_step: the whole W side of a Lanczos step in ONE pass over W ---------------------------------
+// The reference forms w = A_s x - fn w_prev, THEN the Gram-Schmidt coefficients c = W^T w, THEN w - W c
+// (irlb.py:204-216): two passes over W with a grid-wide reduction between them.  But
+//     W^T (A_s x - fn w_prev) = Z^T xs - mvs (W^T 1) - fn (W^T w_prev),       Z = A^T W  (h x m_b),
+// and every column of Z is the vector t = A^T w_j that spmvT_csc computes anyway for the V side, W^T 1 are the
+// column sums the finish step already has, and W^T w_prev is a by-product of the pass that produced w_prev (g
+// below).  So c is known BEFORE the pass (v_step computes it from Z, h ~ 1000 rows) and the W side is one kernel:
+//     y_r = (A xs)_r - mvs - fn W[r, jprev] - sum_c W[r, c] c_c,
+// with one reduction of the vector (g = W^T y, ||y||^2, sum y).  Same arithmetic as the reference up to rounding
+// (no orthogonality of W is assumed: g carries the actual W^T w_prev); Z is rotated with W at a restart.
+template <typename VT>
+__global__ void __launch_bounds__(RT_THREADS, 1)
+    w_step(const i64* __restrict__ rptr, const int* __restrict__ cidx, const VT* __restrict__ rval,
+           const double* __restrict__ xs, const double* __restrict__ sc, const double* __restrict__ W, int ldw, int jprev,
+           int nd, i64 n, const double* __restrict__ cvec, double* __restrict__ ybuf, double* __restrict__ partials,
+           double* __restrict__ gout, unsigned* __restrict__ counter, const PeerComm pc) {
+  const int lane = threadIdx.x & 31;
+  const i64 warps = ((i64)gridDim.x * blockDim.x) >> 5;
+  const double mvs = sc[SC_MVS], fn = sc[SC_FN];
+  double creg[4], acc[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) creg[q] = (lane + 32 * q < nd) ? cvec[lane + 32 * q] : 0.0;
+  double n2 = 0, ax = 0;
+  i64 r = (((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  i64 b = 0, e1 = 0;
+  if (r < n) {
+    b = __ldg(rptr + r);
+    e1 = __ldg(rptr + r + 1);
+  }
+  for (; r < n; r += warps) {
+    const i64 rn = r + warps;
+    i64 nb = 0, ne = 0;
+    if (rn < n) {  // next row's pointers, requested before this row's chain of dependent loads
+      nb = __ldg(rptr + rn);
+      ne = __ldg(rptr + rn + 1);
+    }
+    const double* wr = W + (size_t)r * ldw;
+    double wv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) wv[q] = (lane + 32 * q < nd) ? wr[lane + 32 * q] : 0.0;
+    const double wp = (jprev >= 0) ? wr[jprev] : 0.0;
+    double a = 0;
+#pragma unroll 4
+    for (i64 e = b + lane; e < e1; e += 32) a += (double)__ldg(rval + e) * xs[__ldg(cidx + e)];
+    double p = (wv[0] * creg[0] + wv[1] * creg[1]) + (wv[2] * creg[2] + wv[3] * creg[3]);
+    a = warp_sum(a);
+    p = warp_sum(p);
+    double w = a - mvs;
+    if (jprev >= 0) w -= fn * wp;
+    w -= p;
+    if (lane == 0) ybuf[r] = w;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] += wv[q] * w;
+    n2 += w * w;
+    ax += w;
+    b = nb;
+    e1 = ne;
+  }
+  // the two scalars ride in columns nd, nd + 1 of the vector (w is warp-uniform: one lane deposits them)
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int col = lane + 32 * q;
+    if (col == nd) acc[q] = n2;
+    if (col == nd + 1) acc[q] = ax;
+  }
+  reduce_vec_blocks(acc, nd + 2, partials, gout, counter, pc);
+}
+
 // ---- v_step: the whole V side of a Lanczos step in ONE launch on a thread-block cluster -----------
 // F = A_s^T w - s V[:, j]  (from t = A^T w),  c = V[:, :j+1]^T F,  F -= V c,  ||F||, mu.F,  V[:, j+1] = F / ||F||,
 // x = F / (||F|| sigma)   (irlb.py:185-197, 203-221).  V has only h ~ 1000 rows: v_prep_dots + update_norm + v_finish
@@ -474,16 +543,28 @@ __global__ void __launch_bounds__(RT_THREADS, 1) update_norm(const double* __res
 // CTA sums the eight partials in the same order -- bitwise the same c and ||F|| everywhere, no atomics.
 constexpr int VS_THREADS = 1024, VS_WARPS = VS_THREADS / 32, VS_CLUSTER = 8, VS_ROWS = 4;
 
+// Z formulation (see w_step): the kernel also stores Z[:, j] = t and leaves the Gram-Schmidt coefficients of
+// the NEXT W column in cvec:  c = Z[:, :ncc]^T xs - mvs sumW - [prev] fn g,  g = W^T w_j from w_step's vector.
+struct ZArgs {
+  double* Z = nullptr;  // h x ldv; nullptr: formulation off
+  double* sumW = nullptr;
+  const double* gprev = nullptr;  // w_step output for column j: W^T y (j values), ||y||^2, sum y
+  double* cvec = nullptr;
+  int ncc = 0, prev = 0;
+};
 template <int NQ>  // columns per lane: 3 (m_b <= 96) or 4
 __global__ void __launch_bounds__(VS_THREADS, 1)
     v_step(const double* __restrict__ t, const double* __restrict__ mu, const double* __restrict__ rs,
            const double* __restrict__ murs, double* __restrict__ sc, double* __restrict__ V, int ldv, int j, int m_b, int h,
-           double* __restrict__ ybuf, double* __restrict__ fbuf, double* __restrict__ xs, double* __restrict__ B) {
+           double* __restrict__ ybuf, double* __restrict__ fbuf, double* __restrict__ xs, double* __restrict__ B,
+           const ZArgs z) {
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
   cluster.barrier_arrive();  // matched below, before the first write into a neighbour's shared memory
-  __shared__ double wacc[VS_WARPS][MAXB];
-  __shared__ double call[VS_CLUSTER][MAXB];  // partial dot products of every CTA of the cluster
+  extern __shared__ __align__(16) double vs_dyn[];
+  double(*wacc)[MAXB] = reinterpret_cast<double(*)[MAXB]>(vs_dyn);  // [VS_WARPS][MAXB]
+  __shared__ double call[VS_CLUSTER][MAXB];   // partial dot products of every CTA of the cluster
+  __shared__ double call2[VS_CLUSTER][MAXB];  // partial Z^T (F / sigma) of every CTA
   __shared__ double ctot[MAXB];
   __shared__ double red2[VS_WARPS][2];
   __shared__ double nall[VS_CLUSTER][2];  // partial (||F||^2, mu.F) of every CTA
@@ -503,6 +584,7 @@ __global__ void __launch_bounds__(VS_THREADS, 1)
       const bool ok = r < r1;
       const double* vr = V + (size_t)(ok ? r : r0) * ldv;
       f[i] = ok ? t[r] : 0.0;
+      if (z.Z && ok && lane == 0) z.Z[(size_t)r * ldv + j] = f[i];  // Z[:, j] = A^T w_j
       if (mu) f[i] = ok ? (f[i] - mu[r] * su) * rs[r] : 0.0;
       vj[i] = ok ? vr[j] : 0.0;
 #pragma unroll
@@ -540,6 +622,7 @@ __global__ void __launch_bounds__(VS_THREADS, 1)
 #pragma unroll
   for (int q = 0; q < NQ; ++q) creg[q] = (lane + 32 * q < nd) ? ctot[lane + 32 * q] : 0.0;
   double n2 = 0, ax = 0;
+  double zacc[NQ] = {};
   for (int rb = r0 + warp; rb < r1; rb += VS_WARPS * VS_ROWS) {
     double p[VS_ROWS], y[VS_ROWS], cf[VS_ROWS];
 #pragma unroll
@@ -566,6 +649,23 @@ __global__ void __launch_bounds__(VS_THREADS, 1)
       n2 += y[i] * y[i];
       ax += cf[i] * y[i];
     }
+    if (z.Z) {
+#pragma unroll
+      for (int i = 0; i < VS_ROWS; ++i) {
+        const int r = rb + i * VS_WARPS;
+        if (r < r1) {
+          const double* zr = z.Z + (size_t)r * ldv;
+          const double yz = rs ? y[i] * rs[r] : y[i];
+#pragma unroll
+          for (int q = 0; q < NQ; ++q)
+            if (lane + 32 * q < z.ncc) zacc[q] += zr[lane + 32 * q] * yz;
+        }
+      }
+    }
+  }
+  if (z.Z) {  // wacc is free again: every CTA passed the first cluster barrier after reading it
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) wacc[warp][lane + 32 * q] = zacc[q];
   }
   if (lane == 0) {
     red2[warp][0] = n2;
@@ -577,6 +677,13 @@ __global__ void __launch_bounds__(VS_THREADS, 1)
 #pragma unroll 8
     for (int w = 0; w < VS_WARPS; ++w) p += red2[w][tid];
     for (int q = 0; q < csize; ++q) cluster.map_shared_rank(&nall[0][0], q)[crank * 2 + tid] = p;
+  }
+  if (z.Z && tid >= 32 && tid < 32 + z.ncc) {
+    const int col = tid - 32;
+    double p = 0;
+#pragma unroll 8
+    for (int w = 0; w < VS_WARPS; ++w) p += wacc[w][col];
+    for (int q = 0; q < csize; ++q) cluster.map_shared_rank(&call2[0][0], q)[crank * MAXB + col] = p;
   }
   cluster.sync();  // also orders this CTA's ybuf writes before its own reads below
   double tot0 = 0, tot1 = 0;
@@ -593,6 +700,19 @@ __global__ void __launch_bounds__(VS_THREADS, 1)
     fbuf[r] = v;
     if (jn < m_b) V[(size_t)r * ldv + jn] = v;
     xs[r] = rs ? v * rs[r] : v;
+  }
+  if (z.Z && crank == 0 && tid >= 32 && tid < 32 + z.ncc) {
+    // coefficients of the next W column; column j itself: g = 1, sumW[j] = (sum y) / ||y|| of w_step's vector
+    const int col = tid - 32;
+    double zs = 0;
+    for (int q = 0; q < csize; ++q) zs += call2[q][col];
+    const double sinvp = inv_or_zero(sqrt(z.gprev[j]));
+    const double sw = (col == j) ? z.gprev[j + 1] * sinvp : z.sumW[col];
+    if (col == j) z.sumW[j] = sw;
+    const double mvs = murs ? inv * tot1 : 0.0;
+    double cc = inv * zs - mvs * sw;
+    if (z.prev) cc -= nrm * ((col == j) ? 1.0 : z.gprev[col] * sinvp);
+    z.cvec[col] = cc;
   }
   if (crank == 0 && tid == 0) {
     sc[SC_NRM2] = tot0;
@@ -627,9 +747,10 @@ __global__ void v_finish(const double* __restrict__ ybuf, const double* __restri
 
 // ---- normalise w, store W[:, jn] and the contiguous copy the next A^T u gathers from -----------
 // B[jn, jn] = ||w|| is complete here, so the SVD of B can start while the last F is still being computed
-__global__ void w_finish(const double* __restrict__ ybuf, double* __restrict__ sc, double* __restrict__ W, int ldw,
-                         int jn, i64 n, double* __restrict__ wcur, double* __restrict__ B, int m_b) {
-  const double s = sqrt(sc[SC_NRM2]);
+__global__ void w_finish(const double* __restrict__ ybuf, const double* __restrict__ n2p, double* __restrict__ sc,
+                         double* __restrict__ W, int ldw, int jn, i64 n, double* __restrict__ wcur, double* __restrict__ B,
+                         int m_b) {
+  const double s = sqrt(n2p[0]);
   const double sinv = inv_or_zero(s);
   const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (r < n) {
@@ -639,7 +760,7 @@ __global__ void w_finish(const double* __restrict__ ybuf, double* __restrict__ s
   }
   if (r == 0) {
     sc[SC_S] = s;
-    sc[SC_SU] = sinv * sc[SC_AUX];
+    sc[SC_SU] = sinv * n2p[1];
     B[(size_t)jn * m_b + jn] = s;  // irlb.py:196 / 221
   }
 }
@@ -981,20 +1102,20 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// The V (h rows, few tiles) and W (n rows) rotations of a restart run as ONE launch: CTAs [0, nba) take job a,
-// the rest job b, so the small V job no longer occupies a nearly empty GPU on its own.
-__global__ void __launch_bounds__(512) rotate_basis(const RotJob ja, const RotJob jb, int nba, int ld, int m, int kc,
-                                                    int nbuf) {
-  const bool second = (int)blockIdx.x >= nba;
-  const RotJob& job = second ? jb : ja;
+// The rotations of a restart -- V (h rows), Z = A^T W (h rows, optional) and W (n rows) -- run as ONE launch: CTAs
+// [0, nba) take job a, [nba, nba + nbb) job b, the rest job c, so the small jobs do not occupy a nearly empty GPU.
+__global__ void __launch_bounds__(512) rotate_basis(const RotJob ja, const RotJob jb, const RotJob jc, int nba, int nbb,
+                                                    int ld, int m, int kc, int nbuf) {
+  const int which = ((int)blockIdx.x >= nba) + ((int)blockIdx.x >= nba + nbb);
+  const RotJob& job = which == 0 ? ja : (which == 1 ? jb : jc);
   double* __restrict__ Q = job.Q;
   const i64 rows = job.rows;
   const double* __restrict__ St = job.St;
   double* __restrict__ out = job.out;
   const int ldo = job.ldo;
   const double* __restrict__ colscale = job.colscale;
-  const unsigned bid = second ? blockIdx.x - nba : blockIdx.x;
-  const unsigned nblk = second ? gridDim.x - nba : nba;
+  const unsigned bid = which == 0 ? blockIdx.x : (which == 1 ? blockIdx.x - nba : blockIdx.x - nba - nbb);
+  const unsigned nblk = which == 0 ? nba : (which == 1 ? nbb : gridDim.x - nba - nbb);
   extern __shared__ __align__(16) double sm[];
   const int kcp = (kc + 7) & ~7;
   double* Ssm = sm;                   // [m][kcp]
@@ -1086,16 +1207,17 @@ __device__ __forceinline__ void cp_async_wait() {
 constexpr int RR_CHUNKS = 4;
 
 template <int R>
-__global__ void __launch_bounds__(512) rotate_rows(const RotJob ja, const RotJob jb, int nba, int ld, int m, int kc) {
-  const bool second = (int)blockIdx.x >= nba;
-  const RotJob& job = second ? jb : ja;
+__global__ void __launch_bounds__(512) rotate_rows(const RotJob ja, const RotJob jb, const RotJob jc, int nba, int nbb,
+                                                   int ld, int m, int kc) {
+  const int which = ((int)blockIdx.x >= nba) + ((int)blockIdx.x >= nba + nbb);
+  const RotJob& job = which == 0 ? ja : (which == 1 ? jb : jc);
   double* __restrict__ Q = job.Q;
   const double* __restrict__ St = job.St;
   double* __restrict__ out = job.out;
   const int ldo = job.ldo;
   const double* __restrict__ colscale = job.colscale;
-  const i64 bid = second ? blockIdx.x - nba : blockIdx.x;
-  const i64 nblk = second ? gridDim.x - nba : nba;
+  const i64 bid = which == 0 ? blockIdx.x : (which == 1 ? blockIdx.x - nba : blockIdx.x - nba - nbb);
+  const i64 nblk = which == 0 ? nba : (which == 1 ? nbb : gridDim.x - nba - nbb);
   const i64 per = (job.rows + nblk - 1) / nblk;
   const i64 lo = bid * per, hi = min(job.rows, lo + per);
   constexpr int TR = 32 * R, RP = TR + 1;
@@ -1181,7 +1303,7 @@ __global__ void __launch_bounds__(512) rotate_rows(const RotJob ja, const RotJob
     }
   }
 }
-using rotate_rows_fn = void (*)(const RotJob, const RotJob, int, int, int, int);
+using rotate_rows_fn = void (*)(const RotJob, const RotJob, const RotJob, int, int, int, int, int);
 static rotate_rows_fn rotate_rows_for(int R) {
   switch (R) {
     case 1: return rotate_rows<1>;
@@ -1193,9 +1315,51 @@ static rotate_rows_fn rotate_rows_for(int R) {
 }
 
 // ---- V[:,k] = F ; B = diag(sv[:k]) + R[:k] in column k  (irlb.py:239-244) ------------------------
+// With the Z formulation (see w_step) CTA 0 also maps the pre-computed coefficients and the column sums of W to
+// the rotated basis: c <- Su[:, :k]^T c, sumW <- Su[:, :k]^T sumW  (Su[c * m + i] = component i of left vector c).
 __global__ void set_restart(double* __restrict__ V, int ldv, int h, const double* __restrict__ fbuf,
                             double* __restrict__ B, int m, int k, const double* __restrict__ sv,
-                            const double* __restrict__ R) {
+                            const double* __restrict__ R, double* __restrict__ cvec, double* __restrict__ sumW,
+                            const double* __restrict__ Su) {
+  if (cvec && blockIdx.x == 0) {
+    __shared__ double oc[MAXB], os[MAXB];
+    for (int q = threadIdx.x; q < m; q += blockDim.x) {
+      oc[q] = cvec[q];
+      os[q] = sumW[q];
+    }
+    __syncthreads();
+    // a warp per output, lanes along the (contiguous) vector; four outputs per trip keep their loads in flight
+    const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int q0 = threadIdx.x >> 5; q0 < k; q0 += 4 * nw) {
+      double nc[4] = {0, 0, 0, 0}, ns[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int u4 = 0; u4 < 4; ++u4) {
+        const int q = q0 + u4 * nw;
+#pragma unroll
+        for (int ee = 0; ee < MAXB / 32; ++ee) {
+          const int e = lane + 32 * ee;
+          if (q < k && e < m) {
+            const double u = Su[(size_t)q * m + e];
+            nc[u4] = fma(u, oc[e], nc[u4]);
+            ns[u4] = fma(u, os[e], ns[u4]);
+          }
+        }
+      }
+#pragma unroll
+      for (int u4 = 0; u4 < 4; ++u4) {
+        nc[u4] = warp_sum(nc[u4]);
+        ns[u4] = warp_sum(ns[u4]);
+      }
+#pragma unroll
+      for (int u4 = 0; u4 < 4; ++u4) {
+        const int q = q0 + u4 * nw;
+        if (q < k && lane == 0) {
+          cvec[q] = nc[u4];
+          sumW[q] = ns[u4];
+        }
+      }
+    }
+  }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < h) V[(size_t)i * ldv + k] = fbuf[i];
   if (i < m * m) {
@@ -1236,7 +1400,7 @@ struct IrlbWs {
   i64 sig_n = -1;
   int sig_i[6] = {};
   double sig_tol = 0;
-  DevBuf<double> V, W, B, sc, tbuf, ybuf_h, ybuf_n, fbuf, xs, wcur, cvec, partials, Su, Sv, svd_s, R, murs, St;
+  DevBuf<double> V, W, B, sc, tbuf, ybuf_h, ybuf_n, fbuf, xs, wcur, cvec, partials, Su, Sv, svd_s, R, murs, St, Z, sumW, gout;
   DevBuf<unsigned> counter;
   DevBuf<int> info;
   std::map<int, cudaGraphExec_t> graphs;
@@ -1276,7 +1440,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     const void* sp[8] = {A.rptr.p, A.cidx.p, A.rval.p, A.cptr.p, A.ridx.p, A.cval.p, mu, rs};
     // test hooks read from the environment change what a captured iteration contains
     const int hooks = (getenv("ADOBO_B200_SVD_JACOBI") ? 1 : 0) | (getenv("ADOBO_B200_NO_FORK") ? 2 : 0) |
-                      (getenv("ADOBO_B200_ROTATE_STREAMED") ? 4 : 0) | (getenv("ADOBO_B200_NO_VSTEP") ? 8 : 0) | (getenv("ADOBO_B200_NO_WFOLD") ? 1024 : 0) | (svd_arrow_cluster() << 4);
+                      (getenv("ADOBO_B200_ROTATE_STREAMED") ? 4 : 0) | (getenv("ADOBO_B200_NO_VSTEP") ? 8 : 0) | (getenv("ADOBO_B200_NO_WFOLD") ? 1024 : 0) | (getenv("ADOBO_B200_NO_ZPATH") ? 2048 : 0) | (svd_arrow_cluster() << 4);
     const int si[6] = {h, nu, m_b, c->world, (int)sizeof(VT), hooks};
     bool same = ws.sig_n == n && ws.sig_tol == tol;
     for (int q = 0; q < 8; ++q) same = same && ws.sig_ptr[q] == sp[q];
@@ -1346,18 +1510,35 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   // V[:, :kc] (or outv) = V Sv[:, :kc]  and  W[:, :kc] (or outw) = W Su[:, :kc], one launch each for the
   // transposes and for the two tall-skinny GEMMs
   const bool rot_streamed = getenv("ADOBO_B200_ROTATE_STREAMED") != nullptr;  // test hook: force rotate_basis
+  // Z formulation of the W side (w_step): needs the cluster V kernel and two spare columns in the reduced vector
+  const bool zpath = h <= 8192 && m_b + 2 <= MAXB && getenv("ADOBO_B200_NO_VSTEP") == nullptr &&
+                     getenv("ADOBO_B200_NO_ZPATH") == nullptr;
+  if (zpath) {
+    const double* before[1] = {ws.Z.p};
+    ws.Z.ensure((size_t)h * ld);
+    ws.sumW.ensure(MAXB);
+    ws.gout.ensure(MAXB);
+    if (before[0] != ws.Z.p) ws.clear_graphs();
+    CUDA_CHECK(cudaMemsetAsync(ws.Z.p, 0, sizeof(double) * (size_t)h * ld, st));
+    CUDA_CHECK(cudaMemsetAsync(ws.sumW.p, 0, sizeof(double) * MAXB, st));
+    CUDA_CHECK(cudaMemsetAsync(ws.gout.p, 0, sizeof(double) * MAXB, st));
+  }
+  DevBuf<double>&Z = ws.Z, &sumW = ws.sumW, &gout = ws.gout;
   auto rotate2 = [&](int kc, double* outv, double* outw, int ldo, const double* scale_w) {
     const int kcp = (kc + 7) & ~7;
     LAUNCH(c, "transpose_s", (transpose_s<<<(2 * m_b * kcp + 255) / 256, 256, 0, st>>>(Sv.p, Su.p, m_b, kc, kcp, St.p)));
+    const bool with_z = zpath && outv == nullptr;  // restart rotation: Z = A^T W follows W
     RotJob jv{V.p, (i64)h, St.p, outv, ldo, nullptr};
+    RotJob jz{with_z ? Z.p : nullptr, with_z ? (i64)h : 0, St.p + (size_t)m_b * kcp, nullptr, 0, nullptr};
     RotJob jw{W.p, n, St.p + (size_t)m_b * kcp, outw, ldo, scale_w};
-    // one wave: split the SMs between the two jobs in proportion to their 64-row tiles
-    const i64 tv = (h + RB_ROWS - 1) / RB_ROWS, tw = (n + RB_ROWS - 1) / RB_ROWS, sms = c->sm_count;
-    i64 bv = (tv * sms + (tv + tw) / 2) / (tv + tw);
-    bv = std::max<i64>(1, std::min<i64>(bv, tv));
-    const i64 bw = std::max<i64>(1, std::min<i64>(tw, sms - bv));
-    const unsigned nbv = (unsigned)bv, nbw = (unsigned)bw;
-    WORK(c, 8.0 * (n + h) * (m_b + kc));
+    // one wave: split the SMs between the jobs in proportion to their 64-row tiles
+    const i64 tv = (h + RB_ROWS - 1) / RB_ROWS, tz = with_z ? tv : 0, tw = (n + RB_ROWS - 1) / RB_ROWS, sms = c->sm_count;
+    const i64 tall = tv + tz + tw;
+    i64 bv = std::max<i64>(1, std::min<i64>((tv * sms + tall / 2) / tall, tv));
+    i64 bz = with_z ? bv : 0;
+    const i64 bw = std::max<i64>(1, std::min<i64>(tw, sms - bv - bz));
+    const unsigned nbv = (unsigned)bv, nbz = (unsigned)bz, nbw = (unsigned)bw;
+    WORK(c, 8.0 * (n + h + (with_z ? h : 0)) * (m_b + kc));
     // few tiles per SM: rotate_rows (row range per CTA, loads pipelined along the inner dimension);
     // long shards: rotate_basis (64-row tiles streamed through a double buffer)
     const i64 per = std::max<i64>(((i64)h + bv - 1) / bv, (n + bw - 1) / bw);  // rows per CTA
@@ -1369,10 +1550,10 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
       const size_t smem = s_bytes + sizeof(double) * (size_t)m_b * (32 * Rr + 1);
       rotate_rows_fn fn = rotate_rows_for(Rr);
       CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      LAUNCH(c, "rotate_basis", (fn<<<nbv + nbw, 32 * (kcp / 8), smem, st>>>(jv, jw, (int)nbv, ld, m_b, kc)));
+      LAUNCH(c, "rotate_basis", (fn<<<nbv + nbz + nbw, 32 * (kcp / 8), smem, st>>>(jv, jz, jw, (int)nbv, (int)nbz, ld, m_b, kc)));
     } else {
-      LAUNCH(c, "rotate_basis", (rotate_basis<<<nbv + nbw, 32 * (kcp / 8), rot_smem, st>>>(jv, jw, (int)nbv, ld, m_b, kc,
-                                                                                     rot_nbuf)));
+      LAUNCH(c, "rotate_basis", (rotate_basis<<<nbv + nbz + nbw, 32 * (kcp / 8), rot_smem, st>>>(jv, jz, jw, (int)nbv, (int)nbz,
+                                                                                           ld, m_b, kc, rot_nbuf)));
     }
   };
   const bool use_arrow = getenv("ADOBO_B200_SVD_JACOBI") == nullptr;
@@ -1393,7 +1574,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   const bool fold_v = h <= 16384, fold_w = !wide_rows && n <= 8192 && !(c->world > 1 && !fused);
   // otherwise the W finish rides in the spmvT_csc that consumes the column -- except for the last column, whose
   // norm completes B for the SVD that is forked off before that spmvT_csc
-  const bool fold_wt = !fold_w && getenv("ADOBO_B200_NO_WFOLD") == nullptr;
+  const bool fold_wt = (zpath || !fold_w) && getenv("ADOBO_B200_NO_WFOLD") == nullptr;
   auto v_fin = [&](int jn, int j) {
     Finish f;
     if (!fold_v) return f;
@@ -1416,6 +1597,15 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
 
   auto w_column = [&](int jprev, int nd, int jn) {
     // W[:, jn] = normalise( orthog( A_s x - fn W[:, jprev], W[:, :nd] ) )
+    if (zpath) {  // one pass: the coefficients were left in cvec by v_step (set_restart after a restart)
+      WORK(c, (double)A.nnz * (4.0 + sizeof(VT)) + 8.0 * (n + 1) + 8.0 * n * (nd + (jprev >= 0 ? 1 : 0) + 1) + 8.0 * h);
+      LAUNCH(c, "w_step", (w_step<VT><<<gb_n, RT_THREADS, 0, st>>>(A.rptr.p, A.cidx.p, A.rval.p, xs.p, sc.p, W.p, ld, jprev, nd, n,
+                                                                 cvec.p, ybuf_n.p, partials.p, gout.p, counter.p, pcw)));
+      if (!fused) allreduce_sum_f64(c, gout.p, (size_t)nd + 2);
+      if (!(fold_wt && jn != m_b - 1))
+        LAUNCH(c, "w_finish", (w_finish<<<fin_n, 256, 0, st>>>(ybuf_n.p, gout.p + nd, sc.p, W.p, ld, jn, n, wcur.p, B.p, m_b)));
+      return;
+    }
     WORK(c, (double)A.nnz * (4.0 + sizeof(VT)) + 8.0 * (n + 1) + 8.0 * n * (nd + (jprev >= 0 ? 1 : 0) + 1) + 8.0 * h);
     if (!wide_rows)
       LAUNCH(c, "spmv_dots", (spmv_dots_w32<VT><<<gb_n, RT_THREADS, 0, st>>>(A.rptr.p, A.cidx.p, A.rval.p, xs.p, sc.p, W.p, ld,
@@ -1439,14 +1629,16 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
                                                                     partials.p, sc.p + SC_NRM2, counter.p, pcw,
                                                                     w_fin(jn))));
     if (!fused) allreduce_sum_f64(c, sc.p + SC_NRM2, 2);
-    if ((wide_rows || !fold_w) && !(fold_wt && jn != m_b - 1)) LAUNCH(c, "w_finish", (w_finish<<<fin_n, 256, 0, st>>>(ybuf_n.p, sc.p, W.p, ld, jn, n, wcur.p, B.p,
+    if ((wide_rows || !fold_w) && !(fold_wt && jn != m_b - 1)) LAUNCH(c, "w_finish", (w_finish<<<fin_n, 256, 0, st>>>(ybuf_n.p, sc.p + SC_NRM2, sc.p, W.p, ld, jn, n, wcur.p, B.p,
                                                                                        m_b)));
   };
   // restart update (irlb.py:238-246): Ritz vectors into the leading k columns, V[:,k] = F, new B
   auto restart_update = [&](int k) {
     rotate2(k, nullptr, nullptr, 0, nullptr);
     LAUNCH(c, "set_restart", (set_restart<<<(std::max(h, m_b * m_b) + 255) / 256, 256, 0, st>>>(V.p, ld, h, fbuf.p, B.p,
-                                                                                            m_b, k, svd_s.p, R.p)));
+                                                                                            m_b, k, svd_s.p, R.p,
+                                                                                            zpath ? cvec.p : nullptr, sumW.p,
+                                                                                            Su.p)));
   };
   // one outer iteration (irlb.py:155-231) up to the convergence read-back
   const bool use_graphs = !c->profiling && getenv("ADOBO_B200_NO_GRAPH") == nullptr;
@@ -1462,6 +1654,10 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   const bool fork_svd = use_graphs && getenv("ADOBO_B200_NO_FORK") == nullptr;
   // V side of a step as one cluster kernel (short V), or three grid-wide kernels (very long V)
   const bool use_vstep = h <= 8192 && getenv("ADOBO_B200_NO_VSTEP") == nullptr;
+  if (use_vstep) {  // static + dynamic shared memory of v_step exceeds the 48 KB default
+    CUDA_CHECK(cudaFuncSetAttribute(v_step<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * VS_WARPS * MAXB)));
+    CUDA_CHECK(cudaFuncSetAttribute(v_step<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * VS_WARPS * MAXB)));
+  }
   auto enqueue_iteration = [&](bool first, int k) {
     if (!first) restart_update(k);
     int j = first ? 0 : k;
@@ -1478,7 +1674,9 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
         // column j of W arrives normalised (w_finish / folded finish) or as ybuf + ||w||^2 (finish folded in here)
         WFinish wf;
         const bool infold = fold_wt && j != m_b - 1;
-        if (infold) wf.W = W.p, wf.ldw = ld, wf.jn = j, wf.m_b = m_b, wf.n = n, wf.sc = sc.p, wf.B = B.p;
+        if (infold)
+          wf.W = W.p, wf.ldw = ld, wf.jn = j, wf.m_b = m_b, wf.n = n, wf.sc = sc.p, wf.B = B.p,
+          wf.n2p = zpath ? gout.p + j : sc.p + SC_NRM2;  // column j came from w_step with nd = j
         LAUNCH(c, "spmvT_csc", (spmvT_csc<VT><<<h, 256, 0, st>>>(A.cptr.p, A.ridx.p, A.cval.p, infold ? ybuf_n.p : wcur.p, tbuf.p,
                                                                  h, counter.p + 1, fused_t ? pcw : pc1, wf)));
       }
@@ -1488,7 +1686,12 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(VS_CLUSTER);
         cfg.blockDim = dim3(VS_THREADS);
+        cfg.dynamicSmemBytes = sizeof(double) * VS_WARPS * MAXB;
         cfg.stream = st;
+        ZArgs za;
+        if (zpath)
+          za.Z = Z.p, za.sumW = sumW.p, za.gprev = gout.p, za.cvec = cvec.p, za.ncc = (j < m_b - 1) ? j + 1 : m_b,
+          za.prev = (j < m_b - 1) ? 1 : 0;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = VS_CLUSTER;
@@ -1498,7 +1701,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
         cfg.numAttrs = 1;
         LAUNCH(c, "v_step", CUDA_CHECK(cudaLaunchKernelEx(&cfg, m_b <= 96 ? v_step<3> : v_step<4>, (const double*)tbuf.p, mu, rs,
                                                            (const double*)(centered ? murs.p : nullptr), sc.p, V.p, ld, j,
-                                                           m_b, h, ybuf_h.p, fbuf.p, xs.p, B.p)));
+                                                           m_b, h, ybuf_h.p, fbuf.p, xs.p, B.p, za)));
       } else {
         WORK(c, 8.0 * h * (j + 1 + 4));
         LAUNCH(c, "v_prep_dots", (v_prep_dots<<<gb_h, RT_THREADS, 0, st>>>(tbuf.p, mu, rs, sc.p, V.p, ld, j, j + 1, h, ybuf_h.p,
