@@ -542,6 +542,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1)
 // dot products (then its two partial norms) into the shared memory of all eight, one cluster barrier, and every
 // CTA sums the eight partials in the same order -- bitwise the same c and ||F|| everywhere, no atomics.
 constexpr int VS_THREADS = 1024, VS_WARPS = VS_THREADS / 32, VS_CLUSTER = 8, VS_ROWS = 4;
+static_assert(VS_THREADS == 8 * MAXB, "v_step sums its per-warp partials with 8 threads per column");
 
 // Z formulation (see w_step): the kernel also stores Z[:, j] = t and leaves the Gram-Schmidt coefficients of
 // the NEXT W column in cvec:  c = Z[:, :ncc]^T xs - mvs sumW - [prev] fn g,  g = W^T w_j from w_step's vector.
@@ -562,7 +563,8 @@ __global__ void __launch_bounds__(VS_THREADS, 1)
   const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
   cluster.barrier_arrive();  // matched below, before the first write into a neighbour's shared memory
   extern __shared__ __align__(16) double vs_dyn[];
-  double(*wacc)[MAXB] = reinterpret_cast<double(*)[MAXB]>(vs_dyn);  // [VS_WARPS][MAXB]
+  double(*wacc)[MAXB] = reinterpret_cast<double(*)[MAXB]>(vs_dyn);                    // [VS_WARPS][MAXB]
+  double(*psum)[MAXB] = reinterpret_cast<double(*)[MAXB]>(vs_dyn + VS_WARPS * MAXB);  // [8][MAXB]
   __shared__ double call[VS_CLUSTER][MAXB];   // partial dot products of every CTA of the cluster
   __shared__ double call2[VS_CLUSTER][MAXB];  // partial Z^T (F / sigma) of every CTA
   __shared__ double ctot[MAXB];
@@ -604,10 +606,19 @@ __global__ void __launch_bounds__(VS_THREADS, 1)
     if (lane + 32 * q < MAXB) wacc[warp][lane + 32 * q] = acc[q];
   __syncthreads();
   cluster.barrier_wait();  // every CTA of the cluster is running
+  // sum over the 32 warps in two levels (8 groups of 4 warps, then 8 partials) instead of 32 serial loads
+  {
+    const int col = tid & (MAXB - 1), part = tid >> 7;  // MAXB = 128 columns x 8 parts = 1024 threads
+    double p = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) p += wacc[part * 4 + w][col];
+    psum[part][col] = p;
+  }
+  __syncthreads();
   if (tid < nd) {
     double p = 0;
-#pragma unroll 8
-    for (int w = 0; w < VS_WARPS; ++w) p += wacc[w][tid];
+#pragma unroll
+    for (int g8 = 0; g8 < 8; ++g8) p += psum[g8][tid];
     for (int q = 0; q < csize; ++q) cluster.map_shared_rank(&call[0][0], q)[crank * MAXB + tid] = p;
   }
   cluster.sync();
@@ -678,12 +689,22 @@ __global__ void __launch_bounds__(VS_THREADS, 1)
     for (int w = 0; w < VS_WARPS; ++w) p += red2[w][tid];
     for (int q = 0; q < csize; ++q) cluster.map_shared_rank(&nall[0][0], q)[crank * 2 + tid] = p;
   }
-  if (z.Z && tid >= 32 && tid < 32 + z.ncc) {
-    const int col = tid - 32;
-    double p = 0;
-#pragma unroll 8
-    for (int w = 0; w < VS_WARPS; ++w) p += wacc[w][col];
-    for (int q = 0; q < csize; ++q) cluster.map_shared_rank(&call2[0][0], q)[crank * MAXB + col] = p;
+  if (z.Z) {
+    {
+      const int col = tid & (MAXB - 1), part = tid >> 7;
+      double p = 0;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) p += wacc[part * 4 + w][col];
+      psum[part][col] = p;
+    }
+    __syncthreads();
+    if (tid >= 32 && tid < 32 + z.ncc) {
+      const int col = tid - 32;
+      double p = 0;
+#pragma unroll
+      for (int g8 = 0; g8 < 8; ++g8) p += psum[g8][col];
+      for (int q = 0; q < csize; ++q) cluster.map_shared_rank(&call2[0][0], q)[crank * MAXB + col] = p;
+    }
   }
   cluster.sync();  // also orders this CTA's ybuf writes before its own reads below
   double tot0 = 0, tot1 = 0;
@@ -1655,8 +1676,8 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   // V side of a step as one cluster kernel (short V), or three grid-wide kernels (very long V)
   const bool use_vstep = h <= 8192 && getenv("ADOBO_B200_NO_VSTEP") == nullptr;
   if (use_vstep) {  // static + dynamic shared memory of v_step exceeds the 48 KB default
-    CUDA_CHECK(cudaFuncSetAttribute(v_step<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * VS_WARPS * MAXB)));
-    CUDA_CHECK(cudaFuncSetAttribute(v_step<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * VS_WARPS * MAXB)));
+    CUDA_CHECK(cudaFuncSetAttribute(v_step<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (VS_WARPS + 8) * MAXB)));
+    CUDA_CHECK(cudaFuncSetAttribute(v_step<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (VS_WARPS + 8) * MAXB)));
   }
   auto enqueue_iteration = [&](bool first, int k) {
     if (!first) restart_update(k);
@@ -1686,7 +1707,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(VS_CLUSTER);
         cfg.blockDim = dim3(VS_THREADS);
-        cfg.dynamicSmemBytes = sizeof(double) * VS_WARPS * MAXB;
+        cfg.dynamicSmemBytes = sizeof(double) * (VS_WARPS + 8) * MAXB;
         cfg.stream = st;
         ZArgs za;
         if (zpath)

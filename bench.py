@@ -268,11 +268,15 @@ def main():
     # bandwidth-type kernels of the path for context
     roof = roofline_of(kernels[0])
     if kernels[0]['kernel'] in ('svd_arrow', 'jacobi_svd'):
-        roof['note'] = ('one-CTA m_b x m_b SVD of B: bounded by dependent fp64 latency on a single SM, not by HBM; '
-                        'algorithmic bytes = 24 m_b^2')
+        roof['note'] = ('m_b x m_b SVD of B: bounded by dependent fp64 latency, not by HBM; algorithmic bytes = 24 m_b^2')
+    elif kernels[0]['kernel'] in ('w_step', 'spmv_dots', 'spmvT_csc', 'v_step', 'update_norm'):
+        roof['note'] = ('Lanczos step kernel at %d cells per GPU: the subset matrix and the basis stay in the 126 MB L2 and a '
+                        'launch lasts ~15-25 us, so it is bounded by launch + dependent-load latency + the cross-CTA '
+                        'reduction, not by HBM; us_per_launch includes ~6 us of CUDA-event overhead (non-graph profiled '
+                        'steps); the HBM-bound regime of the same kernels is in profiles/r01_scale_rooflines.md' % args.cells)
     rooflines = [roofline_of(kd) for kd in kernels if kd['kernel'] in
-                 ('csr_libsize_scale_log', 'csr_gene_moments', 'spmv_dots', 'spmvT_csc', 'update_norm', 'rotate_basis',
-                  'knn_scores_tc')]
+                 ('csr_libsize_scale_log', 'csr_gene_moments', 'w_step', 'spmv_dots', 'spmvT_csc', 'update_norm', 'v_step',
+                  'rotate_basis', 'knn_scores_tc')]
 
     # ---------------- CPU baseline (rank 0, N=1) ----------------
     cpu = None
