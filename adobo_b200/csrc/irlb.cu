@@ -553,6 +553,12 @@ struct ZArgs {
   double* cvec = nullptr;
   int ncc = 0, prev = 0;
 };
+#ifdef ADOBO_B200_VSTAMPS  // phase timing of v_step (clock64 of CTA 0), compiled out of the product build
+__device__ long long vs_stamps[16];
+#define VSTAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) vs_stamps[i] = clock64(); } while (0)
+#else
+#define VSTAMP(i) do { } while (0)
+#endif
 template <int NQ>  // columns per lane: 3 (m_b <= 96) or 4
 __global__ void __launch_bounds__(VS_THREADS, 1)
     v_step(const double* __restrict__ t, const double* __restrict__ mu, const double* __restrict__ rs,
@@ -561,6 +567,7 @@ __global__ void __launch_bounds__(VS_THREADS, 1)
            const ZArgs z) {
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
+  VSTAMP(0);
   cluster.barrier_arrive();  // matched below, before the first write into a neighbour's shared memory
   extern __shared__ __align__(16) double vs_dyn[];
   double(*wacc)[MAXB] = reinterpret_cast<double(*)[MAXB]>(vs_dyn);                    // [VS_WARPS][MAXB]
@@ -601,11 +608,14 @@ __global__ void __launch_bounds__(VS_THREADS, 1)
       for (int q = 0; q < NQ; ++q) acc[q] += vq[i][q] * f[i];
     }
   }
+  VSTAMP(1);
 #pragma unroll
   for (int q = 0; q < NQ; ++q)
     if (lane + 32 * q < MAXB) wacc[warp][lane + 32 * q] = acc[q];
   __syncthreads();
+  VSTAMP(2);
   cluster.barrier_wait();  // every CTA of the cluster is running
+  VSTAMP(3);
   // sum over the 32 warps in two levels (8 groups of 4 warps, then 8 partials) instead of 32 serial loads
   {
     const int col = tid & (MAXB - 1), part = tid >> 7;  // MAXB = 128 columns x 8 parts = 1024 threads
@@ -621,13 +631,16 @@ __global__ void __launch_bounds__(VS_THREADS, 1)
     for (int g8 = 0; g8 < 8; ++g8) p += psum[g8][tid];
     for (int q = 0; q < csize; ++q) cluster.map_shared_rank(&call[0][0], q)[crank * MAXB + tid] = p;
   }
+  VSTAMP(4);
   cluster.sync();
+  VSTAMP(5);
   if (tid < nd) {
     double p = 0;
     for (int q = 0; q < csize; ++q) p += call[q][tid];
     ctot[tid] = p;
   }
   __syncthreads();
+  VSTAMP(6);
   // phase B: F -= V c, partial ||F||^2 and mu.F
   double creg[NQ];
 #pragma unroll
@@ -674,6 +687,7 @@ __global__ void __launch_bounds__(VS_THREADS, 1)
       }
     }
   }
+  VSTAMP(7);
   if (z.Z) {  // wacc is free again: every CTA passed the first cluster barrier after reading it
 #pragma unroll
     for (int q = 0; q < NQ; ++q) wacc[warp][lane + 32 * q] = zacc[q];
@@ -706,7 +720,9 @@ __global__ void __launch_bounds__(VS_THREADS, 1)
       for (int q = 0; q < csize; ++q) cluster.map_shared_rank(&call2[0][0], q)[crank * MAXB + col] = p;
     }
   }
+  VSTAMP(8);
   cluster.sync();  // also orders this CTA's ybuf writes before its own reads below
+  VSTAMP(9);
   double tot0 = 0, tot1 = 0;
   for (int q = 0; q < csize; ++q) {
     tot0 += nall[q][0];
@@ -743,6 +759,10 @@ __global__ void __launch_bounds__(VS_THREADS, 1)
     sc[SC_MVS] = murs ? inv * tot1 : 0.0;
     if (j < m_b - 1) B[(size_t)j * m_b + j + 1] = nrm;  // irlb.py:197
   }
+#ifdef ADOBO_B200_VSTAMPS
+  __syncthreads();
+#endif
+  VSTAMP(10);
 }
 
 // ---- normalise F, store V[:, jn], prepare x = F / sigma and mu.x, write B[j,j], B[j,j+1] ---------
@@ -1818,6 +1838,15 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   rotate2(nu, outV.p, outU.p, nu, var_weigh ? svd_s.p : nullptr);
   CUDA_CHECK(cudaMemcpyAsync(outS.p, svd_s.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));
   CUDA_CHECK(cudaStreamSynchronize(st));
+#ifdef ADOBO_B200_VSTAMPS
+  if (getenv("ADOBO_B200_VSTAMPS")) {
+    long long hs[16];
+    cudaMemcpyFromSymbol(hs, vs_stamps, sizeof(hs));
+    fprintf(stderr, "v_step stamps (cycles):");
+    for (int q = 1; q <= 10; ++q) fprintf(stderr, " %d:%lld", q, hs[q] - hs[q - 1]);
+    fprintf(stderr, " total %lld\n", hs[10] - hs[0]);
+  }
+#endif
   res.steps = it;
   res.nmult = nmult;
   if (getenv("ADOBO_B200_DEBUG"))
