@@ -11,7 +11,8 @@ import numpy as np
 from numpy.ctypeslib import ndpointer
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libadobo_b200.so')
+# ADOBO_B200_LIB_SUFFIX selects a diagnostic build of the same library (see build.py); the product is the default
+LIB_PATH = os.path.join(HERE, 'libadobo_b200%s.so' % os.environ.get('ADOBO_B200_LIB_SUFFIX', ''))
 
 
 class AdoboB200Error(Exception):

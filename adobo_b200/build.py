@@ -13,7 +13,9 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-OUT = os.path.join(HERE, 'libadobo_b200.so')
+# ADOBO_B200_LIB_SUFFIX: diagnostic variants (e.g. _tl with ADOBO_B200_CFLAGS=-DADOBO_B200_TIMELINE) beside the product
+SUFFIX = os.environ.get('ADOBO_B200_LIB_SUFFIX', '')
+OUT = os.path.join(HERE, 'libadobo_b200%s.so' % SUFFIX)
 SOURCES = ['api.cu', 'normalize.cu', 'moments.cu', 'gather.cu', 'irlb.cu', 'svd_arrow.cu', 'knn.cu', 'knn_tc.cu', 'snn.cu']
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr',
@@ -39,12 +41,12 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return OUT
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, 'build')
+    objdir = os.path.join(HERE, 'build' + SUFFIX)
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace('.cu', '.o'))
-        cmd = [nvcc] + ARCH + FLAGS + ['-c', os.path.join(CSRC, src), '-o', obj]
+        cmd = [nvcc] + ARCH + FLAGS + os.environ.get('ADOBO_B200_CFLAGS', '').split() + ['-c', os.path.join(CSRC, src), '-o', obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         with open(obj + '.log', 'w') as f:
             f.write(r.stdout + r.stderr)

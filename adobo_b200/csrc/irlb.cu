@@ -14,6 +14,7 @@
 // Reductions are two-stage and ordered (per-CTA partials, summed by the last CTA to finish), so
 // a given shard layout gives bit-identical results run to run.
 #include <cooperative_groups.h>
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -35,6 +36,51 @@ constexpr double EPS2 = 2.0 * 2.220446049250313e-16;
 
 __device__ __forceinline__ double inv_or_zero(double x) { return x > EPS2 ? 1.0 / x : 0.0; }  // irlb.py:84-92
 
+// Diagnostic build (-DADOBO_B200_TIMELINE): CTA 0 stamps entry and the end of the dependency wait, every CTA
+// its exit, per (kernel, column) slot -- the timeline of the last replay of the iteration graph.
+#ifdef ADOBO_B200_TIMELINE
+__device__ unsigned long long tl_buf[6][1024];
+__device__ __forceinline__ unsigned long long tl_gt() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ unsigned long long tl_cta[8][256];  // per-CTA stamps of the last w_step launch
+__device__ unsigned long long tl_ctak[2][8][256];  // ... of the last spmvT_csc_sm (0) and v_step_one (1) launches
+#define TL_CTA(i) do { if (threadIdx.x == 0 && blockIdx.x < 256) tl_cta[i][blockIdx.x] = tl_gt(); } while (0)
+#define TL_CTAK(k, i) do { if (threadIdx.x == 0 && blockIdx.x < 256 && tl_on) tl_ctak[k][i][blockIdx.x] = tl_gt(); } while (0)
+#define TL_ENTRY(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) { tl_buf[0][slot] = tl_gt(); tl_buf[3][slot] = clock64(); } } while (0)
+// kernels with a dependency wait: entry stamps are kept in registers and stored after the halt check
+#define TL_ENTRY_REG() const unsigned long long tl_e0 = tl_gt(), tl_e1 = clock64()
+#define TL_SYNC(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) { tl_buf[0][slot] = tl_e0; tl_buf[3][slot] = tl_e1; tl_buf[1][slot] = tl_gt(); tl_buf[4][slot] = clock64(); } } while (0)
+#define TL_EXIT(slot) do { if (threadIdx.x == 0) { atomicMax(&tl_buf[2][slot], tl_gt()); atomicMax(&tl_buf[5][slot], (unsigned long long)clock64()); } } while (0)
+#else
+#define TL_CTA(i) do { } while (0)
+#define TL_CTAK(k, i) do { } while (0)
+#define TL_ENTRY(slot) do { } while (0)
+#define TL_ENTRY_REG() do { } while (0)
+#define TL_SYNC(slot) do { } while (0)
+#define TL_EXIT(slot) do { } while (0)
+#endif
+
+// Programmatic dependent launch: wait for the previous kernel of the stream, THEN release the next one.  Releasing
+// only after the own wait means that when a kernel starts, everything two or more kernels back has completed.
+__device__ __forceinline__ void pdl_sync() {
+  cudaGridDependencySynchronize();         // no-op without the launch attribute
+  cudaTriggerProgrammaticLaunchCompletion();
+}
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async16_cg(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
 // ---- ordered cross-CTA reductions (row kernels run 1024-thread CTAs, at most one per SM) --------
 constexpr int RT_THREADS = 1024;
 constexpr int RT_WARPS = RT_THREADS / 32;
@@ -45,6 +91,10 @@ constexpr int RT_WARPS = RT_THREADS / 32;
 __device__ __forceinline__ double (*vec_stage())[MAXB] {
   __shared__ double sh[RT_WARPS][MAXB];
   return sh;
+}
+__device__ __forceinline__ double (*part_stage())[MAXB] {  // second level: [part][column]
+  __shared__ double ps[RT_THREADS / MAXB][MAXB];
+  return ps;
 }
 // acc[t] is this lane's partial for column lane + 32 t
 __device__ __forceinline__ void deposit_lane32(double (&acc)[4]) {
@@ -68,35 +118,114 @@ __device__ __forceinline__ void deposit_lane8(double (&acc)[NQ]) {
   if (NQ * 8 < MAXB)
     for (int c = NQ * 8 + lane; c < MAXB; c += 32) sh[warp][c] = 0.0;
 }
+// Both levels are laid out for coalescing: thread = (column, part); a part sums every nparts-th warp (CTA) partial
+// of its column with independent loads, then one thread per column adds the parts in a fixed order.  (Lanes striding
+// the CTA partials of ONE column -- 1 KB apart -- cost the last CTA 15 k separate sector requests: 8.7 us measured.)
 __device__ __forceinline__ void reduce_vec_finish(int nd, double* __restrict__ partials, double* __restrict__ out,
                                                   unsigned* __restrict__ counter, const PeerComm& pc) {
   double(*sh)[MAXB] = vec_stage();
+  double(*ps)[MAXB] = part_stage();
   __shared__ bool is_last;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nwarps = blockDim.x >> 5;
+  const int tid = threadIdx.x, col = tid & (MAXB - 1), part = tid >> 7;
+  const int nwarps = blockDim.x >> 5, nparts = blockDim.x >> 7, wpp = nwarps / nparts;  // blockDim: multiple of 128
   __syncthreads();
-  if (threadIdx.x < nd) {
-    double s = 0;
-    for (int w = 0; w < nwarps; ++w) s += sh[w][threadIdx.x];
-    partials[(size_t)blockIdx.x * MAXB + threadIdx.x] = s;
+  TL_CTA(3);
+  {
+    double p = 0;
+    for (int w = 0; w < wpp; ++w) p += sh[part * wpp + w][col];
+    ps[part][col] = p;
   }
+  __syncthreads();
+  if (tid < nd) {
+    double s = 0;
+    for (int g = 0; g < nparts; ++g) s += ps[g][tid];
+    partials[(size_t)blockIdx.x * MAXB + tid] = s;
+  }
+  TL_CTA(4);
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  TL_CTA(5);
+  if (tid == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
   __syncthreads();
+  TL_CTA(6);
   if (is_last) {
-    // warp w sums columns w, w + nwarps, ...: lanes stride the CTA partials (fixed order -> deterministic)
-    for (int col = warp; col < nd; col += nwarps) {
-      double s = 0;
-      for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + (size_t)b * MAXB + col);
-      s = warp_sum(s);
-      if (lane == 0) out[col] = s;
+    double s = 0;
+    if (col < nd) {
+#pragma unroll 4
+      for (unsigned b = part; b < gridDim.x; b += nparts) s += __ldcg(partials + (size_t)b * MAXB + col);
     }
-    if (threadIdx.x == 0) *counter = 0;
+    ps[part][col] = s;
+    __syncthreads();
+    if (tid < nd) {
+      double t = 0;
+      for (int g = 0; g < nparts; ++g) t += ps[g][tid];
+      out[tid] = t;
+    }
+    if (tid == 0) *counter = 0;
     if (pc.world > 1) {  // sum over ranks, fused: this CTA exchanges the vector over NVLink peer memory
       __syncthreads();
       peer_allreduce_block(pc, out, nd);
     }
+  }
+}
+// Split reduction (single GPU): the producer stops at the per-CTA partials -- no fence, no atomic, no serial last
+// CTA on the step's critical path -- and every consumer sums the CTA partials of the columns it needs itself, in
+// one fixed order: part p = CTAs p, p + 8, ... (ascending), then ((P0 + P1) + ...) + P7.
+__device__ __forceinline__ void reduce_vec_partials(int nd, double* __restrict__ partials) {
+  double(*sh)[MAXB] = vec_stage();
+  double(*ps)[MAXB] = part_stage();
+  const int tid = threadIdx.x, col = tid & (MAXB - 1), part = tid >> 7;
+  const int nwarps = blockDim.x >> 5, nparts = blockDim.x >> 7, wpp = nwarps / nparts;
+  __syncthreads();
+  {
+    double p = 0;
+    for (int w = 0; w < wpp; ++w) p += sh[part * wpp + w][col];
+    ps[part][col] = p;
+  }
+  __syncthreads();
+  if (tid < nd) {
+    double s = 0;
+    for (int g = 0; g < nparts; ++g) s += ps[g][tid];
+    partials[(size_t)blockIdx.x * MAXB + tid] = s;
+  }
+}
+constexpr int SP_PARTS = 8, SP_PER = 19;  // 8 x 19 >= 148 CTAs: a part's loads are issued as one batch
+// the part sum of one column: CTAs part, part + SP_PARTS, ... in ascending order
+__device__ __forceinline__ double sum_partials_part(const double* __restrict__ src, int part, int nparts, int nblk) {
+  double v[SP_PER];
+#pragma unroll
+  for (int i = 0; i < SP_PER; ++i) {
+    const int b = part + nparts * i;
+    v[i] = b < nblk ? __ldcg(src + (size_t)b * MAXB) : 0.0;
+  }
+  double p = 0;
+#pragma unroll
+  for (int i = 0; i < SP_PER; ++i) p += v[i];
+  for (int b = part + nparts * SP_PER; b < nblk; b += nparts) p += __ldcg(src + (size_t)b * MAXB);  // grids beyond 8 x 19
+  return p;
+}
+// one column summed by a full warp: lanes stride the CTAs (<= 5 batched loads each for <= 160 CTAs), butterfly
+__device__ __forceinline__ double sum_partials_warp(const double* __restrict__ src, int nblk) {
+  const int lane = threadIdx.x & 31;
+  double v[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) v[i] = (lane + 32 * i < nblk) ? __ldcg(src + (size_t)(lane + 32 * i) * MAXB) : 0.0;
+  double p = ((v[0] + v[1]) + (v[2] + v[3])) + v[4];
+  for (int b = lane + 160; b < nblk; b += 32) p += __ldcg(src + (size_t)b * MAXB);
+  return warp_sum(p);
+}
+// columns col0 and col0 + 1 (||y||^2 and sum y of w_step's vector): called by one full warp, results in all lanes;
+// 16 parts per column (lanes 0-15 / 16-31), summed in lane order
+__device__ __forceinline__ void sum_partials_two(const double* __restrict__ partials, int nblk, int col0, double& t0,
+                                                 double& t1) {
+  const int lane = threadIdx.x & 31;
+  const double p = sum_partials_part(partials + col0 + (lane >> 4), lane & 15, 16, nblk);
+  t0 = __shfl_sync(0xffffffffu, p, 0);
+  t1 = __shfl_sync(0xffffffffu, p, 16);
+#pragma unroll
+  for (int l = 1; l < 16; ++l) {
+    t0 += __shfl_sync(0xffffffffu, p, l);
+    t1 += __shfl_sync(0xffffffffu, p, 16 + l);
   }
 }
 __device__ __forceinline__ void reduce_vec_blocks(double (&acc)[4], int nd, double* __restrict__ partials,
@@ -206,31 +335,69 @@ struct WFinish {
   double* sc = nullptr;
   double* B = nullptr;
   const double* n2p = nullptr;  // (||w||^2, sum w) of the column: sc + SC_NRM2, or the tail of w_step's vector
+  const double* parts = nullptr;  // split reduction: per-CTA partials of w_step (columns jn, jn + 1 hold the two)
+  int nblk = 0;
+  double* gout = nullptr;  // split reduction: the summed vector (g = W^T y, ||y||^2, sum y) for v_step
 };
+constexpr int ST_EPF = 4;  // entries per thread fetched before the grid-dependency wait (1024 per column)
 template <typename VT>
 __global__ void __launch_bounds__(256) spmvT_csc(const i64* __restrict__ cptr, const int* __restrict__ ridx,
                                                  const VT* __restrict__ cval, const double* __restrict__ u,
                                                  double* __restrict__ t, int h, unsigned* __restrict__ counter,
-                                                 const PeerComm pc, const WFinish wf) {
+                                                 const PeerComm pc, const WFinish wf, const int* __restrict__ halt) {
   __shared__ double red[8];
   __shared__ bool last_cta;
   const int col = blockIdx.x;
-  const i64 b = cptr[col], e1 = cptr[col + 1];
+  TL_ENTRY_REG();
+  // prologue: the static CSC arrays only (see w_step for the programmatic-launch rules)
+  const i64 b = __ldg(cptr + col), e1 = __ldg(cptr + col + 1);
+  int ri[ST_EPF];
+  VT cv[ST_EPF];
+#pragma unroll
+  for (int q = 0; q < ST_EPF; ++q) {
+    const i64 e = b + threadIdx.x + 256 * q;
+    ri[q] = e < e1 ? __ldg(ridx + e) : 0;
+    cv[q] = e < e1 ? __ldg(cval + e) : VT(0);
+  }
+  pdl_sync();
+  if (halt && *halt) return;
+  TL_SYNC(128 + (wf.W ? wf.jn : 127));
   double sinv = 1.0;
   if (wf.W) {
-    const double nrm = sqrt(wf.n2p[0]);
+    __shared__ double s_n2[2];
+    if (wf.parts) {
+      if (threadIdx.x < 32) {
+        double t0, t1;
+        sum_partials_two(wf.parts, wf.nblk, wf.jn, t0, t1);
+        if (threadIdx.x == 0) {
+          s_n2[0] = t0, s_n2[1] = t1;
+          if (wf.gout && col == 0) wf.gout[wf.jn] = t0, wf.gout[wf.jn + 1] = t1;
+        }
+      } else if (wf.gout && threadIdx.x < 64) {
+        for (int gc = col; gc < wf.jn; gc += gridDim.x) {
+          const double g = sum_partials_warp(wf.parts + gc, wf.nblk);
+          if ((threadIdx.x & 31) == 0) wf.gout[gc] = g;
+        }
+      }
+      __syncthreads();
+    }
+    const double n2 = wf.parts ? s_n2[0] : wf.n2p[0], sy = wf.parts ? s_n2[1] : wf.n2p[1];
+    const double nrm = sqrt(n2);
     sinv = inv_or_zero(nrm);
     const i64 chunk = (wf.n + gridDim.x - 1) / gridDim.x, lo = (i64)col * chunk, hi = min(wf.n, lo + chunk);
     for (i64 r = lo + threadIdx.x; r < hi; r += 256) wf.W[(size_t)r * wf.ldw + wf.jn] = sinv * u[r];
     if (col == 0 && threadIdx.x == 0) {
       wf.sc[SC_S] = nrm;
-      wf.sc[SC_SU] = sinv * wf.n2p[1];
+      wf.sc[SC_SU] = sinv * sy;
       wf.B[(size_t)wf.jn * wf.m_b + wf.jn] = nrm;  // irlb.py:196 / 221
     }
   }
   double s = 0;
+#pragma unroll
+  for (int q = 0; q < ST_EPF; ++q)
+    if (b + threadIdx.x + 256 * q < e1) s += (double)cv[q] * u[ri[q]];
 #pragma unroll 4
-  for (i64 e = b + threadIdx.x; e < e1; e += 256) s += (double)__ldg(cval + e) * u[__ldg(ridx + e)];
+  for (i64 e = b + threadIdx.x + 256 * ST_EPF; e < e1; e += 256) s += (double)__ldg(cval + e) * u[__ldg(ridx + e)];
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
@@ -251,6 +418,147 @@ __global__ void __launch_bounds__(256) spmvT_csc(const i64* __restrict__ cptr, c
       if (threadIdx.x == 0) *counter = 0;
     }
   }
+  TL_EXIT(128 + (wf.W ? wf.jn : 127));
+}
+
+// ---- K5 for short shards: u staged in shared memory, columns dealt to CTAs by length -------------------
+// Two things bound spmvT_csc when the whole problem sits in L2 (20 k cells: 11-12 us per launch):
+//  * the gather u[ridx]: rows of a column are ~10 apart, so every 8-byte gather moves its own 32-byte sector and
+//    costs an L1 tag cycle -- when the shard's u fits in shared memory (n <= 25 k rows) each of the one-per-SM
+//    CTAs copies it once with coalesced loads and the gathers become LDS;
+//  * column lengths: HVG columns range from a few hundred to n non-zeros, and a kernel that gives every column
+//    the same number of threads ends when its longest column does (median CTA done after 3.3 us, last after
+//    11.8 us, measured).  Here a CTA owns up to STS_MAXC columns and ALL its threads walk each of them; the host
+//    deals the columns, sorted by length, to the CTAs in snake order (perm), so CTAs carry about equal non-zeros.
+// The first STS_EPF x 512 entries of every owned column are fetched before the grid-dependency wait.
+// (Holding this kernel and w_step2 to 64 registers so that their CTAs co-reside under programmatic launch was
+// measured and rejected: the row loop of w_step2 went from 6.4 to 14.6 us.)
+constexpr int STS_THREADS = 512, STS_MAXC = 8, STS_EPF = 4;
+template <typename VT>
+__global__ void __launch_bounds__(STS_THREADS, 1)
+    spmvT_csc_sm(const i64* __restrict__ cptr, const int* __restrict__ ridx, const VT* __restrict__ cval,
+                 const double* __restrict__ u, double* __restrict__ t, int h, unsigned* __restrict__ counter,
+                 const PeerComm pc, const WFinish wf, const int* __restrict__ halt, int n, const int* __restrict__ perm,
+                 int cpb) {
+  extern __shared__ __align__(16) double us[];  // [n]
+  __shared__ double red[STS_THREADS / 32][STS_MAXC];
+  __shared__ double s_n2[2];
+  __shared__ bool last_cta;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  TL_ENTRY_REG();
+#ifdef ADOBO_B200_TIMELINE
+  const bool tl_on = wf.W && wf.jn == wf.m_b - 2;  // a programmatically launched instance
+  TL_CTAK(0, 5);
+#endif
+  // prologue: static CSC arrays of the owned columns
+  int colk[STS_MAXC], bk[STS_MAXC], lenk[STS_MAXC];
+  int ri[STS_MAXC][STS_EPF];
+  VT cv[STS_MAXC][STS_EPF];
+#pragma unroll
+  for (int k = 0; k < STS_MAXC; ++k) {  // slot descriptors (column, first entry, length), laid out by the host
+    colk[k] = -1, bk[k] = 0, lenk[k] = 0;
+    if (k < cpb) {
+      const int* d = perm + 3 * (size_t)(blockIdx.x + gridDim.x * k);
+      colk[k] = __ldg(d);  // -1: empty slot
+      bk[k] = __ldg(d + 1);
+      lenk[k] = __ldg(d + 2);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < STS_MAXC; ++k)
+#pragma unroll
+    for (int q = 0; q < STS_EPF; ++q) {
+      const int e = tid + STS_THREADS * q;
+      ri[k][q] = e < lenk[k] ? __ldg(ridx + bk[k] + e) : 0;
+      cv[k][q] = e < lenk[k] ? __ldg(cval + bk[k] + e) : VT(0);
+    }
+  TL_CTAK(0, 6);
+  pdl_sync();
+  if (halt && *halt) return;
+  TL_SYNC(128 + (wf.W ? wf.jn : 127));
+  TL_CTAK(0, 0);
+  if (wf.W && tid < 32) {
+    double t0, t1;
+    if (wf.parts)
+      sum_partials_two(wf.parts, wf.nblk, wf.jn, t0, t1);
+    else
+      t0 = wf.n2p[0], t1 = wf.n2p[1];
+    if (tid == 0) {
+      s_n2[0] = t0, s_n2[1] = t1;
+      if (wf.gout && blockIdx.x == 0) wf.gout[wf.jn] = t0, wf.gout[wf.jn + 1] = t1;
+    }
+  }
+  if (wf.W && wf.gout && warp == 1)  // g = W^T y for v_step: CTA b sums column b of w_step's partials
+    for (int gc = blockIdx.x; gc < wf.jn; gc += gridDim.x) {
+      const double g = sum_partials_warp(wf.parts + gc, wf.nblk);
+      if (lane == 0) wf.gout[gc] = g;
+    }
+  {
+    const double2* u2 = reinterpret_cast<const double2*>(u);
+    double2* us2 = reinterpret_cast<double2*>(us);
+#pragma unroll 4
+    for (int i = tid; i < (n >> 1); i += STS_THREADS) us2[i] = __ldcg(u2 + i);
+    if ((n & 1) && tid == 0) us[n - 1] = __ldcg(u + n - 1);
+  }
+  TL_CTAK(0, 1);
+  __syncthreads();
+  TL_CTAK(0, 2);
+  double sinv = 1.0;
+  if (wf.W) {  // W[:, jn] = u / ||u|| for this CTA's slice of rows (see spmvT_csc)
+    const double nrm = sqrt(s_n2[0]);
+    sinv = inv_or_zero(nrm);
+    const int chunk = (n + gridDim.x - 1) / gridDim.x, lo = blockIdx.x * chunk, hi = min(n, lo + chunk);
+    for (int r = lo + tid; r < hi; r += STS_THREADS) wf.W[(size_t)r * wf.ldw + wf.jn] = sinv * us[r];
+    if (blockIdx.x == 0 && tid == 0) {
+      wf.sc[SC_S] = nrm;
+      wf.sc[SC_SU] = sinv * s_n2[1];
+      wf.B[(size_t)wf.jn * wf.m_b + wf.jn] = nrm;  // irlb.py:196 / 221
+    }
+  }
+  TL_CTAK(0, 3);
+  double sk[STS_MAXC];
+#pragma unroll
+  for (int k = 0; k < STS_MAXC; ++k) {
+    double s = 0;
+#pragma unroll
+    for (int q = 0; q < STS_EPF; ++q)
+      if (tid + STS_THREADS * q < lenk[k]) s += (double)cv[k][q] * us[ri[k][q]];
+#pragma unroll 2
+    for (int e = tid + STS_THREADS * STS_EPF; e < lenk[k]; e += STS_THREADS)
+      s += (double)__ldg(cval + bk[k] + e) * us[__ldg(ridx + bk[k] + e)];
+    sk[k] = s;
+  }
+#pragma unroll
+  for (int k = 0; k < STS_MAXC; ++k) {
+    if (k < cpb) {  // uniform
+      const double s = warp_sum(sk[k]);
+      if (lane == 0) red[warp][k] = s;
+    }
+  }
+  __syncthreads();
+  if (warp < cpb) {  // warp k finishes column k: fixed butterfly over the 16 warp partials
+    double v = lane < STS_THREADS / 32 ? red[lane][warp] : 0.0;
+    v = warp_sum(v);
+    int mycol = -1;
+#pragma unroll
+    for (int k = 0; k < STS_MAXC; ++k)
+      if (k == warp) mycol = colk[k];
+    if (lane == 0 && mycol >= 0) t[mycol] = v * sinv;
+  }
+  TL_CTAK(0, 4);
+  if (pc.world > 1) {  // the last CTA to finish sums t over ranks (fused NVLink exchange)
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      last_cta = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last_cta) {
+      peer_allreduce_block(pc, t, h);
+      if (tid == 0) *counter = 0;
+    }
+  }
+  TL_EXIT(128 + (wf.W ? wf.jn : 127));
 }
 
 // ---- F = A_s^T w - s V[:,j]  and  c = V[:, :nd]^T F  (irlb.py:182-190, first half of orthog) ----
@@ -476,41 +784,90 @@ __global__ void __launch_bounds__(RT_THREADS, 1) update_norm(const double* __res
 //     y_r = (A xs)_r - mvs - fn W[r, jprev] - sum_c W[r, c] c_c,
 // with one reduction of the vector (g = W^T y, ||y||^2, sum y).  Same arithmetic as the reference up to rounding
 // (no orthogonality of W is assumed: g carries the actual W^T w_prev); Z is rotated with W at a restart.
-template <typename VT>
+//
+// Latency: a warp takes its rows one after the other and each row is a chain row pointers -> entries -> gather.
+// The chain is software-pipelined two rows deep: while row i is reduced, the entries (first 32 EPF of them) and
+// the W slice of row i + 1 and the pointers of row i + 2 are already in flight in registers.
+//
+// Programmatic dependent launch: everything above pdl_sync() reads only the static CSR arrays and columns of W
+// that were written at least two kernels earlier (spmvT_csc of the previous step; every step kernel releases its
+// dependents only AFTER its own grid-dependency wait, so "two kernels back" has completed).  The first row's
+// whole load chain therefore overlaps the tail of v_step.  W is read with ld.global.cg: no line of it may sit
+// in L1 across the dependency.
+constexpr int WS_EPF = 4;  // entries per lane held in registers for the row in flight (128 per row)
+template <typename VT, int NQ>
+__device__ __forceinline__ void ws_load_row(bool ok, i64 r, int b, int e1, const int* __restrict__ cidx,
+                                            const VT* __restrict__ rval, const double* __restrict__ W, int ldw,
+                                            int jprev, int nd, int lane, int (&ci)[WS_EPF], VT (&va)[WS_EPF],
+                                            double (&wv)[NQ], double& wp) {
+#pragma unroll
+  for (int q = 0; q < WS_EPF; ++q) {
+    const int e = b + lane + 32 * q;
+    const bool in = ok && e < e1;
+    ci[q] = in ? __ldg(cidx + e) : 0;
+    va[q] = in ? __ldg(rval + e) : VT(0);
+  }
+  const double* wr = W + (size_t)(ok ? r : 0) * ldw;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) wv[q] = (ok && lane + 32 * q < nd) ? __ldcg(wr + lane + 32 * q) : 0.0;
+  wp = (ok && jprev >= 0) ? __ldcg(wr + jprev) : 0.0;
+}
+// NQ = columns per lane: 3 (basis <= 94 wide + the two scalars) or 4; entry offsets are 32-bit (subset nnz < 2^31)
+template <typename VT, int NQ>
 __global__ void __launch_bounds__(RT_THREADS, 1)
     w_step(const i64* __restrict__ rptr, const int* __restrict__ cidx, const VT* __restrict__ rval,
            const double* __restrict__ xs, const double* __restrict__ sc, const double* __restrict__ W, int ldw, int jprev,
            int nd, i64 n, const double* __restrict__ cvec, double* __restrict__ ybuf, double* __restrict__ partials,
-           double* __restrict__ gout, unsigned* __restrict__ counter, const PeerComm pc) {
+           double* __restrict__ gout, unsigned* __restrict__ counter, const PeerComm pc, const int* __restrict__ halt) {
   const int lane = threadIdx.x & 31;
   const i64 warps = ((i64)gridDim.x * blockDim.x) >> 5;
-  const double mvs = sc[SC_MVS], fn = sc[SC_FN];
-  double creg[4], acc[4] = {0, 0, 0, 0};
-#pragma unroll
-  for (int q = 0; q < 4; ++q) creg[q] = (lane + 32 * q < nd) ? cvec[lane + 32 * q] : 0.0;
-  double n2 = 0, ax = 0;
   i64 r = (((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  i64 b = 0, e1 = 0;
+  TL_ENTRY_REG();
+  // ---- prologue (independent of the previous kernel) ----
+  int b = 0, e1 = 0, nb = 0, ne = 0;
   if (r < n) {
-    b = __ldg(rptr + r);
-    e1 = __ldg(rptr + r + 1);
+    b = (int)__ldg(rptr + r);
+    e1 = (int)__ldg(rptr + r + 1);
   }
-  for (; r < n; r += warps) {
-    const i64 rn = r + warps;
-    i64 nb = 0, ne = 0;
-    if (rn < n) {  // next row's pointers, requested before this row's chain of dependent loads
-      nb = __ldg(rptr + rn);
-      ne = __ldg(rptr + rn + 1);
-    }
-    const double* wr = W + (size_t)r * ldw;
-    double wv[4];
+  if (r + warps < n) {
+    nb = (int)__ldg(rptr + r + warps);
+    ne = (int)__ldg(rptr + r + warps + 1);
+  }
+  int ci[WS_EPF];
+  VT va[WS_EPF];
+  double wv[NQ], wp;
+  ws_load_row<VT, NQ>(r < n, r, b, e1, cidx, rval, W, ldw, jprev, nd, lane, ci, va, wv, wp);
+  pdl_sync();
+  if (halt && *halt) return;
+  TL_SYNC(nd);
+#ifdef ADOBO_B200_TIMELINE
+  if (threadIdx.x == 0 && blockIdx.x < 256) tl_cta[0][blockIdx.x] = tl_e0;
+#endif
+  TL_CTA(1);
+  const double mvs = sc[SC_MVS], fn = sc[SC_FN];
+  double creg[NQ], acc[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int q = 0; q < 4; ++q) wv[q] = (lane + 32 * q < nd) ? wr[lane + 32 * q] : 0.0;
-    const double wp = (jprev >= 0) ? wr[jprev] : 0.0;
+  for (int q = 0; q < NQ; ++q) creg[q] = (lane + 32 * q < nd) ? cvec[lane + 32 * q] : 0.0;
+  double n2 = 0, ax = 0;
+  for (; r < n; r += warps) {
+    const i64 rn = r + warps, rnn = rn + warps;
+    int nnb = 0, nne = 0;
+    if (rnn < n) {  // pointers two rows ahead
+      nnb = (int)__ldg(rptr + rnn);
+      nne = (int)__ldg(rptr + rnn + 1);
+    }
+    int ci2[WS_EPF];
+    VT va2[WS_EPF];
+    double wv2[NQ], wp2;
+    ws_load_row<VT, NQ>(rn < n, rn, nb, ne, cidx, rval, W, ldw, jprev, nd, lane, ci2, va2, wv2, wp2);  // next row in flight
     double a = 0;
-#pragma unroll 4
-    for (i64 e = b + lane; e < e1; e += 32) a += (double)__ldg(rval + e) * xs[__ldg(cidx + e)];
-    double p = (wv[0] * creg[0] + wv[1] * creg[1]) + (wv[2] * creg[2] + wv[3] * creg[3]);
+#pragma unroll
+    for (int q = 0; q < WS_EPF; ++q)
+      if (b + lane + 32 * q < e1) a += (double)va[q] * xs[ci[q]];
+#pragma unroll 2
+    for (int e = b + 32 * WS_EPF + lane; e < e1; e += 32) a += (double)__ldg(rval + e) * xs[__ldg(cidx + e)];
+    double p = (wv[0] * creg[0] + wv[1] * creg[1]) + wv[2] * creg[2];
+    if (NQ == 4) p += wv[NQ - 1] * creg[NQ - 1];
     a = warp_sum(a);
     p = warp_sum(p);
     double w = a - mvs;
@@ -518,12 +875,16 @@ __global__ void __launch_bounds__(RT_THREADS, 1)
     w -= p;
     if (lane == 0) ybuf[r] = w;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) acc[q] += wv[q] * w;
+    for (int q = 0; q < NQ; ++q) acc[q] += wv[q] * w;
     n2 += w * w;
     ax += w;
-    b = nb;
-    e1 = ne;
+    b = nb, e1 = ne, nb = nnb, ne = nne, wp = wp2;
+#pragma unroll
+    for (int q = 0; q < WS_EPF; ++q) ci[q] = ci2[q], va[q] = va2[q];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) wv[q] = wv2[q];
   }
+  TL_CTA(2);
   // the two scalars ride in columns nd, nd + 1 of the vector (w is warp-uniform: one lane deposits them)
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -532,6 +893,129 @@ __global__ void __launch_bounds__(RT_THREADS, 1)
     if (col == nd + 1) acc[q] = ax;
   }
   reduce_vec_blocks(acc, nd + 2, partials, gout, counter, pc);
+  TL_CTA(7);
+  TL_EXIT(nd);
+}
+
+// ---- w_step2: the same pass, written for instruction count ------------------------------------------
+// ncu on w_step at 20 k cells: neither L2 (7 % of peak) nor memory latency bounds it but ISSUE -- 520 SASS
+// instructions per row (64-bit index arithmetic and predicate logic for every strided row, register rotation,
+// two 64-bit warp reductions), 2.5 IPC per SM for 9 us.  Here a warp owns a CONTIGUOUS block of rows, so row
+// pointers chain (one load per row), W advances by pointer bumps, indices are 32-bit, the two warp sums are one
+// (sum over lanes of a_lane - p_lane), and the two-deep pipeline is unrolled over two register sets instead of
+// rotated.  512-thread CTAs (128 registers per thread: nothing spills or is re-read from the constant bank).
+constexpr int W2_THREADS = 512, W2_EPF = 4;
+template <typename VT, int NQ>
+struct W2Row {
+  int ci[W2_EPF];
+  VT va[W2_EPF];
+  double wv[NQ], wp;
+  int b, len;
+};
+template <typename VT, int NQ>
+__device__ __forceinline__ void w2_load(W2Row<VT, NQ>& R, bool ok, int b, int e1, const int* __restrict__ cl,
+                                        const VT* __restrict__ vl, const double* __restrict__ wr, int jprev,
+                                        const bool (&cm)[NQ], int lane) {
+  R.b = b;
+  R.len = ok ? e1 - b : 0;
+#pragma unroll
+  for (int q = 0; q < W2_EPF; ++q) {
+    const bool in = lane + 32 * q < R.len;
+    R.ci[q] = in ? __ldg(cl + b + 32 * q) : 0;
+    R.va[q] = in ? __ldg(vl + b + 32 * q) : VT(0);
+  }
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) R.wv[q] = (ok && cm[q]) ? __ldcg(wr + 32 * q) : 0.0;
+  R.wp = (ok && jprev >= 0) ? __ldcg(wr - lane + jprev) : 0.0;
+}
+template <typename VT, int NQ>
+__global__ void __launch_bounds__(W2_THREADS, 1)
+    w_step2(const i64* __restrict__ rptr, const int* __restrict__ cidx, const VT* __restrict__ rval,
+            const double* __restrict__ xs, const double* __restrict__ sc, const double* __restrict__ W, int ldw, int jprev,
+            int nd, int n, const double* __restrict__ cvec, double* __restrict__ ybuf, double* __restrict__ partials,
+            double* __restrict__ gout, unsigned* __restrict__ counter, const PeerComm pc, const int* __restrict__ halt,
+            int h, int split) {
+  extern __shared__ __align__(16) double xsm[];  // [h]: the gathers x[cidx] as LDS (32 scattered 8-byte global loads
+                                                 // cost one L1 tag cycle each -- what bounded the row loop)
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (int)((gridDim.x * blockDim.x) >> 5), wg = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int per = (n + nwarps - 1) / nwarps;
+  int r = min(n, wg * per);
+  const int rend = min(n, r + per);
+  TL_ENTRY_REG();
+  // ---- prologue (independent of the previous kernel): pointers of the first three rows, first row's loads ----
+  bool cm[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) cm[q] = lane + 32 * q < nd;
+  const int* cl = cidx + lane;
+  const VT* vl = rval + lane;
+  const double* wr = W + (size_t)r * ldw + lane;
+  int p0 = 0, p1 = 0, p2 = 0;
+  if (r < rend) {
+    p0 = (int)__ldg(rptr + r);
+    p1 = (int)__ldg(rptr + r + 1);
+    p2 = (int)__ldg(rptr + min(r + 2, n));
+  }
+  W2Row<VT, NQ> RA, RB;
+  w2_load<VT, NQ>(RA, r < rend, p0, p1, cl, vl, wr, jprev, cm, lane);
+  pdl_sync();
+  if (halt && *halt) return;
+  TL_SYNC(nd);
+#ifdef ADOBO_B200_TIMELINE
+  if (threadIdx.x == 0 && blockIdx.x < 256) tl_cta[0][blockIdx.x] = tl_e0;
+#endif
+  TL_CTA(1);
+  for (int i = threadIdx.x; i < h; i += W2_THREADS) xsm[i] = xs[i];
+  const double mvs = sc[SC_MVS], fn = (jprev >= 0) ? sc[SC_FN] : 0.0;
+  double creg[NQ], acc[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) creg[q] = cm[q] ? cvec[lane + 32 * q] : 0.0;
+  double n2 = 0, ax = 0;
+  __syncthreads();
+  // one row: issue the loads of the next row (into NX), then reduce the current one (CU)
+  auto step = [&](W2Row<VT, NQ>& CU, W2Row<VT, NQ>& NX) {
+    const int p3 = (r + 2 < rend) ? (int)__ldg(rptr + r + 3) : 0;  // pointer three rows ahead closes row r + 2
+    wr += ldw;
+    w2_load<VT, NQ>(NX, r + 1 < rend, p1, p2, cl, vl, wr, jprev, cm, lane);
+    double a = 0;
+#pragma unroll
+    for (int q = 0; q < W2_EPF; ++q)
+      if (lane + 32 * q < CU.len) a += (double)CU.va[q] * xsm[CU.ci[q]];
+    for (int e = 32 * W2_EPF + lane; e < CU.len; e += 32) a += (double)__ldg(vl + CU.b + e - lane) * xsm[__ldg(cl + CU.b + e - lane)];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) a -= CU.wv[q] * creg[q];
+    a = warp_sum(a);
+    const double w = (a - mvs) - fn * CU.wp;
+    if (lane == 0) ybuf[r] = w;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) acc[q] += CU.wv[q] * w;
+    n2 += w * w;
+    ax += w;
+    p1 = p2;
+    p2 = p3;
+    ++r;
+  };
+  while (r < rend) {
+    step(RA, RB);
+    if (r >= rend) break;
+    step(RB, RA);
+  }
+  TL_CTA(2);
+  // the two scalars ride in columns nd, nd + 1 of the vector (w is warp-uniform: one lane deposits them)
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int col = lane + 32 * q;
+    if (col == nd) acc[q] = n2;
+    if (col == nd + 1) acc[q] = ax;
+  }
+  if (split) {
+    deposit_lane32(acc);
+    reduce_vec_partials(nd + 2, partials);
+  } else {
+    reduce_vec_blocks(acc, nd + 2, partials, gout, counter, pc);
+  }
+  TL_CTA(7);
+  TL_EXIT(nd);
 }
 
 // ---- v_step: the whole V side of a Lanczos step in ONE launch on a thread-block cluster -----------
@@ -564,10 +1048,12 @@ __global__ void __launch_bounds__(VS_THREADS, 1)
     v_step(const double* __restrict__ t, const double* __restrict__ mu, const double* __restrict__ rs,
            const double* __restrict__ murs, double* __restrict__ sc, double* __restrict__ V, int ldv, int j, int m_b, int h,
            double* __restrict__ ybuf, double* __restrict__ fbuf, double* __restrict__ xs, double* __restrict__ B,
-           const ZArgs z) {
+           const ZArgs z, const int* __restrict__ halt) {
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
   VSTAMP(0);
+  pdl_sync();
+  if (halt && *halt) return;  // uniform over the cluster
   cluster.barrier_arrive();  // matched below, before the first write into a neighbour's shared memory
   extern __shared__ __align__(16) double vs_dyn[];
   double(*wacc)[MAXB] = reinterpret_cast<double(*)[MAXB]>(vs_dyn);                    // [VS_WARPS][MAXB]
@@ -765,6 +1251,250 @@ __global__ void __launch_bounds__(VS_THREADS, 1)
   VSTAMP(10);
 }
 
+// ---- v_step_one: the same step when a CTA's rows fit ONE batch (h <= 8 x 128) -----------------------
+// With h ~ 1000 every warp owns at most VS_ROWS rows, so the rows of V stay in registers from the dot products
+// (phase A) to the update (phase B) and F never goes through memory; the CTA's rows of Z are staged in shared
+// memory with cp.async.  Both fetches are issued BEFORE the grid-dependency wait (V[:, :j+1] and Z[:, :j] were
+// written by earlier v_steps, three or more kernels back -- see w_step for the rule), so that after the wait
+// one round trip (t, mu, sigma) separates the kernel from its first reduction.  Arithmetic and summation orders
+// are those of v_step: both give bit-identical results.
+template <int NQ>
+__global__ void __launch_bounds__(VS_THREADS, 1)
+    v_step_one(const double* __restrict__ t, const double* __restrict__ mu, const double* __restrict__ rs,
+               const double* __restrict__ murs, double* __restrict__ sc, double* __restrict__ V, int ldv, int j, int m_b,
+               int h, double* __restrict__ ybuf, double* __restrict__ fbuf, double* __restrict__ xs,
+               double* __restrict__ B, const ZArgs z, const int* __restrict__ halt) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
+  extern __shared__ __align__(16) double vs_dyn[];
+  double(*wacc)[MAXB] = reinterpret_cast<double(*)[MAXB]>(vs_dyn);                    // [VS_WARPS][MAXB]
+  double(*psum)[MAXB] = reinterpret_cast<double(*)[MAXB]>(vs_dyn + VS_WARPS * MAXB);  // [8][MAXB]
+  double* zs = vs_dyn + (VS_WARPS + 8) * MAXB;                                        // [rows of this CTA][ldv]
+  __shared__ double call[VS_CLUSTER][MAXB];
+  __shared__ double call2[VS_CLUSTER][MAXB];
+  __shared__ double ctot[MAXB];
+  __shared__ double red2[VS_WARPS][2];
+  __shared__ double nall[VS_CLUSTER][2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nd = j + 1;
+  const int per = (h + csize - 1) / csize;
+  const int r0 = crank * per, r1 = min(h, r0 + per);
+  TL_ENTRY_REG();
+#ifdef ADOBO_B200_TIMELINE
+  const bool tl_on = true;
+#endif
+  // ---- prologue: nothing here depends on the previous two kernels ----
+  if (z.Z) {
+    const int c2n = (z.ncc + 1) >> 1, nrow = max(0, r1 - r0);
+    for (int idx = tid; idx < nrow * c2n; idx += VS_THREADS) {
+      const int row = idx / c2n, c2 = idx - row * c2n;
+      cp_async16_cg(zs + (size_t)row * ldv + 2 * c2, z.Z + (size_t)(r0 + row) * ldv + 2 * c2);
+    }
+    cp_async_commit();
+  }
+  double vq[VS_ROWS][NQ], vj[VS_ROWS];
+#pragma unroll
+  for (int i = 0; i < VS_ROWS; ++i) {
+    const int r = r0 + warp + i * VS_WARPS;
+    const bool ok = r < r1;
+    const double* vr = V + (size_t)(ok ? r : 0) * ldv;
+    vj[i] = ok ? __ldcg(vr + j) : 0.0;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) vq[i][q] = (ok && lane + 32 * q < nd) ? __ldcg(vr + lane + 32 * q) : 0.0;
+  }
+  pdl_sync();
+  if (halt && *halt) {  // uniform over the cluster
+    cp_async_wait_all();
+    return;
+  }
+  TL_SYNC(256 + j);
+  TL_CTAK(1, 0);
+  cluster.barrier_arrive();  // matched below, before the first write into a neighbour's shared memory
+  const double s = sc[SC_S], su = sc[SC_SU];
+  // ---- phase A: F = prep(t) - s V[:, j], partial c = V^T F ----
+  double f[VS_ROWS], rr[VS_ROWS], acc[NQ] = {};
+  {
+    double tv[VS_ROWS], mm[VS_ROWS];
+#pragma unroll
+    for (int i = 0; i < VS_ROWS; ++i) {
+      const int r = r0 + warp + i * VS_WARPS;
+      const bool ok = r < r1;
+      tv[i] = ok ? t[r] : 0.0;
+      mm[i] = (ok && mu) ? mu[r] : 0.0;
+      rr[i] = (ok && rs) ? rs[r] : 1.0;
+    }
+#pragma unroll
+    for (int i = 0; i < VS_ROWS; ++i) {
+      const int r = r0 + warp + i * VS_WARPS;
+      f[i] = tv[i];
+      if (mu) f[i] = (r < r1) ? (f[i] - mm[i] * su) * rr[i] : 0.0;
+      f[i] -= s * vj[i];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) acc[q] += vq[i][q] * f[i];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+    if (lane + 32 * q < MAXB) wacc[warp][lane + 32 * q] = acc[q];
+  TL_CTAK(1, 1);
+  cp_async_wait_all();
+  __syncthreads();  // the staged rows of Z have landed (every thread waited for its own copies)
+  TL_CTAK(1, 2);
+  if (z.Z && lane == 0) {  // Z[:, j] = A^T w_j, in memory and in the staged copy
+#pragma unroll
+    for (int i = 0; i < VS_ROWS; ++i) {
+      const int r = r0 + warp + i * VS_WARPS;
+      if (r < r1) {
+        const double tv = t[r];
+        z.Z[(size_t)r * ldv + j] = tv;
+        zs[(size_t)(r - r0) * ldv + j] = tv;
+      }
+    }
+  }
+  cluster.barrier_wait();  // every CTA of the cluster is running
+  {
+    const int col = tid & (MAXB - 1), part = tid >> 7;
+    double p = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) p += wacc[part * 4 + w][col];
+    psum[part][col] = p;
+  }
+  __syncthreads();
+  if (tid < nd) {
+    double p = 0;
+#pragma unroll
+    for (int g8 = 0; g8 < 8; ++g8) p += psum[g8][tid];
+    for (int q = 0; q < csize; ++q) cluster.map_shared_rank(&call[0][0], q)[crank * MAXB + tid] = p;
+  }
+  TL_CTAK(1, 3);
+  cluster.sync();
+  TL_CTAK(1, 4);
+  if (tid < nd) {
+    double p = 0;
+    for (int q = 0; q < csize; ++q) p += call[q][tid];
+    ctot[tid] = p;
+  }
+  __syncthreads();
+  // ---- phase B: F -= V c from the registers, partial ||F||^2, mu.F and Z^T (F / sigma) ----
+  double y[VS_ROWS];
+  {
+    double creg[NQ], p[VS_ROWS];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) creg[q] = (lane + 32 * q < nd) ? ctot[lane + 32 * q] : 0.0;
+#pragma unroll
+    for (int i = 0; i < VS_ROWS; ++i) {
+      p[i] = 0;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) p[i] += vq[i][q] * creg[q];
+    }
+#pragma unroll
+    for (int i = 0; i < VS_ROWS; ++i) p[i] = warp_sum(p[i]);
+#pragma unroll
+    for (int i = 0; i < VS_ROWS; ++i) y[i] = f[i] - p[i];
+  }
+  double n2 = 0, ax = 0, zacc[NQ] = {};
+#pragma unroll
+  for (int i = 0; i < VS_ROWS; ++i) {
+    const int r = r0 + warp + i * VS_WARPS;
+    const bool ok = r < r1;
+    const double cf = (ok && murs) ? murs[r] : (ok ? 1.0 : 0.0);
+    if (lane == 0 && ok) ybuf[r] = y[i];
+    n2 += y[i] * y[i];
+    ax += cf * y[i];
+    if (z.Z && ok) {
+      const double* zr = zs + (size_t)(r - r0) * ldv;
+      const double yz = rs ? y[i] * rr[i] : y[i];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+        if (lane + 32 * q < z.ncc) zacc[q] += zr[lane + 32 * q] * yz;
+    }
+  }
+  if (z.Z) {  // wacc is free again: every CTA passed the first cluster barrier after reading it
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) wacc[warp][lane + 32 * q] = zacc[q];
+  }
+  if (lane == 0) {
+    red2[warp][0] = n2;
+    red2[warp][1] = ax;
+  }
+  __syncthreads();
+  if (warp == 0) {  // the 32 warp partials of (||F||^2, mu.F): one butterfly each instead of two serial chains
+    const double p0 = warp_sum(red2[lane][0]), p1 = warp_sum(red2[lane][1]);
+    if (lane < 2) {
+      const double p = lane == 0 ? p0 : p1;
+      for (int q = 0; q < csize; ++q) cluster.map_shared_rank(&nall[0][0], q)[crank * 2 + lane] = p;
+    }
+  }
+  if (z.Z) {
+    {
+      const int col = tid & (MAXB - 1), part = tid >> 7;
+      double p = 0;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) p += wacc[part * 4 + w][col];
+      psum[part][col] = p;
+    }
+    __syncthreads();
+    if (tid >= 32 && tid < 32 + z.ncc) {
+      const int col = tid - 32;
+      double p = 0;
+#pragma unroll
+      for (int g8 = 0; g8 < 8; ++g8) p += psum[g8][col];
+      for (int q = 0; q < csize; ++q) cluster.map_shared_rank(&call2[0][0], q)[crank * MAXB + col] = p;
+    }
+  }
+  // inputs of the coefficient update are fetched before the barrier (w_step / spmvT_csc wrote them, not this kernel)
+  const bool ccthread = z.Z && crank == 0 && tid >= 32 && tid < 32 + z.ncc;
+  double g_j = 0, g_j1 = 0, g_col = 0, sw_col = 0;
+  if (ccthread) {
+    g_j = z.gprev[j], g_j1 = z.gprev[j + 1];
+    if (tid - 32 != j) g_col = z.gprev[tid - 32], sw_col = z.sumW[tid - 32];
+  }
+  TL_CTAK(1, 5);
+  cluster.sync();
+  TL_CTAK(1, 6);
+  double tot0 = (lane < csize) ? nall[lane][0] : 0.0, tot1 = (lane < csize) ? nall[lane][1] : 0.0;
+  tot0 = warp_sum(tot0);  // fixed butterfly, identical in every warp of every CTA
+  tot1 = warp_sum(tot1);
+  // finish from the registers: V[:, j+1] = F / ||F||, x = F / (||F|| sigma)
+  const double nrm = sqrt(tot0);
+  const double inv = inv_or_zero(nrm);
+  const int jn = j + 1;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < VS_ROWS; ++i) {
+      const int r = r0 + warp + i * VS_WARPS;
+      if (r < r1) {
+        const double v = inv * y[i];
+        fbuf[r] = v;
+        if (jn < m_b) V[(size_t)r * ldv + jn] = v;
+        xs[r] = rs ? v * rr[i] : v;
+      }
+    }
+  }
+  if (ccthread) {
+    const int col = tid - 32;
+    double zsum = 0;
+    for (int q = 0; q < csize; ++q) zsum += call2[q][col];
+    const double sinvp = inv_or_zero(sqrt(g_j));
+    const double sw = (col == j) ? g_j1 * sinvp : sw_col;
+    if (col == j) z.sumW[j] = sw;
+    const double mvs = murs ? inv * tot1 : 0.0;
+    double cc = inv * zsum - mvs * sw;
+    if (z.prev) cc -= nrm * ((col == j) ? 1.0 : g_col * sinvp);
+    z.cvec[col] = cc;
+  }
+  if (crank == 0 && tid == 0) {
+    sc[SC_NRM2] = tot0;
+    sc[SC_AUX] = tot1;
+    sc[SC_FN] = nrm;
+    sc[SC_FNINV] = inv;
+    sc[SC_MVS] = murs ? inv * tot1 : 0.0;
+    if (j < m_b - 1) B[(size_t)j * m_b + j + 1] = nrm;  // irlb.py:197
+  }
+  TL_CTAK(1, 7);
+  TL_EXIT(256 + j);
+}
+
 // ---- normalise F, store V[:, jn], prepare x = F / sigma and mu.x, write B[j,j], B[j,j+1] ---------
 __global__ void v_finish(const double* __restrict__ ybuf, const double* __restrict__ rs, double* __restrict__ sc,
                          double* __restrict__ V, int ldv, int jn, int m_b, int h, double* __restrict__ fbuf,
@@ -790,8 +1520,23 @@ __global__ void v_finish(const double* __restrict__ ybuf, const double* __restri
 // B[jn, jn] = ||w|| is complete here, so the SVD of B can start while the last F is still being computed
 __global__ void w_finish(const double* __restrict__ ybuf, const double* __restrict__ n2p, double* __restrict__ sc,
                          double* __restrict__ W, int ldw, int jn, i64 n, double* __restrict__ wcur, double* __restrict__ B,
-                         int m_b) {
-  const double s = sqrt(n2p[0]);
+                         int m_b, const int* __restrict__ halt, const double* __restrict__ parts, int nblk,
+                         double* __restrict__ gout) {
+  if (halt && *halt) return;
+  __shared__ double s_n2[2];
+  if (parts) {  // split reduction: columns jn, jn + 1 of w_step's per-CTA partials
+    if (threadIdx.x < 32) {
+      double t0, t1;
+      sum_partials_two(parts, nblk, jn, t0, t1);
+      if (threadIdx.x == 0) {
+        s_n2[0] = t0, s_n2[1] = t1;
+        if (blockIdx.x == 0) gout[jn] = t0, gout[jn + 1] = t1;  // v_step reads them for sumW[jn]
+      }
+    }
+    __syncthreads();
+  }
+  const double n2v = parts ? s_n2[0] : n2p[0], syv = parts ? s_n2[1] : n2p[1];
+  const double s = sqrt(n2v);
   const double sinv = inv_or_zero(s);
   const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (r < n) {
@@ -801,9 +1546,11 @@ __global__ void w_finish(const double* __restrict__ ybuf, const double* __restri
   }
   if (r == 0) {
     sc[SC_S] = s;
-    sc[SC_SU] = sinv * n2p[1];
+    sc[SC_SU] = sinv * syv;
     B[(size_t)jn * m_b + jn] = s;  // irlb.py:196 / 221
   }
+  TL_ENTRY(387);
+  TL_EXIT(387);
 }
 
 // ---- one-sided Jacobi SVD of B (m x m, row-major, m <= 128) in one CTA ---------------------------
@@ -893,6 +1640,7 @@ __global__ void __launch_bounds__(JTHREADS, 1) jacobi_svd(const double* __restri
   __shared__ int rankof[128];
   const int tid = threadIdx.x;
   const int grp = tid / JL, sl = tid % JL;
+  if (info[4] != 0) return;  // halt flag (see conv_check)
   for (int idx = tid; idx < mc * LD; idx += blockDim.x) {
     const int col = idx / LD, row = idx - col * LD;
     G[idx] = (row < m && col < m) ? B[(size_t)row * m + col] : 0.0;
@@ -1073,14 +1821,23 @@ static jacobi_fn jacobi_for(int m) {
 }
 
 // ---- residuals, convergence count and the next k (irlb.py:225-234) ------------------------------
+// info[0] = converged values (-1: svd_arrow rejected its own result), info[1] = next k, info[4] = halt flag
+// (1 converged, 2 SVD rejected: every kernel of a later, speculatively launched iteration returns at once),
+// info[5] = outer iterations completed.  `force`: run although the halt flag is set (host fallback path).
+// With St != nullptr all CTAs also lay out the two rotation matrices of the coming restart (transpose_s, for
+// the k this kernel has just decided), so the restart starts with the rotation itself.
 __global__ void conv_check(const double* __restrict__ Su, const double* __restrict__ sv, double* __restrict__ sc,
                            int m, int nu, int k, int it, double tol, double* __restrict__ R, int* __restrict__ info,
-                           int honour_flag) {
-  __shared__ int cnt;
+                           int honour_flag, int force, const double* __restrict__ Sv, double* __restrict__ St,
+                           const double* __restrict__ cvec, const double* __restrict__ sumW, double* __restrict__ crot) {
+  __shared__ int cnt, s_kn;
+  if (!force && info[4] != 0) return;
+  TL_ENTRY(386);
   if (honour_flag && info[3] == 0) {  // svd_arrow rejected its own result: the host re-runs jacobi_svd
-    if (threadIdx.x == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
       info[0] = -1;
       info[1] = k;
+      info[4] = 2;
     }
     return;
   }
@@ -1088,19 +1845,58 @@ __global__ void conv_check(const double* __restrict__ Su, const double* __restri
   __syncthreads();
   const double fn = sc[SC_FN];
   double smax = sv[0];
-  if (it > 0) smax = fmax(smax, sc[SC_SMAX]);
+  if (it > 0) smax = fmax(smax, sc[SC_SMAX]);  // CTA 0 may already have stored the new maximum: same value
   for (int i = threadIdx.x; i < m; i += blockDim.x) {
     const double r = fn * Su[(size_t)i * m + (m - 1)];
-    R[i] = r;
+    if (blockIdx.x == 0) R[i] = r;
     if (i < nu && fabs(r) < tol * smax) atomicAdd(&cnt, 1);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    sc[SC_SMAX] = smax;
     int kn = max(cnt + nu, k);
     kn = min(kn, m - 3);
-    info[0] = cnt;
-    info[1] = kn;
+    s_kn = kn;
+    if (blockIdx.x == 0) {
+      sc[SC_SMAX] = smax;
+      info[0] = cnt;
+      info[1] = kn;
+      info[4] = (cnt >= nu) ? 1 : 0;
+      info[5] += 1;
+    }
+  }
+  if (St == nullptr) return;
+  __syncthreads();
+  const int kc = s_kn, kcp = (kc + 7) & ~7, per = m * kcp;
+  if (cvec && blockIdx.x > 0) {
+    // Z formulation (see w_step): the pre-computed coefficients and the column sums of W in the rotated basis,
+    // c <- Su[:, :k]^T c, sumW <- Su[:, :k]^T sumW (Su[c * m + i] = component i of left vector c); a warp per
+    // output, into crot[0..MAXB) / crot[MAXB..) -- set_restart copies them in place after the rotation
+    const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int q = ((int)blockIdx.x - 1) * nw + (threadIdx.x >> 5); q < kc; q += ((int)gridDim.x - 1) * nw) {
+      double nc = 0, ns = 0;
+#pragma unroll
+      for (int ee = 0; ee < MAXB / 32; ++ee) {
+        const int e = lane + 32 * ee;
+        if (e < m) {
+          const double u = Su[(size_t)q * m + e];
+          nc = fma(u, cvec[e], nc);
+          ns = fma(u, sumW[e], ns);
+        }
+      }
+      nc = warp_sum(nc);
+      ns = warp_sum(ns);
+      if (lane == 0) {
+        crot[q] = nc;
+        crot[MAXB + q] = ns;
+      }
+    }
+  }
+  TL_EXIT(386);
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 2 * per; idx += gridDim.x * blockDim.x) {
+    const double* S = (idx < per) ? Sv : Su;
+    const int e = (idx < per) ? idx : idx - per;
+    const int i = e / kcp, c = e - i * kcp;
+    St[idx] = (c < kc) ? S[(size_t)c * m + i] : 0.0;
   }
 }
 
@@ -1136,17 +1932,12 @@ struct RotJob {
   const double* colscale;  // optional per-column factor (var_weigh)
 };
 
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // The rotations of a restart -- V (h rows), Z = A^T W (h rows, optional) and W (n rows) -- run as ONE launch: CTAs
 // [0, nba) take job a, [nba, nba + nbb) job b, the rest job c, so the small jobs do not occupy a nearly empty GPU.
 __global__ void __launch_bounds__(512) rotate_basis(const RotJob ja, const RotJob jb, const RotJob jc, int nba, int nbb,
-                                                    int ld, int m, int kc, int nbuf) {
+                                                    int ld, int m, int kc, int nbuf, const int* __restrict__ halt) {
+  if (halt && *halt) return;
   const int which = ((int)blockIdx.x >= nba) + ((int)blockIdx.x >= nba + nbb);
   const RotJob& job = which == 0 ? ja : (which == 1 ? jb : jc);
   double* __restrict__ Q = job.Q;
@@ -1249,7 +2040,9 @@ constexpr int RR_CHUNKS = 4;
 
 template <int R>
 __global__ void __launch_bounds__(512) rotate_rows(const RotJob ja, const RotJob jb, const RotJob jc, int nba, int nbb,
-                                                   int ld, int m, int kc) {
+                                                   int ld, int m, int kc, const int* __restrict__ halt) {
+  if (halt && *halt) return;
+  TL_ENTRY(384);
   const int which = ((int)blockIdx.x >= nba) + ((int)blockIdx.x >= nba + nbb);
   const RotJob& job = which == 0 ? ja : (which == 1 ? jb : jc);
   double* __restrict__ Q = job.Q;
@@ -1343,8 +2136,9 @@ __global__ void __launch_bounds__(512) rotate_rows(const RotJob ja, const RotJob
       }
     }
   }
+  TL_EXIT(384);
 }
-using rotate_rows_fn = void (*)(const RotJob, const RotJob, const RotJob, int, int, int, int, int);
+using rotate_rows_fn = void (*)(const RotJob, const RotJob, const RotJob, int, int, int, int, int, const int*);
 static rotate_rows_fn rotate_rows_for(int R) {
   switch (R) {
     case 1: return rotate_rows<1>;
@@ -1356,50 +2150,16 @@ static rotate_rows_fn rotate_rows_for(int R) {
 }
 
 // ---- V[:,k] = F ; B = diag(sv[:k]) + R[:k] in column k  (irlb.py:239-244) ------------------------
-// With the Z formulation (see w_step) CTA 0 also maps the pre-computed coefficients and the column sums of W to
-// the rotated basis: c <- Su[:, :k]^T c, sumW <- Su[:, :k]^T sumW  (Su[c * m + i] = component i of left vector c).
+// With the Z formulation (see w_step) CTA 0 also installs the pre-computed coefficients and the column sums of W
+// in the rotated basis (computed by conv_check).
 __global__ void set_restart(double* __restrict__ V, int ldv, int h, const double* __restrict__ fbuf,
                             double* __restrict__ B, int m, int k, const double* __restrict__ sv,
                             const double* __restrict__ R, double* __restrict__ cvec, double* __restrict__ sumW,
-                            const double* __restrict__ Su) {
-  if (cvec && blockIdx.x == 0) {
-    __shared__ double oc[MAXB], os[MAXB];
-    for (int q = threadIdx.x; q < m; q += blockDim.x) {
-      oc[q] = cvec[q];
-      os[q] = sumW[q];
-    }
-    __syncthreads();
-    // a warp per output, lanes along the (contiguous) vector; four outputs per trip keep their loads in flight
-    const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int q0 = threadIdx.x >> 5; q0 < k; q0 += 4 * nw) {
-      double nc[4] = {0, 0, 0, 0}, ns[4] = {0, 0, 0, 0};
-#pragma unroll
-      for (int u4 = 0; u4 < 4; ++u4) {
-        const int q = q0 + u4 * nw;
-#pragma unroll
-        for (int ee = 0; ee < MAXB / 32; ++ee) {
-          const int e = lane + 32 * ee;
-          if (q < k && e < m) {
-            const double u = Su[(size_t)q * m + e];
-            nc[u4] = fma(u, oc[e], nc[u4]);
-            ns[u4] = fma(u, os[e], ns[u4]);
-          }
-        }
-      }
-#pragma unroll
-      for (int u4 = 0; u4 < 4; ++u4) {
-        nc[u4] = warp_sum(nc[u4]);
-        ns[u4] = warp_sum(ns[u4]);
-      }
-#pragma unroll
-      for (int u4 = 0; u4 < 4; ++u4) {
-        const int q = q0 + u4 * nw;
-        if (q < k && lane == 0) {
-          cvec[q] = nc[u4];
-          sumW[q] = ns[u4];
-        }
-      }
-    }
+                            const double* __restrict__ crot, const int* __restrict__ halt) {
+  if (halt && *halt) return;
+  if (cvec && blockIdx.x == 0 && threadIdx.x < k) {  // rotated by the conv_check of the previous iteration
+    cvec[threadIdx.x] = crot[threadIdx.x];
+    sumW[threadIdx.x] = crot[MAXB + threadIdx.x];
   }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < h) V[(size_t)i * ldv + k] = fbuf[i];
@@ -1410,6 +2170,8 @@ __global__ void set_restart(double* __restrict__ V, int ldv, int h, const double
     if (r < k && c == k) v = R[r];
     B[i] = v;
   }
+  TL_ENTRY(385);
+  TL_EXIT(385);
 }
 
 __global__ void mul_vec(const double* a, const double* b, double* out, int n) {
@@ -1432,6 +2194,35 @@ static unsigned red_blocks(adobo_ctx* c, i64 rows) {  // 1024-thread CTAs of the
   return (unsigned)b;
 }
 
+// Launch with optional attributes: thread-block cluster, programmatic dependent launch (the kernel may start
+// while the previous kernel of the stream drains; it calls pdl_sync() before touching that kernel's output).
+template <typename... KA, typename... A>
+static cudaError_t launch_k(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, int cluster,
+                            A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  unsigned na = 0;
+  if (cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)cluster;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);
+}
+
 // Workspace of the Lanczos driver.  It lives in the context across calls so that (a) repeated PCA
 // calls on same-shaped data do not re-allocate and (b) the CUDA graphs of one outer iteration --
 // keyed by (first iteration?, k) -- stay valid and are replayed: one graph launch and one 16-byte
@@ -1441,17 +2232,22 @@ struct IrlbWs {
   i64 sig_n = -1;
   int sig_i[6] = {};
   double sig_tol = 0;
-  DevBuf<double> V, W, B, sc, tbuf, ybuf_h, ybuf_n, fbuf, xs, wcur, cvec, partials, Su, Sv, svd_s, R, murs, St, Z, sumW, gout;
+  DevBuf<double> V, W, B, sc, tbuf, ybuf_h, ybuf_n, fbuf, xs, wcur, cvec, partials, Su, Sv, svd_s, R, murs, St, Z, sumW, gout, crot;
   DevBuf<unsigned> counter;
-  DevBuf<int> info;
+  DevBuf<int> info, perm;
   std::map<int, cudaGraphExec_t> graphs;
   std::map<int, i64> graph_launches;
+  cudaEvent_t ev[4] = {};  // completion of the outer iterations in flight (run-ahead)
   void clear_graphs() {
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
     graphs.clear();
     graph_launches.clear();
   }
-  ~IrlbWs() { clear_graphs(); }
+  ~IrlbWs() {
+    clear_graphs();
+    for (auto& e : ev)
+      if (e) cudaEventDestroy(e);
+  }
 };
 static void free_irlb_ws(void* p) { delete (IrlbWs*)p; }
 
@@ -1481,7 +2277,10 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     const void* sp[8] = {A.rptr.p, A.cidx.p, A.rval.p, A.cptr.p, A.ridx.p, A.cval.p, mu, rs};
     // test hooks read from the environment change what a captured iteration contains
     const int hooks = (getenv("ADOBO_B200_SVD_JACOBI") ? 1 : 0) | (getenv("ADOBO_B200_NO_FORK") ? 2 : 0) |
-                      (getenv("ADOBO_B200_ROTATE_STREAMED") ? 4 : 0) | (getenv("ADOBO_B200_NO_VSTEP") ? 8 : 0) | (getenv("ADOBO_B200_NO_WFOLD") ? 1024 : 0) | (getenv("ADOBO_B200_NO_ZPATH") ? 2048 : 0) | (svd_arrow_cluster() << 4);
+                      (getenv("ADOBO_B200_ROTATE_STREAMED") ? 4 : 0) | (getenv("ADOBO_B200_NO_VSTEP") ? 8 : 0) | (getenv("ADOBO_B200_NO_WFOLD") ? 1024 : 0) | (getenv("ADOBO_B200_NO_ZPATH") ? 2048 : 0) | (getenv("ADOBO_B200_NO_PDL") ? 4096 : 0) |
+                      (getenv("ADOBO_B200_NO_RUNAHEAD") ? 8192 : 0) | (getenv("ADOBO_B200_NO_VONE") ? 16384 : 0) | (getenv("ADOBO_B200_NO_STSM") ? (1 << 17) : 0) | (getenv("ADOBO_B200_WSTEP_V1") ? (1 << 18) : 0) | (getenv("ADOBO_B200_NO_SPLIT") ? (1 << 19) : 0) |
+                      (getenv("ADOBO_B200_IRLB_TRACE") ? 32768 : 0) | (getenv("ADOBO_B200_SVD_FORCE_FALLBACK") ? 65536 : 0) |
+                      (svd_arrow_cluster() << 4);
     const int si[6] = {h, nu, m_b, c->world, (int)sizeof(VT), hooks};
     bool same = ws.sig_n == n && ws.sig_tol == tol;
     for (int q = 0; q < 8; ++q) same = same && ws.sig_ptr[q] == sp[q];
@@ -1519,7 +2318,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     svd_s.ensure((size_t)MAXB);
     R.ensure((size_t)MAXB);
     counter.ensure(2);
-    info.ensure(4);
+    info.ensure(8);
     murs.ensure((size_t)h);
     const double* after[4] = {V.p, W.p, partials.p, murs.p};
     for (int q = 0; q < 4; ++q)
@@ -1535,7 +2334,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   CUDA_CHECK(cudaMemsetAsync(sc.p, 0, sizeof(double) * SC_COUNT, st));
   CUDA_CHECK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned) * 2, st));
   CUDA_CHECK(cudaMemsetAsync(cvec.p, 0, sizeof(double) * MAXB, st));
-  CUDA_CHECK(cudaMemsetAsync(info.p, 0, sizeof(int) * 4, st));
+  CUDA_CHECK(cudaMemsetAsync(info.p, 0, sizeof(int) * 8, st));
   if (centered) LAUNCH(c, "mul_vec", (mul_vec<<<(h + 255) / 256, 256, 0, st>>>(mu, rs, murs.p, h)));
   // SVD kernel resources
   const size_t svd_smem = sizeof(double) * ((size_t)(m_b + 1) * JL * jacobi_rows_per_lane(m_b) + 260);
@@ -1547,6 +2346,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   const size_t rot_smem = rot_s + rot_nbuf * rot_q;
   CUDA_CHECK(cudaFuncSetAttribute(rotate_basis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rot_smem));
   ws.St.ensure((size_t)2 * MAXB * MAXB);
+  ws.crot.ensure((size_t)2 * MAXB);
   DevBuf<double>& St = ws.St;
   // V[:, :kc] (or outv) = V Sv[:, :kc]  and  W[:, :kc] (or outw) = W Su[:, :kc], one launch each for the
   // transposes and for the two tall-skinny GEMMs
@@ -1565,9 +2365,30 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     CUDA_CHECK(cudaMemsetAsync(ws.gout.p, 0, sizeof(double) * MAXB, st));
   }
   DevBuf<double>&Z = ws.Z, &sumW = ws.sumW, &gout = ws.gout;
-  auto rotate2 = [&](int kc, double* outv, double* outw, int ldo, const double* scale_w) {
+  const bool pdl = getenv("ADOBO_B200_NO_PDL") == nullptr;  // programmatic dependent launch of the step kernels
+  const bool use_vstep = h <= 8192 && getenv("ADOBO_B200_NO_VSTEP") == nullptr;
+  // one batch of rows per warp and the CTA's rows of Z staged in shared memory: v_step_one
+  const int vs_per = (h + VS_CLUSTER - 1) / VS_CLUSTER;
+  const size_t vs_one_smem = sizeof(double) * ((size_t)(VS_WARPS + 8) * MAXB + (zpath ? (size_t)vs_per * ld : 0));
+  const bool vs_one = use_vstep && vs_per <= VS_WARPS * VS_ROWS && vs_one_smem <= 200 * 1024 &&
+                      getenv("ADOBO_B200_NO_VONE") == nullptr;
+  const bool wstep2 = n < (i64(1) << 31) && getenv("ADOBO_B200_WSTEP_V1") == nullptr;
+  // split reduction of w_step's vector (see reduce_vec_partials): single GPU, lean kernels on both sides
+  const bool split = c->world == 1 && zpath && vs_one && wstep2 && getenv("ADOBO_B200_NO_SPLIT") == nullptr &&
+                     getenv("ADOBO_B200_NO_WFOLD") == nullptr;  // the consuming spmvT_csc sums g: needs the folded finish
+  if (wstep2) {
+    CUDA_CHECK(cudaFuncSetAttribute(w_step2<VT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * h)));
+    CUDA_CHECK(cudaFuncSetAttribute(w_step2<VT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * h)));
+  }
+  // under programmatic launch w_step2's CTAs start while v_step still holds VS_CLUSTER SMs: a CTA that had to wait
+  // for one of those runs its whole prologue after everybody else's -- leave them out of the grid
+  const i64 w2_sms = (pdl && use_vstep && c->sm_count > 4 * VS_CLUSTER) ? c->sm_count - VS_CLUSTER : c->sm_count;
+  const unsigned gb_w2 = (unsigned)std::max<i64>(1, std::min<i64>(w2_sms, (n + W2_THREADS / 32 - 1) / (W2_THREADS / 32)));
+  const int* hp = nullptr;  // halt flag handed to the kernels of an outer iteration (run-ahead), else none
+  auto rotate2 = [&](int kc, double* outv, double* outw, int ldo, const double* scale_w, bool st_ready) {
     const int kcp = (kc + 7) & ~7;
-    LAUNCH(c, "transpose_s", (transpose_s<<<(2 * m_b * kcp + 255) / 256, 256, 0, st>>>(Sv.p, Su.p, m_b, kc, kcp, St.p)));
+    if (!st_ready)  // restarts: conv_check has laid the two matrices out already
+      LAUNCH(c, "transpose_s", (transpose_s<<<(2 * m_b * kcp + 255) / 256, 256, 0, st>>>(Sv.p, Su.p, m_b, kc, kcp, St.p)));
     const bool with_z = zpath && outv == nullptr;  // restart rotation: Z = A^T W follows W
     RotJob jv{V.p, (i64)h, St.p, outv, ldo, nullptr};
     RotJob jz{with_z ? Z.p : nullptr, with_z ? (i64)h : 0, St.p + (size_t)m_b * kcp, nullptr, 0, nullptr};
@@ -1591,10 +2412,10 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
       const size_t smem = s_bytes + sizeof(double) * (size_t)m_b * (32 * Rr + 1);
       rotate_rows_fn fn = rotate_rows_for(Rr);
       CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      LAUNCH(c, "rotate_basis", (fn<<<nbv + nbz + nbw, 32 * (kcp / 8), smem, st>>>(jv, jz, jw, (int)nbv, (int)nbz, ld, m_b, kc)));
+      LAUNCH(c, "rotate_basis", (fn<<<nbv + nbz + nbw, 32 * (kcp / 8), smem, st>>>(jv, jz, jw, (int)nbv, (int)nbz, ld, m_b, kc, hp)));
     } else {
       LAUNCH(c, "rotate_basis", (rotate_basis<<<nbv + nbz + nbw, 32 * (kcp / 8), rot_smem, st>>>(jv, jz, jw, (int)nbv, (int)nbz,
-                                                                                           ld, m_b, kc, rot_nbuf)));
+                                                                                           ld, m_b, kc, rot_nbuf, hp)));
     }
   };
   const bool use_arrow = getenv("ADOBO_B200_SVD_JACOBI") == nullptr;
@@ -1640,11 +2461,20 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     // W[:, jn] = normalise( orthog( A_s x - fn W[:, jprev], W[:, :nd] ) )
     if (zpath) {  // one pass: the coefficients were left in cvec by v_step (set_restart after a restart)
       WORK(c, (double)A.nnz * (4.0 + sizeof(VT)) + 8.0 * (n + 1) + 8.0 * n * (nd + (jprev >= 0 ? 1 : 0) + 1) + 8.0 * h);
-      LAUNCH(c, "w_step", (w_step<VT><<<gb_n, RT_THREADS, 0, st>>>(A.rptr.p, A.cidx.p, A.rval.p, xs.p, sc.p, W.p, ld, jprev, nd, n,
-                                                                 cvec.p, ybuf_n.p, partials.p, gout.p, counter.p, pcw)));
+      // programmatic launch behind v_step; the first column after a restart follows ordinary kernels
+      if (wstep2)
+        LAUNCH(c, "w_step", CUDA_CHECK(launch_k(m_b + 1 <= 96 ? w_step2<VT, 3> : w_step2<VT, 4>, dim3(gb_w2), dim3(W2_THREADS),
+                                                sizeof(double) * h, st, pdl && jprev >= 0, 1, A.rptr.p, A.cidx.p, A.rval.p, xs.p,
+                                                sc.p, W.p, ld, jprev, nd, (int)n, cvec.p, ybuf_n.p, partials.p, gout.p, counter.p,
+                                                pcw, hp, h, split ? 1 : 0)));
+      else
+        LAUNCH(c, "w_step", CUDA_CHECK(launch_k(m_b + 1 <= 96 ? w_step<VT, 3> : w_step<VT, 4>, dim3(gb_n), dim3(RT_THREADS), 0, st,
+                                                pdl && jprev >= 0, 1, A.rptr.p, A.cidx.p, A.rval.p, xs.p, sc.p, W.p, ld, jprev, nd, n,
+                                                cvec.p, ybuf_n.p, partials.p, gout.p, counter.p, pcw, hp)));
       if (!fused) allreduce_sum_f64(c, gout.p, (size_t)nd + 2);
       if (!(fold_wt && jn != m_b - 1))
-        LAUNCH(c, "w_finish", (w_finish<<<fin_n, 256, 0, st>>>(ybuf_n.p, gout.p + nd, sc.p, W.p, ld, jn, n, wcur.p, B.p, m_b)));
+        LAUNCH(c, "w_finish", (w_finish<<<fin_n, 256, 0, st>>>(ybuf_n.p, gout.p + nd, sc.p, W.p, ld, jn, n, wcur.p, B.p, m_b, hp,
+                                                               split ? partials.p : nullptr, (int)gb_w2, gout.p)));
       return;
     }
     WORK(c, (double)A.nnz * (4.0 + sizeof(VT)) + 8.0 * (n + 1) + 8.0 * n * (nd + (jprev >= 0 ? 1 : 0) + 1) + 8.0 * h);
@@ -1671,15 +2501,15 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
                                                                     w_fin(jn))));
     if (!fused) allreduce_sum_f64(c, sc.p + SC_NRM2, 2);
     if ((wide_rows || !fold_w) && !(fold_wt && jn != m_b - 1)) LAUNCH(c, "w_finish", (w_finish<<<fin_n, 256, 0, st>>>(ybuf_n.p, sc.p + SC_NRM2, sc.p, W.p, ld, jn, n, wcur.p, B.p,
-                                                                                       m_b)));
+                                                                                       m_b, nullptr, nullptr, 0, nullptr)));
   };
   // restart update (irlb.py:238-246): Ritz vectors into the leading k columns, V[:,k] = F, new B
   auto restart_update = [&](int k) {
-    rotate2(k, nullptr, nullptr, 0, nullptr);
+    rotate2(k, nullptr, nullptr, 0, nullptr, true);
     LAUNCH(c, "set_restart", (set_restart<<<(std::max(h, m_b * m_b) + 255) / 256, 256, 0, st>>>(V.p, ld, h, fbuf.p, B.p,
                                                                                             m_b, k, svd_s.p, R.p,
                                                                                             zpath ? cvec.p : nullptr, sumW.p,
-                                                                                            Su.p)));
+                                                                                            ws.crot.p, hp)));
   };
   // one outer iteration (irlb.py:155-231) up to the convergence read-back
   const bool use_graphs = !c->profiling && getenv("ADOBO_B200_NO_GRAPH") == nullptr;
@@ -1693,13 +2523,67 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
       LAUNCH(c, "jacobi_svd", (jacobi<<<1, JTHREADS, svd_smem, s>>>(B.p, m_b, Su.p, svd_s.p, Sv.p, info.p)));
   };
   const bool fork_svd = use_graphs && getenv("ADOBO_B200_NO_FORK") == nullptr;
+  constexpr int RUN_DEPTH = 3, CC_BLOCKS = 16;
+  const bool trace = getenv("ADOBO_B200_IRLB_TRACE") != nullptr;  // diagnostic: one line per outer iteration
+  const bool runahead = use_graphs && zpath && (c->world == 1 || (fused && fused_t)) && !trace && !force_fallback &&
+                        getenv("ADOBO_B200_NO_RUNAHEAD") == nullptr;
   // V side of a step as one cluster kernel (short V), or three grid-wide kernels (very long V)
-  const bool use_vstep = h <= 8192 && getenv("ADOBO_B200_NO_VSTEP") == nullptr;
   if (use_vstep) {  // static + dynamic shared memory of v_step exceeds the 48 KB default
     CUDA_CHECK(cudaFuncSetAttribute(v_step<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (VS_WARPS + 8) * MAXB)));
     CUDA_CHECK(cudaFuncSetAttribute(v_step<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (VS_WARPS + 8) * MAXB)));
+    if (vs_one) {
+      CUDA_CHECK(cudaFuncSetAttribute(v_step_one<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vs_one_smem));
+      CUDA_CHECK(cudaFuncSetAttribute(v_step_one<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vs_one_smem));
+    }
+  }
+  // short shards: A^T u with u staged in shared memory, one CTA per SM
+  const size_t st_smem = sizeof(double) * (size_t)std::max<i64>(n, 2);
+  const int st_cpb = (h + c->sm_count - 1) / c->sm_count;  // columns per CTA
+  const bool st_sm = n >= 2 && n < (1 << 30) && st_smem <= 200 * 1024 && st_cpb <= STS_MAXC && A.nnz < (i64(1) << 31) &&
+                     getenv("ADOBO_B200_NO_STSM") == nullptr;
+  const unsigned st_grid = (unsigned)((h + st_cpb - 1) / st_cpb);
+  if (st_sm) {
+    // deal the columns to the CTAs by length: sorted descending, snake order, slot k of CTA b at perm[b + grid k]
+    std::vector<i64> hc((size_t)h + 1);
+    CUDA_CHECK(cudaMemcpyAsync(hc.data(), A.cptr.p, sizeof(i64) * (h + 1), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    std::vector<int> order(h), permh((size_t)3 * st_grid * st_cpb, 0);
+    for (size_t q = 0; q < (size_t)st_grid * st_cpb; ++q) permh[3 * q] = -1;
+    for (int q = 0; q < h; ++q) order[q] = q;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return hc[a + 1] - hc[a] > hc[b + 1] - hc[b]; });
+    for (int q = 0; q < h; ++q) {
+      const int k = q / (int)st_grid, pos = q % (int)st_grid, col = order[q];
+      int* d = &permh[3 * ((size_t)k * st_grid + ((k & 1) ? (int)st_grid - 1 - pos : pos))];
+      d[0] = col, d[1] = (int)hc[col], d[2] = (int)(hc[col + 1] - hc[col]);
+    }
+    {
+      const int* before = ws.perm.p;
+      ws.perm.ensure(permh.size());
+      if (before != ws.perm.p) ws.clear_graphs();
+    }
+    CUDA_CHECK(cudaMemcpyAsync(ws.perm.p, permh.data(), sizeof(int) * permh.size(), cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));  // permh goes out of scope
+  }
+  if (st_sm) CUDA_CHECK(cudaFuncSetAttribute(spmvT_csc_sm<VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem));
+  // One shared-memory carve-out for every kernel of the iteration: spmvT_csc_sm / v_step_one / rotate_rows need
+  // 150-200 KB, and an SM that alternates between a small and a large carve-out is reconfigured (drained) at
+  // each switch.
+  if (getenv("ADOBO_B200_NO_CARVEOUT") == nullptr) {
+    auto prefer = [&](const void* fn) {
+      CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    };
+    prefer((const void*)w_step<VT, 3>), prefer((const void*)w_step<VT, 4>);
+    prefer((const void*)w_step2<VT, 3>), prefer((const void*)w_step2<VT, 4>);
+    prefer((const void*)spmvT_csc<VT>), prefer((const void*)spmvT_csc_sm<VT>);
+    prefer((const void*)v_step<3>), prefer((const void*)v_step<4>);
+    prefer((const void*)v_step_one<3>), prefer((const void*)v_step_one<4>);
+    prefer((const void*)w_finish), prefer((const void*)set_restart), prefer((const void*)conv_check);
+    prefer((const void*)rotate_basis);
+    for (int R = 1; R <= 5; ++R) prefer((const void*)rotate_rows_for(R));
+    prefer((const void*)jacobi);
   }
   auto enqueue_iteration = [&](bool first, int k) {
+    hp = runahead ? info.p + 4 : nullptr;
     if (!first) restart_update(k);
     int j = first ? 0 : k;
     w_column(-1, j, j);
@@ -1717,32 +2601,37 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
         const bool infold = fold_wt && j != m_b - 1;
         if (infold)
           wf.W = W.p, wf.ldw = ld, wf.jn = j, wf.m_b = m_b, wf.n = n, wf.sc = sc.p, wf.B = B.p,
-          wf.n2p = zpath ? gout.p + j : sc.p + SC_NRM2;  // column j came from w_step with nd = j
-        LAUNCH(c, "spmvT_csc", (spmvT_csc<VT><<<h, 256, 0, st>>>(A.cptr.p, A.ridx.p, A.cval.p, infold ? ybuf_n.p : wcur.p, tbuf.p,
-                                                                 h, counter.p + 1, fused_t ? pcw : pc1, wf)));
+          wf.n2p = zpath ? gout.p + j : sc.p + SC_NRM2,  // column j came from w_step with nd = j
+          wf.parts = split ? partials.p : nullptr, wf.nblk = (int)gb_w2, wf.gout = split ? gout.p : nullptr;
+        const bool spdl = pdl && infold && zpath && (fused || c->world == 1);
+        if (st_sm)
+          LAUNCH(c, "spmvT_csc", CUDA_CHECK(launch_k(spmvT_csc_sm<VT>, dim3(st_grid), dim3(STS_THREADS), st_smem, st, spdl, 1, A.cptr.p,
+                                                     A.ridx.p, A.cval.p, (const double*)(infold ? ybuf_n.p : wcur.p), tbuf.p, h,
+                                                     counter.p + 1, fused_t ? pcw : pc1, wf, hp, (int)n, (const int*)ws.perm.p,
+                                                     st_cpb)));
+        else
+          LAUNCH(c, "spmvT_csc", CUDA_CHECK(launch_k(spmvT_csc<VT>, dim3(h), dim3(256), 0, st, spdl, 1, A.cptr.p, A.ridx.p, A.cval.p,
+                                                     (const double*)(infold ? ybuf_n.p : wcur.p), tbuf.p, h, counter.p + 1,
+                                                     fused_t ? pcw : pc1, wf, hp)));
       }
       if (!fused_t) allreduce_sum_f64(c, tbuf.p, (size_t)h);
       if (use_vstep) {
         WORK(c, 8.0 * h * (2.0 * (j + 1) + 8));
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(VS_CLUSTER);
-        cfg.blockDim = dim3(VS_THREADS);
-        cfg.dynamicSmemBytes = sizeof(double) * (VS_WARPS + 8) * MAXB;
-        cfg.stream = st;
         ZArgs za;
         if (zpath)
           za.Z = Z.p, za.sumW = sumW.p, za.gprev = gout.p, za.cvec = cvec.p, za.ncc = (j < m_b - 1) ? j + 1 : m_b,
           za.prev = (j < m_b - 1) ? 1 : 0;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = VS_CLUSTER;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        LAUNCH(c, "v_step", CUDA_CHECK(cudaLaunchKernelEx(&cfg, m_b <= 96 ? v_step<3> : v_step<4>, (const double*)tbuf.p, mu, rs,
-                                                           (const double*)(centered ? murs.p : nullptr), sc.p, V.p, ld, j,
-                                                           m_b, h, ybuf_h.p, fbuf.p, xs.p, B.p, za)));
+        const bool vpdl = pdl && (fused_t || c->world == 1);
+        if (vs_one)
+          LAUNCH(c, "v_step", CUDA_CHECK(launch_k(m_b <= 96 ? v_step_one<3> : v_step_one<4>, dim3(VS_CLUSTER), dim3(VS_THREADS),
+                                                  vs_one_smem, st, vpdl, VS_CLUSTER, (const double*)tbuf.p, mu, rs,
+                                                  (const double*)(centered ? murs.p : nullptr), sc.p, V.p, ld, j, m_b, h,
+                                                  ybuf_h.p, fbuf.p, xs.p, B.p, za, hp)));
+        else
+          LAUNCH(c, "v_step", CUDA_CHECK(launch_k(m_b <= 96 ? v_step<3> : v_step<4>, dim3(VS_CLUSTER), dim3(VS_THREADS),
+                                                  sizeof(double) * (VS_WARPS + 8) * MAXB, st, vpdl, VS_CLUSTER,
+                                                  (const double*)tbuf.p, mu, rs, (const double*)(centered ? murs.p : nullptr),
+                                                  sc.p, V.p, ld, j, m_b, h, ybuf_h.p, fbuf.p, xs.p, B.p, za, hp)));
       } else {
         WORK(c, 8.0 * h * (j + 1 + 4));
         LAUNCH(c, "v_prep_dots", (v_prep_dots<<<gb_h, RT_THREADS, 0, st>>>(tbuf.p, mu, rs, sc.p, V.p, ld, j, j + 1, h, ybuf_h.p,
@@ -1763,16 +2652,20 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
       CUDA_CHECK(cudaStreamWaitEvent(st, c->join_ev, 0));
     else
       enqueue_svd(first, k, st);
-    LAUNCH(c, "conv_check", (conv_check<<<1, 128, 0, st>>>(Su.p, svd_s.p, sc.p, m_b, nu, k, first ? 0 : 1, tol, R.p,
-                                                         info.p, arrow ? 1 : 0)));
-    CUDA_CHECK(cudaMemcpyAsync(h_info, info.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+    LAUNCH(c, "conv_check", (conv_check<<<CC_BLOCKS, 256, 0, st>>>(Su.p, svd_s.p, sc.p, m_b, nu, k, first ? 0 : 1, tol, R.p,
+                                                                 info.p, arrow ? 1 : 0, 0, Sv.p, St.p,
+                                                                 zpath ? cvec.p : nullptr, sumW.p, ws.crot.p)));
+    CUDA_CHECK(cudaMemcpyAsync(h_info, info.p, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
+    hp = nullptr;
   };
   // fallback when svd_arrow rejected its own result: generic Jacobi SVD of the same B
   auto svd_fallback = [&](bool first, int k) {
+    CUDA_CHECK(cudaMemsetAsync(info.p + 4, 0, sizeof(int), st));  // clear the halt flag: jacobi_svd honours it
     LAUNCH(c, "jacobi_svd", (jacobi<<<1, JTHREADS, svd_smem, st>>>(B.p, m_b, Su.p, svd_s.p, Sv.p, info.p)));
-    LAUNCH(c, "conv_check", (conv_check<<<1, 128, 0, st>>>(Su.p, svd_s.p, sc.p, m_b, nu, k, first ? 0 : 1, tol, R.p,
-                                                         info.p, 0)));
-    CUDA_CHECK(cudaMemcpyAsync(h_info, info.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+    LAUNCH(c, "conv_check", (conv_check<<<CC_BLOCKS, 256, 0, st>>>(Su.p, svd_s.p, sc.p, m_b, nu, k, first ? 0 : 1, tol, R.p,
+                                                                 info.p, 0, 1, Sv.p, St.p, zpath ? cvec.p : nullptr,
+                                                                 sumW.p, ws.crot.p)));
+    CUDA_CHECK(cudaMemcpyAsync(h_info, info.p, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
   };
   auto run_iteration = [&](bool first, int k) {
@@ -1810,13 +2703,36 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   };
 
   IrlbResult res;
-  const bool trace = getenv("ADOBO_B200_IRLB_TRACE") != nullptr;  // diagnostic: one line per outer iteration
-  int it = 0, k = nu, nmult = 0;
+  // Outer loop.  k only grows and stays at m_b - 3 once it gets there (conv_check), which is where almost all
+  // restarts happen: from then on the host does not wait for the 32-byte read-back before enqueueing the next
+  // iteration.  It runs up to RUN_DEPTH iterations ahead; when an iteration converges (or its SVD is rejected)
+  // conv_check raises the halt flag on the device and every kernel of the iterations already enqueued behind it
+  // returns at once, leaving V, W, B and the SVD of the converged iteration untouched.
+  std::vector<int> ks;  // k of every enqueued iteration
+  int it = 0, k = nu, enq = 0;
   bool converged = false;
+  if (runahead)
+    for (auto& e : ws.ev)
+      if (!e) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   while (it < maxit) {
-    run_iteration(it == 0, k);
-    nmult += 2 * (m_b - (it == 0 ? 0 : k));  // 1 + sum over j of (1 + [j < m_b-1]) mat-vecs
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    while (enq < maxit && (enq == it || (runahead && enq - it < RUN_DEPTH && it > 0 && k == m_b - 3))) {
+      run_iteration(enq == 0, k);
+      if (runahead) CUDA_CHECK(cudaEventRecord(ws.ev[enq % RUN_DEPTH], st));
+      ks.push_back(k);
+      ++enq;
+    }
+    if (runahead)
+      CUDA_CHECK(cudaEventSynchronize(ws.ev[it % RUN_DEPTH]));
+    else
+      CUDA_CHECK(cudaStreamSynchronize(st));
+    if (runahead && h_info[4] != 0) {
+      // something stopped: drain the (no-op) iterations behind it and read the final state
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      it = (h_info[4] == 1) ? h_info[5] - 1 : h_info[5];
+      k = ks[it];
+      enq = it + 1;
+      ks.resize(enq);
+    }
     if (h_info[0] < 0 || (force_fallback && it > 0)) {  // structured SVD failed its self-check (kept for safety)
       svd_fallback(it == 0, k);
       ++res.svd_fallbacks;
@@ -1829,13 +2745,15 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     k = h_info[1];
     ++it;
   }
+  int nmult = 0;  // 1 + sum over j of (1 + [j < m_b-1]) mat-vecs per outer iteration
+  for (int i = 0; i < (int)ks.size() && i <= it; ++i) nmult += 2 * (m_b - (i == 0 ? 0 : ks[i]));
   // the reference applies the restart update before `it` reaches maxit (irlb.py:238-247)
-  if (!converged && it > 0) restart_update(k);
+  if (!converged && it > 0) restart_update(k);  // St for this k was laid out by the last conv_check
   // ---- U = W Su[:, :nu] (x diag(s) when var_weigh), V = V Sv[:, :nu]  (irlb.py:249-250, dr.py:164-168) ----
   outU.ensure((size_t)std::max<i64>(n, 1) * nu);
   outV.ensure((size_t)h * nu);
   outS.ensure((size_t)nu);
-  rotate2(nu, outV.p, outU.p, nu, var_weigh ? svd_s.p : nullptr);
+  rotate2(nu, outV.p, outU.p, nu, var_weigh ? svd_s.p : nullptr, false);
   CUDA_CHECK(cudaMemcpyAsync(outS.p, svd_s.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));
   CUDA_CHECK(cudaStreamSynchronize(st));
 #ifdef ADOBO_B200_VSTAMPS
@@ -1845,6 +2763,67 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     fprintf(stderr, "v_step stamps (cycles):");
     for (int q = 1; q <= 10; ++q) fprintf(stderr, " %d:%lld", q, hs[q] - hs[q - 1]);
     fprintf(stderr, " total %lld\n", hs[10] - hs[0]);
+  }
+#endif
+#ifdef ADOBO_B200_TIMELINE
+  if (getenv("ADOBO_B200_TIMELINE")) {
+    static unsigned long long tl[6][1024];
+    cudaMemcpyFromSymbol(tl, tl_buf, sizeof(tl));
+    struct Ev { unsigned long long t0, t1, t2, c0, c1, c2; char name[24]; };
+    std::vector<Ev> evs;
+    auto add = [&](int slot, const char* nm, int j) {
+      if (!tl[0][slot]) return;
+      Ev e{tl[0][slot], tl[1][slot], tl[2][slot], tl[3][slot], tl[4][slot], tl[5][slot], {}};
+      snprintf(e.name, sizeof(e.name), "%s[%d]", nm, j);
+      evs.push_back(e);
+    };
+    for (int j = 0; j < 128; ++j) add(j, "w_step", j), add(128 + j, "spmvT", j), add(256 + j, "v_step", j);
+    add(384, "rotate", 0), add(385, "set_restart", 0), add(386, "conv_check", 0), add(387, "w_finish", 0);
+    {
+      static unsigned long long tc[8][256];
+      cudaMemcpyFromSymbol(tc, tl_cta, sizeof(tc));
+      unsigned long long b0 = ~0ull;
+      for (unsigned q = 0; q < gb_n; ++q) b0 = std::min(b0, tc[1][q]);
+      const char* nm[8] = {"entry", "sync", "rows done", "deposit+sync", "partials", "fence+sync", "atomic", "exit"};
+      fprintf(stderr, "last w_step, per-CTA stamps relative to the earliest sync return (us): min / median / max\n");
+      for (int i = 0; i < 8; ++i) {
+        std::vector<double> v;
+        for (unsigned q = 0; q < gb_n && q < 256; ++q) v.push_back(((double)tc[i][q] - (double)b0) * 1e-3);
+        std::sort(v.begin(), v.end());
+        fprintf(stderr, "  %-14s %8.2f %8.2f %8.2f   (p90 %8.2f)\n", nm[i], v.front(), v[v.size() / 2], v.back(), v[v.size() * 9 / 10]);
+      }
+    }
+    {
+      static unsigned long long tk[2][8][256];
+      cudaMemcpyFromSymbol(tk, tl_ctak, sizeof(tk));
+      const char* nm0[8] = {"sync", "u issued", "u synced", "W stored", "columns", "entry", "prologue issued", ""};
+      const char* nm1[8] = {"sync", "phase A", "Z landed", "c pushed", "cluster sync 1", "phase B pushed", "cluster sync 2", "exit"};
+      for (int kq = 0; kq < 2; ++kq) {
+        const unsigned nb = kq == 0 ? st_grid : (unsigned)VS_CLUSTER;
+        unsigned long long b0 = ~0ull;
+        for (unsigned q = 0; q < nb; ++q) b0 = std::min(b0, tk[kq][0][q]);
+        fprintf(stderr, "last %s, per-CTA stamps relative to the earliest sync return (us): min / median / max\n",
+                kq == 0 ? "spmvT_csc_sm" : "v_step_one");
+        for (int i = 0; i < 8; ++i) {
+          if (!tk[kq][i][0]) continue;
+          std::vector<double> v;
+          for (unsigned q = 0; q < nb && q < 256; ++q) v.push_back(((double)tk[kq][i][q] - (double)b0) * 1e-3);
+          std::sort(v.begin(), v.end());
+          fprintf(stderr, "  %-16s %8.2f %8.2f %8.2f\n", kq == 0 ? nm0[i] : nm1[i], v.front(), v[v.size() / 2], v.back());
+        }
+      }
+    }
+    std::sort(evs.begin(), evs.end(), [](const Ev& a, const Ev& b) { return a.t0 < b.t0; });
+    const size_t from = evs.size() > 24 ? evs.size() - 24 : 0;
+    const unsigned long long base = evs.empty() ? 0 : evs[from].t0, cbase = evs.empty() ? 0 : evs[from].c0;
+    fprintf(stderr, "timeline of the last kernels (us from the first; globaltimer | clock64 / 1.965 GHz)\n");
+    for (size_t q = from; q < evs.size(); ++q) {
+      const Ev& e = evs[q];
+      fprintf(stderr, "%-16s entry %8.2f sync %8.2f exit %8.2f | entry %8.2f sync %8.2f exit %8.2f\n", e.name,
+              (e.t0 - base) * 1e-3, e.t1 ? (e.t1 - base) * 1e-3 : -1.0, (e.t2 - base) * 1e-3,
+              ((long long)(e.c0 - cbase)) / 1965.0, e.c1 ? ((long long)(e.c1 - cbase)) / 1965.0 : -1.0,
+              ((long long)(e.c2 - cbase)) / 1965.0);
+    }
   }
 #endif
   res.steps = it;

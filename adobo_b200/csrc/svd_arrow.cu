@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(SA_THREADS, 1) svd_arrow(const double* __restr
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
+  if (info[4] != 0) return;  // halt flag of the Lanczos driver (conv_check): uniform over the cluster
   if (crank == 0 && tid == 0) info[3] = 1;
   cluster.barrier_arrive();  // matched by the wait before the first write into a neighbour's shared memory
 

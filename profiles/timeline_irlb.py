@@ -1,0 +1,18 @@
+"""Timeline of the last outer iteration of IRLB inside the replayed CUDA graph (diagnostic build:
+ADOBO_B200_CFLAGS=-DADOBO_B200_TIMELINE python -m adobo_b200.build --force; run with ADOBO_B200_TIMELINE=1)."""
+import os
+import sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from adobo_b200.engine import Engine
+from adobo_b200.synth import synth_counts
+
+cells = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+eng = Engine(0)
+counts = synth_counts(cells, 3000, 0.10, 77)
+eng.upload_counts(counts)
+np.random.seed(42)
+v0 = np.random.randn(1000)
+for rep in range(2):
+    r = eng.embed_path(v0, ngenes=1000, ncomp=75, k=10)
+print(r)

@@ -223,7 +223,8 @@ def test_knn_blobs_30k_tensor_core_path(eng):
 
 @pytest.mark.parametrize('env', ['ADOBO_B200_SVD_JACOBI', 'ADOBO_B200_SVD_FORCE_FALLBACK', 'ADOBO_B200_NO_GRAPH',
                                  'ADOBO_B200_NO_FORK', 'ADOBO_B200_ROTATE_STREAMED', 'ADOBO_B200_SVD_CLUSTER', 'ADOBO_B200_NO_VSTEP',
-                                 'ADOBO_B200_NO_WFOLD', 'ADOBO_B200_NO_ZPATH'])
+                                 'ADOBO_B200_NO_WFOLD', 'ADOBO_B200_NO_ZPATH', 'ADOBO_B200_NO_PDL', 'ADOBO_B200_NO_RUNAHEAD',
+                                 'ADOBO_B200_NO_VONE', 'ADOBO_B200_NO_STSM', 'ADOBO_B200_WSTEP_V1', 'ADOBO_B200_NO_SPLIT'])
 def test_irlb_alternative_svd_paths(eng, env, monkeypatch):
     """The generic Jacobi SVD of B (first iteration / fallback of the structured solver) and the
     non-graph launch path must give the same PCA as the default path."""
@@ -237,3 +238,20 @@ def test_irlb_alternative_svd_paths(eng, env, monkeypatch):
     P.assert_pca_close(alt['comp'], alt['contr'], case['comp'], case['contr'], ex_comp, ex_contr)
     np.testing.assert_allclose(alt['s'], base['s'], rtol=1e-7)  # converged to tol^2; the paths round differently
     assert np.max(P.component_err(alt['comp'], base['comp'])[:case['ncomp'] - 8]) < 1e-6
+
+
+@pytest.mark.parametrize('maxit', [1, 2, 7, 1000])
+def test_irlb_runahead_is_the_synchronous_loop(eng, maxit, monkeypatch):
+    """The host enqueues outer iterations ahead of the convergence read-back (device-side halt flag) and the
+    step kernels are launched programmatically; neither changes arithmetic: same restarts, mat-vecs and bits as
+    the loop that waits for every read-back -- converged or cut off by maxit (irlb.py:155, 238-247)."""
+    case = P.load_case('medium')
+    eng.upload_normalized(case['norm_csr'])
+    fast = eng.irlb(case['hvg_ordered'], ncomp=case['ncomp'], seed=42, maxit=maxit)
+    monkeypatch.setenv('ADOBO_B200_NO_RUNAHEAD', '1')
+    monkeypatch.setenv('ADOBO_B200_NO_PDL', '1')
+    eng.upload_normalized(case['norm_csr'])
+    slow = eng.irlb(case['hvg_ordered'], ncomp=case['ncomp'], seed=42, maxit=maxit)
+    assert (fast['steps'], fast['nmult']) == (slow['steps'], slow['nmult'])
+    assert np.array_equal(fast['s'], slow['s'])
+    assert np.array_equal(fast['comp'], slow['comp']) and np.array_equal(fast['contr'], slow['contr'])
