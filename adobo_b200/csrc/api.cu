@@ -470,11 +470,21 @@ int adobo_event_elapsed_ms(adobo_ctx* c, int a, int b, float* ms) {
   API_END
 }
 
+// Calibration of the profiler itself: an empty kernel between the same pair of events.  Its time is what every
+// profiled launch carries on top of its own duration (event record + launch latency); reported as "_event_overhead".
+__global__ void prof_noop() {}
+
 int adobo_profile(adobo_ctx* c, int on) {
   API_BEGIN
   prof_collect(c);
   if (on) c->prof.clear();
   c->profiling = on != 0;
+  if (on) {
+    const i64 launches = c->launches;
+    for (int q = 0; q < 64; ++q) LAUNCH(c, "_event_overhead", (prof_noop<<<1, 32, 0, c->stream>>>()));
+    c->launches = launches;  // not part of the path
+    prof_collect(c);
+  }
   API_END
 }
 

@@ -118,6 +118,22 @@ __device__ __forceinline__ void deposit_lane8(double (&acc)[NQ]) {
   if (NQ * 8 < MAXB)
     for (int c = NQ * 8 + lane; c < MAXB; c += 32) sh[warp][c] = 0.0;
 }
+constexpr int SP_PARTS = 8, SP_PER = 19;  // 8 x 19 >= 148 CTAs: a part's loads are issued as one batch
+// the part sum of one column: CTAs part, part + SP_PARTS, ... in ascending order
+__device__ __forceinline__ double sum_partials_part(const double* __restrict__ src, int part, int nparts, int nblk) {
+  double p = 0;
+  for (int base = part; base < nblk; base += nparts * SP_PER) {  // one trip for <= nparts x 19 CTAs
+    double v[SP_PER];
+#pragma unroll
+    for (int i = 0; i < SP_PER; ++i) {
+      const int b = base + nparts * i;
+      v[i] = b < nblk ? __ldcg(src + (size_t)b * MAXB) : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < SP_PER; ++i) p += v[i];
+  }
+  return p;
+}
 // Both levels are laid out for coalescing: thread = (column, part); a part sums every nparts-th warp (CTA) partial
 // of its column with independent loads, then one thread per column adds the parts in a fixed order.  (Lanes striding
 // the CTA partials of ONE column -- 1 KB apart -- cost the last CTA 15 k separate sector requests: 8.7 us measured.)
@@ -149,11 +165,7 @@ __device__ __forceinline__ void reduce_vec_finish(int nd, double* __restrict__ p
   __syncthreads();
   TL_CTA(6);
   if (is_last) {
-    double s = 0;
-    if (col < nd) {
-#pragma unroll 4
-      for (unsigned b = part; b < gridDim.x; b += nparts) s += __ldcg(partials + (size_t)b * MAXB + col);
-    }
+    const double s = col < nd ? sum_partials_part(partials + col, part, nparts, (int)gridDim.x) : 0.0;  // batched loads
     ps[part][col] = s;
     __syncthreads();
     if (tid < nd) {
@@ -188,21 +200,6 @@ __device__ __forceinline__ void reduce_vec_partials(int nd, double* __restrict__
     for (int g = 0; g < nparts; ++g) s += ps[g][tid];
     partials[(size_t)blockIdx.x * MAXB + tid] = s;
   }
-}
-constexpr int SP_PARTS = 8, SP_PER = 19;  // 8 x 19 >= 148 CTAs: a part's loads are issued as one batch
-// the part sum of one column: CTAs part, part + SP_PARTS, ... in ascending order
-__device__ __forceinline__ double sum_partials_part(const double* __restrict__ src, int part, int nparts, int nblk) {
-  double v[SP_PER];
-#pragma unroll
-  for (int i = 0; i < SP_PER; ++i) {
-    const int b = part + nparts * i;
-    v[i] = b < nblk ? __ldcg(src + (size_t)b * MAXB) : 0.0;
-  }
-  double p = 0;
-#pragma unroll
-  for (int i = 0; i < SP_PER; ++i) p += v[i];
-  for (int b = part + nparts * SP_PER; b < nblk; b += nparts) p += __ldcg(src + (size_t)b * MAXB);  // grids beyond 8 x 19
-  return p;
 }
 // one column summed by a full warp: lanes stride the CTAs (<= 5 batched loads each for <= 160 CTAs), butterfly
 __device__ __forceinline__ double sum_partials_warp(const double* __restrict__ src, int nblk) {

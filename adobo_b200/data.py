@@ -47,6 +47,14 @@ class dataset:
         df = df.astype(pd.SparseDtype(counts.dtype, 0))
         return cls(df, **kw)
 
+    @classmethod
+    def from_matrix_market(cls, filename, **kw):
+        """10x-style archive (see IO.load_matrix_market) -> dataset, CSR all the way."""
+        from .IO import read_matrix_market_csr
+        counts, genes, cells = read_matrix_market_csr(filename)
+        kw.setdefault('input_file', filename)
+        return cls.from_csr(counts, genes=genes, cells=cells, **kw)
+
     @property
     def norm_data(self):
         return self._norm_data
