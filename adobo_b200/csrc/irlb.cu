@@ -2035,8 +2035,10 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 constexpr int RR_CHUNKS = 4;
 
-template <int R>
-__global__ void __launch_bounds__(512) rotate_rows(const RotJob ja, const RotJob jb, const RotJob jc, int nba, int nbb,
+// RS = row splits: the tile's rows are divided between RS groups of (kcp / 8) warps, which doubles the resident warps
+// (ncu on rotate_rows<5>: 12 warps per SM keep the fp64 pipe 42 % busy; the rest is dependency and LDS waits).
+template <int R, int RS>
+__global__ void __launch_bounds__(RS == 1 ? 512 : 768) rotate_rows(const RotJob ja, const RotJob jb, const RotJob jc, int nba, int nbb,
                                                    int ld, int m, int kc, const int* __restrict__ halt) {
   if (halt && *halt) return;
   TL_ENTRY(384);
@@ -2051,12 +2053,15 @@ __global__ void __launch_bounds__(512) rotate_rows(const RotJob ja, const RotJob
   const i64 nblk = which == 0 ? nba : (which == 1 ? nbb : gridDim.x - nba - nbb);
   const i64 per = (job.rows + nblk - 1) / nblk;
   const i64 lo = bid * per, hi = min(job.rows, lo + per);
-  constexpr int TR = 32 * R, RP = TR + 1;
+  constexpr int TR = 32 * R * RS, RP = TR + 1;
   extern __shared__ __align__(16) double sm[];
   const int kcp = (kc + 7) & ~7;
   double* Ssm = sm;                   // [m][kcp]
   double* Qs = sm + (size_t)m * kcp;  // [m][RP], transposed tile
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nthr = blockDim.x;
+  const int lane = threadIdx.x & 31, nthr = blockDim.x;
+  const int wcols = (int)(blockDim.x >> 5) / RS;                      // warps along the columns
+  const int warp = (int)(threadIdx.x >> 5) % wcols;                   // column group: columns 8 warp .. 8 warp + 7
+  const int rbase = ((int)(threadIdx.x >> 5) / wcols) * 32 * R;       // first row of this warp's share of the tile
   bool s_loaded = false;
   for (i64 row0 = lo; row0 < hi; row0 += TR) {
     const int nrow = (int)min((i64)TR, hi - row0);
@@ -2079,7 +2084,7 @@ __global__ void __launch_bounds__(512) rotate_rows(const RotJob ja, const RotJob
     for (int q = 0; q < R; ++q)
 #pragma unroll
       for (int c = 0; c < 8; ++c) acc[q][c] = 0.0;
-    const double* qp = Qs + lane;
+    const double* qp = Qs + rbase + lane;
     const double* sp = Ssm + warp * 8;
 #pragma unroll
     for (int ch = 0; ch < RR_CHUNKS; ++ch) {
@@ -2114,7 +2119,7 @@ __global__ void __launch_bounds__(512) rotate_rows(const RotJob ja, const RotJob
     const bool vec = out == nullptr && warp * 8 + 8 <= kc;  // in place, full column group: 128-bit stores
 #pragma unroll
     for (int q = 0; q < R; ++q) {
-      const int r = lane + 32 * q;
+      const int r = rbase + lane + 32 * q;
       if (r < nrow) {
         if (vec) {
           double2* dst = reinterpret_cast<double2*>(Q + (size_t)(row0 + r) * ld + warp * 8);
@@ -2136,13 +2141,14 @@ __global__ void __launch_bounds__(512) rotate_rows(const RotJob ja, const RotJob
   TL_EXIT(384);
 }
 using rotate_rows_fn = void (*)(const RotJob, const RotJob, const RotJob, int, int, int, int, int, const int*);
-static rotate_rows_fn rotate_rows_for(int R) {
+static rotate_rows_fn rotate_rows_for(int R, int RS = 1) {
+  if (RS == 2) return R <= 2 ? rotate_rows<2, 2> : rotate_rows<3, 2>;
   switch (R) {
-    case 1: return rotate_rows<1>;
-    case 2: return rotate_rows<2>;
-    case 3: return rotate_rows<3>;
-    case 4: return rotate_rows<4>;
-    default: return rotate_rows<5>;
+    case 1: return rotate_rows<1, 1>;
+    case 2: return rotate_rows<2, 1>;
+    case 3: return rotate_rows<3, 1>;
+    case 4: return rotate_rows<4, 1>;
+    default: return rotate_rows<5, 1>;
   }
 }
 
@@ -2275,7 +2281,8 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     // test hooks read from the environment change what a captured iteration contains
     const int hooks = (getenv("ADOBO_B200_SVD_JACOBI") ? 1 : 0) | (getenv("ADOBO_B200_NO_FORK") ? 2 : 0) |
                       (getenv("ADOBO_B200_ROTATE_STREAMED") ? 4 : 0) | (getenv("ADOBO_B200_NO_VSTEP") ? 8 : 0) | (getenv("ADOBO_B200_NO_WFOLD") ? 1024 : 0) | (getenv("ADOBO_B200_NO_ZPATH") ? 2048 : 0) | (getenv("ADOBO_B200_NO_PDL") ? 4096 : 0) |
-                      (getenv("ADOBO_B200_NO_RUNAHEAD") ? 8192 : 0) | (getenv("ADOBO_B200_NO_VONE") ? 16384 : 0) | (getenv("ADOBO_B200_NO_STSM") ? (1 << 17) : 0) | (getenv("ADOBO_B200_WSTEP_V1") ? (1 << 18) : 0) | (getenv("ADOBO_B200_NO_SPLIT") ? (1 << 19) : 0) |
+                      (getenv("ADOBO_B200_NO_RUNAHEAD") ? 8192 : 0) | (getenv("ADOBO_B200_NO_VONE") ? 16384 : 0) | (getenv("ADOBO_B200_WSTEP_V1") ? (1 << 18) : 0) | (getenv("ADOBO_B200_ROTSPLIT") ? (1 << 20) : 0) |
+                      (getenv("ADOBO_B200_STSM") ? (1 << 21) : 0) | (getenv("ADOBO_B200_NO_SPLIT") ? (1 << 19) : 0) |
                       (getenv("ADOBO_B200_IRLB_TRACE") ? 32768 : 0) | (getenv("ADOBO_B200_SVD_FORCE_FALLBACK") ? 65536 : 0) |
                       (svd_arrow_cluster() << 4);
     const int si[6] = {h, nu, m_b, c->world, (int)sizeof(VT), hooks};
@@ -2348,6 +2355,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   // V[:, :kc] (or outv) = V Sv[:, :kc]  and  W[:, :kc] (or outw) = W Su[:, :kc], one launch each for the
   // transposes and for the two tall-skinny GEMMs
   const bool rot_streamed = getenv("ADOBO_B200_ROTATE_STREAMED") != nullptr;  // test hook: force rotate_basis
+  const bool rot_split = getenv("ADOBO_B200_ROTSPLIT") != nullptr;  // opt-in: measured slower (36.6 against 31.4 us per restart)
   // Z formulation of the W side (w_step): needs the cluster V kernel and two spare columns in the reduced vector
   const bool zpath = h <= 8192 && m_b + 2 <= MAXB && getenv("ADOBO_B200_NO_VSTEP") == nullptr &&
                      getenv("ADOBO_B200_NO_ZPATH") == nullptr;
@@ -2406,10 +2414,15 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     if (!rot_streamed && r_fit >= 1 && per <= 2 * 32 * r_fit) {
       const i64 ntile = (per + 32 * r_fit - 1) / (32 * r_fit);
       const int Rr = (int)std::min<i64>(r_fit, ((per + ntile - 1) / ntile + 31) / 32);
-      const size_t smem = s_bytes + sizeof(double) * (size_t)m_b * (32 * Rr + 1);
-      rotate_rows_fn fn = rotate_rows_for(Rr);
+      // two row groups of warps (768 threads) when the column groups leave room for them and the wider tile fits
+      const int R2 = std::max(2, (Rr + 1) / 2);
+      const size_t smem2 = s_bytes + sizeof(double) * (size_t)m_b * (64 * R2 + 1);
+      const bool split_rows = rot_split && Rr >= 3 && kcp / 8 <= 12 && smem2 <= 225 * 1024;
+      const size_t smem = split_rows ? smem2 : s_bytes + sizeof(double) * (size_t)m_b * (32 * Rr + 1);
+      rotate_rows_fn fn = split_rows ? rotate_rows_for(R2, 2) : rotate_rows_for(Rr);
       CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      LAUNCH(c, "rotate_basis", (fn<<<nbv + nbz + nbw, 32 * (kcp / 8), smem, st>>>(jv, jz, jw, (int)nbv, (int)nbz, ld, m_b, kc, hp)));
+      LAUNCH(c, "rotate_basis", (fn<<<nbv + nbz + nbw, 32 * (kcp / 8) * (split_rows ? 2 : 1), smem, st>>>(jv, jz, jw, (int)nbv, (int)nbz, ld,
+                                                                                                   m_b, kc, hp)));
     } else {
       LAUNCH(c, "rotate_basis", (rotate_basis<<<nbv + nbz + nbw, 32 * (kcp / 8), rot_smem, st>>>(jv, jz, jw, (int)nbv, (int)nbz,
                                                                                            ld, m_b, kc, rot_nbuf, hp)));
@@ -2537,7 +2550,8 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   const size_t st_smem = sizeof(double) * (size_t)std::max<i64>(n, 2);
   const int st_cpb = (h + c->sm_count - 1) / c->sm_count;  // columns per CTA
   const bool st_sm = n >= 2 && n < (1 << 30) && st_smem <= 200 * 1024 && st_cpb <= STS_MAXC && A.nnz < (i64(1) << 31) &&
-                     getenv("ADOBO_B200_NO_STSM") == nullptr;
+                     getenv("ADOBO_B200_STSM") != nullptr;  // opt-in: measured equal to spmvT_csc in the replayed graph (12.9 us
+                                                            // against 11-13 us) and slower from a cold cache (35 against 20 us)
   const unsigned st_grid = (unsigned)((h + st_cpb - 1) / st_cpb);
   if (st_sm) {
     // deal the columns to the CTAs by length: sorted descending, snake order, slot k of CTA b at perm[b + grid k]
@@ -2577,6 +2591,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     prefer((const void*)w_finish), prefer((const void*)set_restart), prefer((const void*)conv_check);
     prefer((const void*)rotate_basis);
     for (int R = 1; R <= 5; ++R) prefer((const void*)rotate_rows_for(R));
+    prefer((const void*)rotate_rows_for(2, 2)), prefer((const void*)rotate_rows_for(3, 2));
     prefer((const void*)jacobi);
   }
   auto enqueue_iteration = [&](bool first, int k) {

@@ -283,6 +283,7 @@ def main():
                         'between the same events); in-graph durations are in profiles/r01_timeline_irlb.md and the HBM-bound '
                         'regime of the same kernels in profiles/r01_scale_rooflines.md' % (args.cells, event_overhead_us))
     roof['event_overhead_us'] = event_overhead_us
+    roof['empty_kernel_between_events_us'] = (ov['ms'] * 1e3 / max(ov['launches'], 1)) if ov else None
     rooflines = [roofline_of(kd) for kd in kernels if kd['kernel'] in
                  ('csr_libsize_scale_log', 'csr_gene_moments', 'w_step', 'spmv_dots', 'spmvT_csc', 'update_norm', 'v_step',
                   'rotate_basis', 'knn_scores_tc')]
