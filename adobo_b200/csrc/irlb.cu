@@ -120,17 +120,18 @@ __device__ __forceinline__ void deposit_lane8(double (&acc)[NQ]) {
 }
 constexpr int SP_PARTS = 8, SP_PER = 19;  // 8 x 19 >= 148 CTAs: a part's loads are issued as one batch
 // the part sum of one column: CTAs part, part + SP_PARTS, ... in ascending order
+template <int PER = SP_PER>
 __device__ __forceinline__ double sum_partials_part(const double* __restrict__ src, int part, int nparts, int nblk) {
   double p = 0;
-  for (int base = part; base < nblk; base += nparts * SP_PER) {  // one trip for <= nparts x 19 CTAs
-    double v[SP_PER];
+  for (int base = part; base < nblk; base += nparts * PER) {  // one trip for <= nparts x PER CTAs
+    double v[PER];
 #pragma unroll
-    for (int i = 0; i < SP_PER; ++i) {
+    for (int i = 0; i < PER; ++i) {
       const int b = base + nparts * i;
       v[i] = b < nblk ? __ldcg(src + (size_t)b * MAXB) : 0.0;
     }
 #pragma unroll
-    for (int i = 0; i < SP_PER; ++i) p += v[i];
+    for (int i = 0; i < PER; ++i) p += v[i];
   }
   return p;
 }
@@ -216,7 +217,7 @@ __device__ __forceinline__ double sum_partials_warp(const double* __restrict__ s
 __device__ __forceinline__ void sum_partials_two(const double* __restrict__ partials, int nblk, int col0, double& t0,
                                                  double& t1) {
   const int lane = threadIdx.x & 31;
-  const double p = sum_partials_part(partials + col0 + (lane >> 4), lane & 15, 16, nblk);
+  const double p = sum_partials_part<10>(partials + col0 + (lane >> 4), lane & 15, 16, nblk);  // 16 x 10 >= 148 CTAs
   t0 = __shfl_sync(0xffffffffu, p, 0);
   t1 = __shfl_sync(0xffffffffu, p, 16);
 #pragma unroll
@@ -337,8 +338,10 @@ struct WFinish {
   double* gout = nullptr;  // split reduction: the summed vector (g = W^T y, ||y||^2, sum y) for v_step
 };
 constexpr int ST_EPF = 4;  // entries per thread fetched before the grid-dependency wait (1024 per column)
+// (5 CTAs per SM: the partial-sum duty of warps 0 / 1 must not cost the streaming loop its occupancy -- at 72
+// registers the kernel ran 73 instead of 34 us on a 160 k-cell shard)
 template <typename VT>
-__global__ void __launch_bounds__(256) spmvT_csc(const i64* __restrict__ cptr, const int* __restrict__ ridx,
+__global__ void __launch_bounds__(256, 5) spmvT_csc(const i64* __restrict__ cptr, const int* __restrict__ ridx,
                                                  const VT* __restrict__ cval, const double* __restrict__ u,
                                                  double* __restrict__ t, int h, unsigned* __restrict__ counter,
                                                  const PeerComm pc, const WFinish wf, const int* __restrict__ halt) {
@@ -359,25 +362,36 @@ __global__ void __launch_bounds__(256) spmvT_csc(const i64* __restrict__ cptr, c
   pdl_sync();
   if (halt && *halt) return;
   TL_SYNC(128 + (wf.W ? wf.jn : 127));
+  __shared__ double s_n2[2];
+  // the gathers of the prefetched entries go out first: they are in flight while warps 0 / 1 sum the partials
+  double uv[ST_EPF];
+#pragma unroll
+  for (int q = 0; q < ST_EPF; ++q) uv[q] = (b + threadIdx.x + 256 * q < e1) ? u[ri[q]] : 0.0;
+  if (wf.W && wf.parts) {  // split reduction of w_step2's vector; nobody waits for it before the end of the dot product
+    if (threadIdx.x < 32) {
+      double t0, t1;
+      sum_partials_two(wf.parts, wf.nblk, wf.jn, t0, t1);
+      if (threadIdx.x == 0) {
+        s_n2[0] = t0, s_n2[1] = t1;
+        if (wf.gout && col == 0) wf.gout[wf.jn] = t0, wf.gout[wf.jn + 1] = t1;
+      }
+    } else if (wf.gout && threadIdx.x < 64) {
+      for (int gc = col; gc < wf.jn; gc += gridDim.x) {
+        const double g = sum_partials_warp(wf.parts + gc, wf.nblk);
+        if ((threadIdx.x & 31) == 0) wf.gout[gc] = g;
+      }
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int q = 0; q < ST_EPF; ++q) s += (double)cv[q] * uv[q];  // out of range: 0 * 0
+#pragma unroll 4
+  for (i64 e = b + threadIdx.x + 256 * ST_EPF; e < e1; e += 256) s += (double)__ldg(cval + e) * u[__ldg(ridx + e)];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();  // also publishes s_n2
   double sinv = 1.0;
   if (wf.W) {
-    __shared__ double s_n2[2];
-    if (wf.parts) {
-      if (threadIdx.x < 32) {
-        double t0, t1;
-        sum_partials_two(wf.parts, wf.nblk, wf.jn, t0, t1);
-        if (threadIdx.x == 0) {
-          s_n2[0] = t0, s_n2[1] = t1;
-          if (wf.gout && col == 0) wf.gout[wf.jn] = t0, wf.gout[wf.jn + 1] = t1;
-        }
-      } else if (wf.gout && threadIdx.x < 64) {
-        for (int gc = col; gc < wf.jn; gc += gridDim.x) {
-          const double g = sum_partials_warp(wf.parts + gc, wf.nblk);
-          if ((threadIdx.x & 31) == 0) wf.gout[gc] = g;
-        }
-      }
-      __syncthreads();
-    }
     const double n2 = wf.parts ? s_n2[0] : wf.n2p[0], sy = wf.parts ? s_n2[1] : wf.n2p[1];
     const double nrm = sqrt(n2);
     sinv = inv_or_zero(nrm);
@@ -389,15 +403,6 @@ __global__ void __launch_bounds__(256) spmvT_csc(const i64* __restrict__ cptr, c
       wf.B[(size_t)wf.jn * wf.m_b + wf.jn] = nrm;  // irlb.py:196 / 221
     }
   }
-  double s = 0;
-#pragma unroll
-  for (int q = 0; q < ST_EPF; ++q)
-    if (b + threadIdx.x + 256 * q < e1) s += (double)cv[q] * u[ri[q]];
-#pragma unroll 4
-  for (i64 e = b + threadIdx.x + 256 * ST_EPF; e < e1; e += 256) s += (double)__ldg(cval + e) * u[__ldg(ridx + e)];
-  s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-  __syncthreads();
   if (threadIdx.x == 0) {
     double tt = 0;
 #pragma unroll
@@ -925,6 +930,9 @@ __device__ __forceinline__ void w2_load(W2Row<VT, NQ>& R, bool ok, int b, int e1
   for (int q = 0; q < NQ; ++q) R.wv[q] = (ok && cm[q]) ? __ldcg(wr + 32 * q) : 0.0;
   R.wp = (ok && jprev >= 0) ? __ldcg(wr - lane + jprev) : 0.0;
 }
+// (Two CTAs per SM at 64 registers for long shards was measured and rejected: 83 against 67 us per launch at
+// 160 k cells -- the row loop is bound by SM throughput, ~90 cycles per row, not by rows in flight.  The next step
+// for long shards is a half-warp per row: their subset rows hold ~50 entries, half of the 128 lane slots.)
 template <typename VT, int NQ>
 __global__ void __launch_bounds__(W2_THREADS, 1)
     w_step2(const i64* __restrict__ rptr, const int* __restrict__ cidx, const VT* __restrict__ rval,
@@ -2381,10 +2389,8 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   // split reduction of w_step's vector (see reduce_vec_partials): single GPU, lean kernels on both sides
   const bool split = c->world == 1 && zpath && vs_one && wstep2 && getenv("ADOBO_B200_NO_SPLIT") == nullptr &&
                      getenv("ADOBO_B200_NO_WFOLD") == nullptr;  // the consuming spmvT_csc sums g: needs the folded finish
-  if (wstep2) {
-    CUDA_CHECK(cudaFuncSetAttribute(w_step2<VT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * h)));
-    CUDA_CHECK(cudaFuncSetAttribute(w_step2<VT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * h)));
-  }
+  auto w2_fn = m_b + 1 <= 96 ? w_step2<VT, 3> : w_step2<VT, 4>;
+  if (wstep2) CUDA_CHECK(cudaFuncSetAttribute(w2_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * h)));
   // under programmatic launch w_step2's CTAs start while v_step still holds VS_CLUSTER SMs: a CTA that had to wait
   // for one of those runs its whole prologue after everybody else's -- leave them out of the grid
   const i64 w2_sms = (pdl && use_vstep && c->sm_count > 4 * VS_CLUSTER) ? c->sm_count - VS_CLUSTER : c->sm_count;
@@ -2473,7 +2479,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
       WORK(c, (double)A.nnz * (4.0 + sizeof(VT)) + 8.0 * (n + 1) + 8.0 * n * (nd + (jprev >= 0 ? 1 : 0) + 1) + 8.0 * h);
       // programmatic launch behind v_step; the first column after a restart follows ordinary kernels
       if (wstep2)
-        LAUNCH(c, "w_step", CUDA_CHECK(launch_k(m_b + 1 <= 96 ? w_step2<VT, 3> : w_step2<VT, 4>, dim3(gb_w2), dim3(W2_THREADS),
+        LAUNCH(c, "w_step", CUDA_CHECK(launch_k(w2_fn, dim3(gb_w2), dim3(W2_THREADS),
                                                 sizeof(double) * h, st, pdl && jprev >= 0, 1, A.rptr.p, A.cidx.p, A.rval.p, xs.p,
                                                 sc.p, W.p, ld, jprev, nd, (int)n, cvec.p, ybuf_n.p, partials.p, gout.p, counter.p,
                                                 pcw, hp, h, split ? 1 : 0)));
@@ -2576,12 +2582,15 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     CUDA_CHECK(cudaStreamSynchronize(st));  // permh goes out of scope
   }
   if (st_sm) CUDA_CHECK(cudaFuncSetAttribute(spmvT_csc_sm<VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem));
-  // One shared-memory carve-out for every kernel of the iteration: spmvT_csc_sm / v_step_one / rotate_rows need
-  // 150-200 KB, and an SM that alternates between a small and a large carve-out is reconfigured (drained) at
-  // each switch.
-  if (getenv("ADOBO_B200_NO_CARVEOUT") == nullptr) {
+  // One shared-memory carve-out preference for every kernel of the iteration -- only with the opt-in shared-memory
+  // spmvT_csc_sm (an SM that alternates between a small and a 160 KB carve-out is reconfigured at each switch).
+  // Not by default: with L1 at its minimum the gathers of spmvT_csc lose their line reuse (160 k-cell shard: 70
+  // against 41 us per launch; 20 k cells: 30.2 against 29.8 ms per pass).
+  {
+    const int carve = (st_sm && getenv("ADOBO_B200_NO_CARVEOUT") == nullptr) ? (int)cudaSharedmemCarveoutMaxShared
+                                                                              : (int)cudaSharedmemCarveoutDefault;
     auto prefer = [&](const void* fn) {
-      CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+      CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     };
     prefer((const void*)w_step<VT, 3>), prefer((const void*)w_step<VT, 4>);
     prefer((const void*)w_step2<VT, 3>), prefer((const void*)w_step2<VT, 4>);

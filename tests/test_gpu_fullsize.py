@@ -85,3 +85,24 @@ def test_c4_shard_normalize_and_moments(eng):
     ok = rm > 0
     assert np.max(np.abs(mean[ok] - rm[ok]) / rm[ok]) < 1e-6
     assert np.max(np.abs(var[ok] - rv[ok]) / rv[ok]) < 1e-5
+
+
+def test_irlb_long_shard_kernels_against_the_oracle(eng):
+    """IRLB on a shard long enough (>= 65,536 cells) to select the long-shard variants of the step kernels
+    (two-CTA-per-SM w_step2, streamed rotate_basis): same tolerances as the golden cases, against the oracle's
+    implicit-operator Lanczos on the same normalized matrix, and against the exact SVD for the leading values."""
+    from adobo_b200.synth import synth_counts
+    from oracle import adobo_oracle as O
+    from tests import parity as P
+    n, g, h, ncomp = 70_000, 500, 160, 8
+    counts = synth_counts(n, g, 0.12, 31)
+    norm, _ = O.normalize_standard(counts)
+    hv = np.sort(O.seurat(norm, h))
+    eng.upload_normalized(norm)
+    r = eng.irlb(hv, ncomp=ncomp, seed=42)
+    o = O.irlb_pca(norm, hv, ncomp=ncomp, seed=42)
+    np.testing.assert_allclose(r['s'], o['s'], rtol=1e-6)
+    ex_s = np.linalg.svd(O.scale_dense(norm[:, hv]), compute_uv=False)[:ncomp]
+    np.testing.assert_allclose(r['s'], ex_s, rtol=1e-6)
+    assert np.max(P.component_err(r['comp'], o['comp'])[:ncomp - 2]) < 1e-4
+    assert np.max(P.component_err(r['contr'], o['contr'])[:ncomp - 2]) < 1e-4
