@@ -1023,6 +1023,139 @@ __global__ void __launch_bounds__(W2_THREADS, 1)
   TL_EXIT(nd);
 }
 
+// ---- w_step3: w_step2 with a HALF-WARP per row --------------------------------------------------------
+// A subset row holds 50-90 entries and 70-96 basis columns: a full warp per row leaves a third of its entry
+// slots empty and pays a 5-level reduction for every single row.  Here the two halves of a warp take two
+// consecutive rows at once -- the same instruction stream serves both (6 entry slots and NH basis columns per
+// lane, a 4-level reduction) -- which nearly halves the issue slots per row; ncu had w_step2 at 173 instructions
+// per row, 0.5 IPC per scheduler, stalled on its own dependent latencies rather than on memory.
+constexpr int W3_EPF = 6;  // entry slots per lane: 96 per row in registers, the rest in a loop
+template <typename VT, int NH>
+struct W3Row {
+  int ci[W3_EPF];
+  VT va[W3_EPF];
+  double wv[NH], wp;
+  int b, len;
+};
+template <typename VT, int NH>
+__device__ __forceinline__ void w3_load(W3Row<VT, NH>& R, bool ok, const i64* __restrict__ rptr, int row,
+                                        const int* __restrict__ cl, const VT* __restrict__ vl,
+                                        const double* __restrict__ wr, int jprev, const bool (&cm)[NH], int hl) {
+  int b = 0, e1 = 0;
+  if (ok) {
+    b = (int)__ldg(rptr + row);
+    e1 = (int)__ldg(rptr + row + 1);
+  }
+  R.b = b;
+  R.len = e1 - b;
+#pragma unroll
+  for (int q = 0; q < W3_EPF; ++q) {
+    const bool in = hl + 16 * q < R.len;
+    R.ci[q] = in ? __ldg(cl + b + 16 * q) : 0;
+    R.va[q] = in ? __ldg(vl + b + 16 * q) : VT(0);
+  }
+#pragma unroll
+  for (int q = 0; q < NH; ++q) R.wv[q] = (ok && cm[q]) ? __ldcg(wr + 16 * q) : 0.0;
+  R.wp = (ok && jprev >= 0) ? __ldcg(wr - hl + jprev) : 0.0;
+}
+// NH = basis columns per lane: 6 (<= 96 columns including the two scalars) or 8
+template <typename VT, int NH>
+__global__ void __launch_bounds__(W2_THREADS, 1)
+    w_step3(const i64* __restrict__ rptr, const int* __restrict__ cidx, const VT* __restrict__ rval,
+            const double* __restrict__ xs, const double* __restrict__ sc, const double* __restrict__ W, int ldw, int jprev,
+            int nd, int n, const double* __restrict__ cvec, double* __restrict__ ybuf, double* __restrict__ partials,
+            double* __restrict__ gout, unsigned* __restrict__ counter, const PeerComm pc, const int* __restrict__ halt,
+            int h, int split) {
+  extern __shared__ __align__(16) double xsm[];  // [h]
+  const int lane = threadIdx.x & 31, hl = lane & 15, hf = lane >> 4, warp = threadIdx.x >> 5;
+  const int nwarps = (int)((gridDim.x * blockDim.x) >> 5), wg = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  int per = (n + nwarps - 1) / nwarps;
+  per += per & 1;                       // even: a warp takes its rows two at a time
+  const int r0 = min(n, wg * per), rend = min(n, r0 + per);
+  int r = r0 + hf;                      // this half-warp's row; advances by 2
+  TL_ENTRY_REG();
+  // ---- prologue (independent of the previous kernel) ----
+  bool cm[NH];
+#pragma unroll
+  for (int q = 0; q < NH; ++q) cm[q] = hl + 16 * q < nd;
+  const int* cl = cidx + hl;
+  const VT* vl = rval + hl;
+  const double* wr = W + (size_t)r * ldw + hl;
+  W3Row<VT, NH> RA, RB;
+  w3_load<VT, NH>(RA, r < rend, rptr, r, cl, vl, wr, jprev, cm, hl);
+  pdl_sync();
+  if (halt && *halt) return;
+  TL_SYNC(nd);
+#ifdef ADOBO_B200_TIMELINE
+  if (threadIdx.x == 0 && blockIdx.x < 256) tl_cta[0][blockIdx.x] = tl_e0;
+#endif
+  TL_CTA(1);
+  for (int i = threadIdx.x; i < h; i += W2_THREADS) xsm[i] = xs[i];
+  const double mvs = sc[SC_MVS], fn = (jprev >= 0) ? sc[SC_FN] : 0.0;
+  double creg[NH], acc[NH];
+#pragma unroll
+  for (int q = 0; q < NH; ++q) {
+    creg[q] = cm[q] ? cvec[hl + 16 * q] : 0.0;
+    acc[q] = 0.0;
+  }
+  double n2 = 0, ax = 0;
+  __syncthreads();
+  // one pair of rows: issue the loads of the next pair (into NX), then reduce the current one (CU)
+  auto step = [&](W3Row<VT, NH>& CU, W3Row<VT, NH>& NX) {
+    wr += 2 * (size_t)ldw;
+    w3_load<VT, NH>(NX, r + 2 < rend, rptr, r + 2, cl, vl, wr, jprev, cm, hl);
+    double a = 0;
+#pragma unroll
+    for (int q = 0; q < W3_EPF; ++q)
+      if (hl + 16 * q < CU.len) a += (double)CU.va[q] * xsm[CU.ci[q]];
+    for (int e = 16 * W3_EPF + hl; e < CU.len; e += 16) a += (double)__ldg(vl + CU.b + e - hl) * xsm[__ldg(cl + CU.b + e - hl)];
+#pragma unroll
+    for (int q = 0; q < NH; ++q) a -= CU.wv[q] * creg[q];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);  // within the half-warp
+    const bool ok = r < rend;
+    const double w = ok ? (a - mvs) - fn * CU.wp : 0.0;
+    if (hl == 0 && ok) ybuf[r] = w;
+#pragma unroll
+    for (int q = 0; q < NH; ++q) acc[q] += CU.wv[q] * w;
+    n2 += w * w;
+    ax += w;
+    r += 2;
+  };
+  while (r - hf < rend) {  // warp-uniform: r - hf is the pair's first row
+    step(RA, RB);
+    if (r - hf >= rend) break;
+    step(RB, RA);
+  }
+  TL_CTA(2);
+  // the halves hold partial sums of the same columns (hl + 16 q): add them, then one half deposits
+#pragma unroll
+  for (int q = 0; q < NH; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 16);
+  n2 += __shfl_xor_sync(0xffffffffu, n2, 16);
+  ax += __shfl_xor_sync(0xffffffffu, ax, 16);
+  {
+    double(*sh)[MAXB] = vec_stage();
+    if (hf == 0) {
+#pragma unroll
+      for (int q = 0; q < NH; ++q) {
+        const int col = hl + 16 * q;
+        double v = acc[q];
+        if (col == nd) v = n2;        // the two scalars ride in columns nd, nd + 1 (w is uniform in a half-warp)
+        if (col == nd + 1) v = ax;
+        sh[warp][col] = v;
+      }
+    } else {
+      for (int col = 16 * NH + hl; col < MAXB; col += 16) sh[warp][col] = 0.0;
+    }
+  }
+  if (split)
+    reduce_vec_partials(nd + 2, partials);
+  else
+    reduce_vec_finish(nd + 2, partials, gout, counter, pc);
+  TL_CTA(7);
+  TL_EXIT(nd);
+}
+
 // ---- v_step: the whole V side of a Lanczos step in ONE launch on a thread-block cluster -----------
 // F = A_s^T w - s V[:, j]  (from t = A^T w),  c = V[:, :j+1]^T F,  F -= V c,  ||F||, mu.F,  V[:, j+1] = F / ||F||,
 // x = F / (||F|| sigma)   (irlb.py:185-197, 203-221).  V has only h ~ 1000 rows: v_prep_dots + update_norm + v_finish
@@ -2289,7 +2422,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     // test hooks read from the environment change what a captured iteration contains
     const int hooks = (getenv("ADOBO_B200_SVD_JACOBI") ? 1 : 0) | (getenv("ADOBO_B200_NO_FORK") ? 2 : 0) |
                       (getenv("ADOBO_B200_ROTATE_STREAMED") ? 4 : 0) | (getenv("ADOBO_B200_NO_VSTEP") ? 8 : 0) | (getenv("ADOBO_B200_NO_WFOLD") ? 1024 : 0) | (getenv("ADOBO_B200_NO_ZPATH") ? 2048 : 0) | (getenv("ADOBO_B200_NO_PDL") ? 4096 : 0) |
-                      (getenv("ADOBO_B200_NO_RUNAHEAD") ? 8192 : 0) | (getenv("ADOBO_B200_NO_VONE") ? 16384 : 0) | (getenv("ADOBO_B200_WSTEP_V1") ? (1 << 18) : 0) | (getenv("ADOBO_B200_ROTSPLIT") ? (1 << 20) : 0) |
+                      (getenv("ADOBO_B200_NO_RUNAHEAD") ? 8192 : 0) | (getenv("ADOBO_B200_NO_VONE") ? 16384 : 0) | (getenv("ADOBO_B200_WSTEP_V1") ? (1 << 18) : 0) | (getenv("ADOBO_B200_WSTEP2") ? (1 << 17) : 0) | (getenv("ADOBO_B200_ROTSPLIT") ? (1 << 20) : 0) |
                       (getenv("ADOBO_B200_STSM") ? (1 << 21) : 0) | (getenv("ADOBO_B200_NO_SPLIT") ? (1 << 19) : 0) |
                       (getenv("ADOBO_B200_IRLB_TRACE") ? 32768 : 0) | (getenv("ADOBO_B200_SVD_FORCE_FALLBACK") ? 65536 : 0) |
                       (svd_arrow_cluster() << 4);
@@ -2389,7 +2522,8 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   // split reduction of w_step's vector (see reduce_vec_partials): single GPU, lean kernels on both sides
   const bool split = c->world == 1 && zpath && vs_one && wstep2 && getenv("ADOBO_B200_NO_SPLIT") == nullptr &&
                      getenv("ADOBO_B200_NO_WFOLD") == nullptr;  // the consuming spmvT_csc sums g: needs the folded finish
-  auto w2_fn = m_b + 1 <= 96 ? w_step2<VT, 3> : w_step2<VT, 4>;
+  const bool wstep3 = getenv("ADOBO_B200_WSTEP2") == nullptr;  // half-warp per row; w_step2 kept as a test hook
+  auto w2_fn = wstep3 ? (m_b + 1 <= 96 ? w_step3<VT, 6> : w_step3<VT, 8>) : (m_b + 1 <= 96 ? w_step2<VT, 3> : w_step2<VT, 4>);
   if (wstep2) CUDA_CHECK(cudaFuncSetAttribute(w2_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * h)));
   // under programmatic launch w_step2's CTAs start while v_step still holds VS_CLUSTER SMs: a CTA that had to wait
   // for one of those runs its whole prologue after everybody else's -- leave them out of the grid
@@ -2594,6 +2728,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     };
     prefer((const void*)w_step<VT, 3>), prefer((const void*)w_step<VT, 4>);
     prefer((const void*)w_step2<VT, 3>), prefer((const void*)w_step2<VT, 4>);
+    prefer((const void*)w_step3<VT, 6>), prefer((const void*)w_step3<VT, 8>);
     prefer((const void*)spmvT_csc<VT>), prefer((const void*)spmvT_csc_sm<VT>);
     prefer((const void*)v_step<3>), prefer((const void*)v_step<4>);
     prefer((const void*)v_step_one<3>), prefer((const void*)v_step_one<4>);
@@ -2804,12 +2939,14 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
       static unsigned long long tc[8][256];
       cudaMemcpyFromSymbol(tc, tl_cta, sizeof(tc));
       unsigned long long b0 = ~0ull;
-      for (unsigned q = 0; q < gb_n; ++q) b0 = std::min(b0, tc[1][q]);
+      const unsigned nbw = wstep2 ? gb_w2 : gb_n;
+      for (unsigned q = 0; q < nbw; ++q) b0 = std::min(b0, tc[1][q]);
       const char* nm[8] = {"entry", "sync", "rows done", "deposit+sync", "partials", "fence+sync", "atomic", "exit"};
       fprintf(stderr, "last w_step, per-CTA stamps relative to the earliest sync return (us): min / median / max\n");
       for (int i = 0; i < 8; ++i) {
         std::vector<double> v;
-        for (unsigned q = 0; q < gb_n && q < 256; ++q) v.push_back(((double)tc[i][q] - (double)b0) * 1e-3);
+        if (!tc[i][0]) continue;
+        for (unsigned q = 0; q < nbw && q < 256; ++q) v.push_back(((double)tc[i][q] - (double)b0) * 1e-3);
         std::sort(v.begin(), v.end());
         fprintf(stderr, "  %-14s %8.2f %8.2f %8.2f   (p90 %8.2f)\n", nm[i], v.front(), v[v.size() / 2], v.back(), v[v.size() * 9 / 10]);
       }

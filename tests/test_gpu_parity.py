@@ -224,7 +224,7 @@ def test_knn_blobs_30k_tensor_core_path(eng):
 @pytest.mark.parametrize('env', ['ADOBO_B200_SVD_JACOBI', 'ADOBO_B200_SVD_FORCE_FALLBACK', 'ADOBO_B200_NO_GRAPH',
                                  'ADOBO_B200_NO_FORK', 'ADOBO_B200_ROTATE_STREAMED', 'ADOBO_B200_SVD_CLUSTER', 'ADOBO_B200_NO_VSTEP',
                                  'ADOBO_B200_NO_WFOLD', 'ADOBO_B200_NO_ZPATH', 'ADOBO_B200_NO_PDL', 'ADOBO_B200_NO_RUNAHEAD',
-                                 'ADOBO_B200_NO_VONE', 'ADOBO_B200_STSM', 'ADOBO_B200_ROTSPLIT', 'ADOBO_B200_WSTEP_V1', 'ADOBO_B200_NO_SPLIT'])
+                                 'ADOBO_B200_NO_VONE', 'ADOBO_B200_STSM', 'ADOBO_B200_ROTSPLIT', 'ADOBO_B200_WSTEP_V1', 'ADOBO_B200_WSTEP2', 'ADOBO_B200_NO_SPLIT'])
 def test_irlb_alternative_svd_paths(eng, env, monkeypatch):
     """The generic Jacobi SVD of B (first iteration / fallback of the structured solver) and the
     non-graph launch path must give the same PCA as the default path."""
