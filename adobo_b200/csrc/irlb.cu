@@ -367,15 +367,29 @@ __global__ void __launch_bounds__(256, 5) spmvT_csc(const i64* __restrict__ cptr
   double uv[ST_EPF];
 #pragma unroll
   for (int q = 0; q < ST_EPF; ++q) uv[q] = (b + threadIdx.x + 256 * q < e1) ? u[ri[q]] : 0.0;
-  if (wf.W && wf.parts) {  // split reduction of w_step2's vector; nobody waits for it before the end of the dot product
+  // Warp 0 owns the norm of the W column this launch consumes: it sums the two scalars from w_step's partials
+  // (split reduction) or reads them, stores the CTA's slice of W[:, jn] = u / ||u|| and publishes the pair for the
+  // epilogue.  Nobody waits for it before the end of the dot product; warp 1 of CTA b sums column b of g for v_step.
+  if (wf.W) {
     if (threadIdx.x < 32) {
       double t0, t1;
-      sum_partials_two(wf.parts, wf.nblk, wf.jn, t0, t1);
+      if (wf.parts)
+        sum_partials_two(wf.parts, wf.nblk, wf.jn, t0, t1);
+      else
+        t0 = wf.n2p[0], t1 = wf.n2p[1];
+      const double nrm0 = sqrt(t0), sinv0 = inv_or_zero(nrm0);
+      const i64 chunk = (wf.n + gridDim.x - 1) / gridDim.x, lo = (i64)col * chunk, hi = min(wf.n, lo + chunk);
+      for (i64 r = lo + threadIdx.x; r < hi; r += 32) wf.W[(size_t)r * wf.ldw + wf.jn] = sinv0 * u[r];
       if (threadIdx.x == 0) {
         s_n2[0] = t0, s_n2[1] = t1;
-        if (wf.gout && col == 0) wf.gout[wf.jn] = t0, wf.gout[wf.jn + 1] = t1;
+        if (wf.parts && wf.gout && col == 0) wf.gout[wf.jn] = t0, wf.gout[wf.jn + 1] = t1;
+        if (col == 0) {
+          wf.sc[SC_S] = nrm0;
+          wf.sc[SC_SU] = sinv0 * t1;
+          wf.B[(size_t)wf.jn * wf.m_b + wf.jn] = nrm0;  // irlb.py:196 / 221
+        }
       }
-    } else if (wf.gout && threadIdx.x < 64) {
+    } else if (wf.parts && wf.gout && threadIdx.x < 64) {
       for (int gc = col; gc < wf.jn; gc += gridDim.x) {
         const double g = sum_partials_warp(wf.parts + gc, wf.nblk);
         if ((threadIdx.x & 31) == 0) wf.gout[gc] = g;
@@ -390,20 +404,8 @@ __global__ void __launch_bounds__(256, 5) spmvT_csc(const i64* __restrict__ cptr
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();  // also publishes s_n2
-  double sinv = 1.0;
-  if (wf.W) {
-    const double n2 = wf.parts ? s_n2[0] : wf.n2p[0], sy = wf.parts ? s_n2[1] : wf.n2p[1];
-    const double nrm = sqrt(n2);
-    sinv = inv_or_zero(nrm);
-    const i64 chunk = (wf.n + gridDim.x - 1) / gridDim.x, lo = (i64)col * chunk, hi = min(wf.n, lo + chunk);
-    for (i64 r = lo + threadIdx.x; r < hi; r += 256) wf.W[(size_t)r * wf.ldw + wf.jn] = sinv * u[r];
-    if (col == 0 && threadIdx.x == 0) {
-      wf.sc[SC_S] = nrm;
-      wf.sc[SC_SU] = sinv * sy;
-      wf.B[(size_t)wf.jn * wf.m_b + wf.jn] = nrm;  // irlb.py:196 / 221
-    }
-  }
   if (threadIdx.x == 0) {
+    const double sinv = wf.W ? inv_or_zero(sqrt(s_n2[0])) : 1.0;
     double tt = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) tt += red[w];
