@@ -72,3 +72,113 @@ https://oscar-franzen.github.io/adobo/adobo.html#adobo.normalize.norm')
         if verbose:
             print('saving %s components' % ncomp)
         obj.set_assay(sys._getframe().f_code.co_name, method)
+
+
+# ---- dr.jackstraw (dr.py:520-654): the 500 x irlb() multiplier of the hot path ------------------------------
+def _p_adjust_bh(p):
+    """Benjamini-Hochberg adjusted p-values (adobo/_stats.py:133-158)."""
+    p = np.asarray(p, dtype=np.float64)
+    q = np.full(p.shape, np.nan)
+    ok = ~np.isnan(p)
+    pv = p[ok]
+    m = float(pv.shape[0])
+    by_descend = pv.argsort()[::-1]
+    by_orig = by_descend.argsort()
+    steps = m / np.arange(m, 0, -1)
+    q[ok] = np.minimum(1, np.minimum.accumulate(steps * pv[by_descend]))[by_orig]
+    return q
+
+
+def permute_gene_columns(sub_csc, cols, rng):
+    """Independent random permutation, across cells, of the given gene columns of a cells x genes CSC matrix.
+
+    The reference permutes rows of the DENSE scaled genes x cells matrix (dr.py:606-613).  Permuting a gene across
+    cells leaves its mean and standard deviation untouched, so scaling the permuted gene equals permuting the
+    scaled gene: the matrix can stay sparse and unscaled, and the centring / scaling stays inside the mat-vecs of
+    the GPU path.  A uniformly random permutation sends the gene's nnz non-zeros to nnz distinct cells chosen
+    uniformly, each value to one of them."""
+    import scipy.sparse as sp
+    m = sp.csc_matrix(sub_csc, copy=True)
+    n = m.shape[0]
+    for j in cols:
+        lo, hi = m.indptr[j], m.indptr[j + 1]
+        pos = rng.choice(n, hi - lo, replace=False)          # entry i of the column moves to cell pos[i]
+        order = np.argsort(pos, kind='stable')
+        m.indices[lo:hi] = pos[order]
+        m.data[lo:hi] = m.data[lo:hi][order]
+    return m
+
+
+def jackstraw(obj, normalization=None, permutations=500, ncomp=None, subset_frac_genes=0.05, score_thr=1e-03,
+              fdr=0.01, retx=True, verbose=False, seed=None, eng=None):
+    """dr.jackstraw (dr.py:520-654, Chung & Storey 2015): empirical p-values of every HVG's loading on every
+    component from `permutations` PCAs of the matrix with a random 5 % of the genes permuted across cells, then
+    one chi-square p-value per component.  Every permutation is one IRLB through the GPU path (scale=True on the
+    sparse permuted subset, see `permute_gene_columns`).  `seed` (extension) makes the random draws reproducible;
+    the reference draws from the global `random` / `numpy.random` state."""
+    from scipy.stats import chi2_contingency
+    from .data import frame_to_csr
+    if normalization is None or normalization == '':
+        norm = list(obj.norm_data.keys())[-1]                # dr.py:577
+    else:
+        norm = normalization
+    item = obj.norm_data[norm]
+    try:
+        loadings = np.abs(item['dr']['pca']['contr'])
+    except KeyError:
+        raise Exception('Run `adobo.dr.pca(...)` first.')
+    X = item['data']
+    if not ncomp:
+        ncomp = loadings.shape[1]
+    elif ncomp > loadings.shape[1]:
+        raise Exception('"ncomp" is higher than the number of available \
+components computed by adobo.dr.pca(...)')
+    if verbose:
+        print('computing for ncomp=%s' % ncomp)
+    try:
+        hvg = item['hvg']['genes']
+    except KeyError:
+        raise Exception('Run adobo.dr.find_hvg() first.')
+    keep = np.flatnonzero(X.index.isin(hvg))                 # dr.py:597: original gene order
+    genes = X.index[keep]
+    sub = frame_to_csr(X)[:, keep].tocsc()                   # cells x h, sparse, unscaled
+    h = sub.shape[1]
+    nrand = int(round(h * subset_frac_genes))
+    rng = np.random.default_rng(seed)
+    eng = eng or _engine.default_engine()
+    perm_loadings = []
+    for perm in range(permutations):
+        if verbose:
+            print('random set %s ' % perm)
+        rand = np.sort(rng.choice(h, nrand, replace=False))  # dr.py:606; rows of contr come back in gene order (:616)
+        eng.upload_normalized(permute_gene_columns(sub, rand, rng).tocsr())
+        r = eng.irlb(np.arange(h), ncomp=ncomp, maxit=1000, seed=int(rng.integers(0, 2**31 - 1)), scale=True,
+                     var_weigh=True)
+        perm_loadings.append(np.abs(r['contr'][rand, :ncomp]))
+    null = np.concatenate(perm_loadings, axis=0) if perm_loadings else np.zeros((0, ncomp))
+    real = np.asarray(loadings)[:, :ncomp]
+    # empirical p-value of a loading: share of the null loadings of that component above it (dr.py:621-624)
+    res = np.empty(real.shape)
+    for i in range(ncomp):
+        srt = np.sort(null[:, i])
+        res[:, i] = (srt.shape[0] - np.searchsorted(srt, real[:, i], side='right')) / max(srt.shape[0], 1)
+    res = pd.DataFrame(res, columns=['PC%d' % i for i in range(ncomp)])    # dr.py:625-628 (ignore_index: 0..h-1)
+    final = []
+    for i in range(ncomp):                                   # dr.py:630-643
+        pc = res.iloc[:, i].values
+        nsign_found = np.sum(pc < score_thr)
+        nsign_expected = np.floor(len(pc) * score_thr)
+        ct = [[nsign_found, nsign_expected], [len(pc) - nsign_found, len(pc) - nsign_expected]]
+        try:
+            pv = chi2_contingency(np.array(ct))[1]
+        except ValueError:
+            pv = 1
+        final.append(['PC%d' % i, pv])
+    final = pd.DataFrame(final)
+    final['p.adj'] = _p_adjust_bh(final[1])
+    final.columns = ['PC', 'chi2_p', 'chi2_p_adj']
+    final['significant'] = final.chi2_p_adj < fdr
+    eng.resident_key = None                                  # the device holds the last permuted copy, not `X`
+    obj.norm_data[norm]['dr']['jackstraw'] = {'score_mat': res, 'results_by_comp': final}
+    if retx:
+        return res, final
