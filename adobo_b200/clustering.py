@@ -33,13 +33,24 @@ def snn(nn_idx, k=10, prune_snn=0.067, verbose=False, eng=None):
     return pd.DataFrame({'source_node': edges[:, 0].astype(np.int64), 'target_node': edges[:, 1].astype(np.int64)})
 
 
+def edge_arrays(snn_graph):
+    """What the partitioners need from the SNN graph, as arrays: the number of vertices exactly as
+    the reference counts them -- distinct values of the first column (clustering.py:155, 196) -- and a C-contiguous
+    (E, 2) int32 edge array, which `igraph.Graph.add_edges` takes directly.  The reference builds a Python list of
+    tuples with `itertuples` (clustering.py:159-162): minutes at a million cells."""
+    cols = snn_graph.columns
+    src = np.asarray(snn_graph[cols[0]])
+    edges = np.ascontiguousarray(np.stack([src, np.asarray(snn_graph[cols[1]])], axis=1), dtype=np.int32)
+    return int(np.unique(src).shape[0]), edges
+
+
 def _igraph_from_edges(snn_graph):
     import igraph as ig
-    n = len(set(snn_graph[snn_graph.columns[0]]))
+    n, edges = edge_arrays(snn_graph)
     g = ig.Graph()
     g.add_vertices(n)
-    g.vs['name'] = list(range(1, n + 1))
-    g.add_edges(snn_graph.values.tolist())               # clustering.py:154-162 without the Python loop
+    g.vs['name'] = list(range(1, n + 1))                 # clustering.py:158
+    g.add_edges(edges)                                   # clustering.py:159-162 without the Python loop
     return g
 
 

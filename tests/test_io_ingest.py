@@ -53,3 +53,14 @@ def test_live_reference_when_present():
     ours = IO.load_matrix_market(ARCHIVE)
     assert list(ref.index) == list(ours.index) and list(ref.columns) == list(ours.columns)
     assert np.array_equal(np.asarray(ref.values), np.asarray(ours.sparse.to_dense().values))
+
+
+def test_edge_arrays_is_the_reference_graph_construction():
+    """clustering.py:154-162: vertices = distinct source nodes, edges = the rows as tuples."""
+    import pandas as pd
+    from adobo_b200.clustering import edge_arrays
+    g = pd.DataFrame({'source_node': [0, 0, 1, 2, 2, 2, 4], 'target_node': [0, 2, 1, 0, 2, 4, 4]})
+    n, edges = edge_arrays(g)
+    ll = [tuple(i) for i in g.itertuples(index=False)]                 # the reference's loop
+    assert n == len(set(g[g.columns[0]])) == 4
+    assert edges.dtype == np.int32 and edges.flags['C_CONTIGUOUS'] and [tuple(e) for e in edges.tolist()] == ll
