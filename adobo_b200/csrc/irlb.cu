@@ -425,6 +425,99 @@ __global__ void __launch_bounds__(256, 5) spmvT_csc(const i64* __restrict__ cptr
   TL_EXIT(128 + (wf.W ? wf.jn : 127));
 }
 
+// ---- spmvT_csc_mg (opt-in, ADOBO_B200_MGSPLIT; NOT yet run on hardware): split reduction with several GPUs ------
+// With several GPUs w_step3 still ends in a serial last CTA (fence, atomic, 4.6 us of sums, NVLink exchange) before
+// spmvT_csc may start.  Here w_step3 stops at its per-CTA partials on every rank and this kernel's CTA 0 -- an extra
+// CTA without a column -- sums the local partials of all j + 2 columns, exchanges the vector with its peers
+// (peer_allreduce_block: the sums land in rank order on every rank, bit-identical) and raises a flag; the column CTAs
+// compute their dot products meanwhile and only wait for the flag before the epilogue that needs ||y||.  The last CTA
+// to finish resets the flag and exchanges t as before.  Only for folded W finishes (wf.W != nullptr).
+template <typename VT>
+__global__ void __launch_bounds__(256, 5) spmvT_csc_mg(const i64* __restrict__ cptr, const int* __restrict__ ridx,
+                                                    const VT* __restrict__ cval, const double* __restrict__ u,
+                                                    double* __restrict__ t, int h, unsigned* __restrict__ counter,
+                                                    const PeerComm pc, const WFinish wf, const int* __restrict__ halt,
+                                                    unsigned* __restrict__ flag) {
+  __shared__ double red[8];
+  __shared__ double ps2[2][MAXB];
+  __shared__ bool last_cta;
+  const int col = (int)blockIdx.x - 1;  // CTA 0: the exchange; CTA c + 1: column c
+  i64 b = 0, e1 = 0;
+  int ri[ST_EPF];
+  VT cv[ST_EPF];
+  if (col >= 0) {
+    b = __ldg(cptr + col), e1 = __ldg(cptr + col + 1);
+#pragma unroll
+    for (int q = 0; q < ST_EPF; ++q) {
+      const i64 e = b + threadIdx.x + 256 * q;
+      ri[q] = e < e1 ? __ldg(ridx + e) : 0;
+      cv[q] = e < e1 ? __ldg(cval + e) : VT(0);
+    }
+  }
+  pdl_sync();
+  if (halt && *halt) return;
+  const int nv = wf.jn + 2;  // g (jn columns), ||y||^2, sum y
+  if (col < 0) {
+    // local sums, thread = (column, part of 2), then the exchange, then the flag
+    const int c = threadIdx.x & (MAXB - 1), part = threadIdx.x >> 7;
+    ps2[part][c] = c < nv ? sum_partials_part(wf.parts + c, part, 2, wf.nblk) : 0.0;
+    __syncthreads();
+    if ((int)threadIdx.x < nv) wf.gout[threadIdx.x] = ps2[0][threadIdx.x] + ps2[1][threadIdx.x];
+    __syncthreads();
+    peer_allreduce_block(pc, wf.gout, nv);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const double n2 = __ldcg(wf.gout + wf.jn), sy = __ldcg(wf.gout + wf.jn + 1);
+      const double nrm = sqrt(n2), sinv = inv_or_zero(nrm);
+      wf.sc[SC_S] = nrm;
+      wf.sc[SC_SU] = sinv * sy;
+      wf.B[(size_t)wf.jn * wf.m_b + wf.jn] = nrm;  // irlb.py:196 / 221
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(1u) : "memory");
+    }
+  } else {
+    double uv[ST_EPF];
+#pragma unroll
+    for (int q = 0; q < ST_EPF; ++q) uv[q] = (b + threadIdx.x + 256 * q < e1) ? u[ri[q]] : 0.0;
+    double s = 0;
+#pragma unroll
+    for (int q = 0; q < ST_EPF; ++q) s += (double)cv[q] * uv[q];
+#pragma unroll 4
+    for (i64 e = b + threadIdx.x + 256 * ST_EPF; e < e1; e += 256) s += (double)__ldg(cval + e) * u[__ldg(ridx + e)];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    if (threadIdx.x == 0) {  // the global ||y||^2 is there once CTA 0 has raised the flag
+      unsigned v;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+      } while (v == 0u);
+    }
+    __syncthreads();
+    const double sinv = inv_or_zero(sqrt(__ldcg(wf.gout + wf.jn)));
+    const i64 ncol = (i64)gridDim.x - 1;
+    const i64 chunk = (wf.n + ncol - 1) / ncol, lo = (i64)col * chunk, hi = min(wf.n, lo + chunk);
+    for (i64 r = lo + threadIdx.x; r < hi; r += 256) wf.W[(size_t)r * wf.ldw + wf.jn] = sinv * u[r];
+    if (threadIdx.x == 0) {
+      double tt = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) tt += red[w];
+      t[col] = tt * sinv;
+    }
+  }
+  // every CTA (the exchange CTA too) checks out; the last one resets the flag and sums t over the ranks
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last_cta = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last_cta) {
+    if (threadIdx.x == 0) *flag = 0u;
+    peer_allreduce_block(pc, t, h);
+    if (threadIdx.x == 0) *counter = 0;
+  }
+}
+
 // ---- K5 for short shards: u staged in shared memory, columns dealt to CTAs by length -------------------
 // Two things bound spmvT_csc when the whole problem sits in L2 (20 k cells: 11-12 us per launch):
 //  * the gather u[ridx]: rows of a column are ~10 apart, so every 8-byte gather moves its own 32-byte sector and
@@ -2379,7 +2472,7 @@ struct IrlbWs {
   int sig_i[6] = {};
   double sig_tol = 0;
   DevBuf<double> V, W, B, sc, tbuf, ybuf_h, ybuf_n, fbuf, xs, wcur, cvec, partials, Su, Sv, svd_s, R, murs, St, Z, sumW, gout, crot;
-  DevBuf<unsigned> counter;
+  DevBuf<unsigned> counter, mgflag;
   DevBuf<int> info, perm;
   std::map<int, cudaGraphExec_t> graphs;
   std::map<int, i64> graph_launches;
@@ -2424,7 +2517,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     // test hooks read from the environment change what a captured iteration contains
     const int hooks = (getenv("ADOBO_B200_SVD_JACOBI") ? 1 : 0) | (getenv("ADOBO_B200_NO_FORK") ? 2 : 0) |
                       (getenv("ADOBO_B200_ROTATE_STREAMED") ? 4 : 0) | (getenv("ADOBO_B200_NO_VSTEP") ? 8 : 0) | (getenv("ADOBO_B200_NO_WFOLD") ? 1024 : 0) | (getenv("ADOBO_B200_NO_ZPATH") ? 2048 : 0) | (getenv("ADOBO_B200_NO_PDL") ? 4096 : 0) |
-                      (getenv("ADOBO_B200_NO_RUNAHEAD") ? 8192 : 0) | (getenv("ADOBO_B200_NO_VONE") ? 16384 : 0) | (getenv("ADOBO_B200_WSTEP_V1") ? (1 << 18) : 0) | (getenv("ADOBO_B200_WSTEP2") ? (1 << 17) : 0) | (getenv("ADOBO_B200_ROTSPLIT") ? (1 << 20) : 0) |
+                      (getenv("ADOBO_B200_NO_RUNAHEAD") ? 8192 : 0) | (getenv("ADOBO_B200_NO_VONE") ? 16384 : 0) | (getenv("ADOBO_B200_WSTEP_V1") ? (1 << 18) : 0) | (getenv("ADOBO_B200_MGSPLIT") ? (1 << 23) : 0) | (getenv("ADOBO_B200_WSTEP2") ? (1 << 17) : 0) | (getenv("ADOBO_B200_ROTSPLIT") ? (1 << 20) : 0) |
                       (getenv("ADOBO_B200_STSM") ? (1 << 21) : 0) | (getenv("ADOBO_B200_NO_SPLIT") ? (1 << 19) : 0) |
                       (getenv("ADOBO_B200_IRLB_TRACE") ? 32768 : 0) | (getenv("ADOBO_B200_SVD_FORCE_FALLBACK") ? 65536 : 0) |
                       (svd_arrow_cluster() << 4);
@@ -2524,6 +2617,13 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   // split reduction of w_step's vector (see reduce_vec_partials): single GPU, lean kernels on both sides
   const bool split = c->world == 1 && zpath && vs_one && wstep2 && getenv("ADOBO_B200_NO_SPLIT") == nullptr &&
                      getenv("ADOBO_B200_NO_WFOLD") == nullptr;  // the consuming spmvT_csc sums g: needs the folded finish
+  // the same with several GPUs (spmvT_csc_mg): opt-in until it has been run on hardware
+  const bool mgsplit = c->world > 1 && c->peer.world == c->world && h <= PEER_SLOT && zpath && vs_one && wstep2 &&
+                       getenv("ADOBO_B200_NO_WFOLD") == nullptr && getenv("ADOBO_B200_MGSPLIT") != nullptr;
+  if (mgsplit) {
+    ws.mgflag.ensure(1);
+    CUDA_CHECK(cudaMemsetAsync(ws.mgflag.p, 0, sizeof(unsigned), st));
+  }
   const bool wstep3 = getenv("ADOBO_B200_WSTEP2") == nullptr;  // half-warp per row; w_step2 kept as a test hook
   auto w2_fn = wstep3 ? (m_b + 1 <= 96 ? w_step3<VT, 6> : w_step3<VT, 8>) : (m_b + 1 <= 96 ? w_step2<VT, 3> : w_step2<VT, 4>);
   if (wstep2) CUDA_CHECK(cudaFuncSetAttribute(w2_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * h)));
@@ -2618,7 +2718,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
         LAUNCH(c, "w_step", CUDA_CHECK(launch_k(w2_fn, dim3(gb_w2), dim3(W2_THREADS),
                                                 sizeof(double) * h, st, pdl && jprev >= 0, 1, A.rptr.p, A.cidx.p, A.rval.p, xs.p,
                                                 sc.p, W.p, ld, jprev, nd, (int)n, cvec.p, ybuf_n.p, partials.p, gout.p, counter.p,
-                                                pcw, hp, h, split ? 1 : 0)));
+                                                pcw, hp, h, (split || (mgsplit && jn != m_b - 1)) ? 1 : 0)));
       else
         LAUNCH(c, "w_step", CUDA_CHECK(launch_k(m_b + 1 <= 96 ? w_step<VT, 3> : w_step<VT, 4>, dim3(gb_n), dim3(RT_THREADS), 0, st,
                                                 pdl && jprev >= 0, 1, A.rptr.p, A.cidx.p, A.rval.p, xs.p, sc.p, W.p, ld, jprev, nd, n,
@@ -2762,7 +2862,12 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
           wf.n2p = zpath ? gout.p + j : sc.p + SC_NRM2,  // column j came from w_step with nd = j
           wf.parts = split ? partials.p : nullptr, wf.nblk = (int)gb_w2, wf.gout = split ? gout.p : nullptr;
         const bool spdl = pdl && infold && zpath && (fused || c->world == 1);
-        if (st_sm)
+        if (mgsplit && infold) {
+          wf.parts = partials.p, wf.nblk = (int)gb_w2, wf.gout = gout.p;
+          LAUNCH(c, "spmvT_csc", CUDA_CHECK(launch_k(spmvT_csc_mg<VT>, dim3(h + 1), dim3(256), 0, st, spdl, 1, A.cptr.p, A.ridx.p,
+                                                     A.cval.p, (const double*)ybuf_n.p, tbuf.p, h, counter.p + 1, pcw, wf, hp,
+                                                     ws.mgflag.p)));
+        } else if (st_sm)
           LAUNCH(c, "spmvT_csc", CUDA_CHECK(launch_k(spmvT_csc_sm<VT>, dim3(st_grid), dim3(STS_THREADS), st_smem, st, spdl, 1, A.cptr.p,
                                                      A.ridx.p, A.cval.p, (const double*)(infold ? ybuf_n.p : wcur.p), tbuf.p, h,
                                                      counter.p + 1, fused_t ? pcw : pc1, wf, hp, (int)n, (const int*)ws.perm.p,
