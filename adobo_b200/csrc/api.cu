@@ -227,9 +227,9 @@ static void prof_collect(adobo_ctx* c) {
 // with CUDA IPC (one process per GPU on one node).
 static void setup_peer(adobo_ctx* c) {
   const int W = c->world;
-  const size_t data_bytes = sizeof(double) * 2 * (size_t)W * PEER_SLOT;
-  const size_t flag_bytes = sizeof(unsigned) * 2 * (size_t)W * 32;
-  const size_t bytes = data_bytes + flag_bytes + 256;
+  const size_t data_bytes = sizeof(double) * 2 * (size_t)W * (2 * PEER_SLOT);
+  const size_t flag_bytes = sizeof(unsigned) * 2 * (size_t)W * PEER_CH * 32;
+  const size_t bytes = data_bytes + flag_bytes + 256;  // + the PEER_CH sequence counters
   void* mb = nullptr;
   CUDA_CHECK(cudaMalloc(&mb, bytes));
   CUDA_CHECK(cudaMemset(mb, 0, bytes));

@@ -96,18 +96,26 @@ struct SparsePair {
 struct Comm;  // NCCL wrapper, api.cu
 
 // One-shot all-reduce over NVLink peer memory (api.cu sets it up with CUDA IPC when world > 1).
-// Every rank owns a mailbox data[parity][rank][PEER_SLOT] + flags[parity][rank]; a reducing kernel's
-// last CTA writes its vector into ITS slot of EVERY peer's mailbox, releases a sequence flag, waits for
-// the flags of all ranks in its own mailbox and sums the slots in rank order -- the result is bitwise
-// identical on all ranks, and the exchange is part of the kernel that produced the partial sums
-// (no separate collective launch; ~3 of these per Lanczos step replace three ncclAllReduce calls).
+// Every rank owns a mailbox data[parity][rank][2 PEER_SLOT] + flags[parity][rank][channel]; an exchanging CTA writes
+// its vector into ITS slot of EVERY peer's mailbox, releases a sequence flag, waits for the flags of all ranks in
+// its own mailbox and sums the slots in rank order -- the result is bitwise identical on all ranks, and the exchange
+// is part of the kernel that needs the sum (no separate collective launch).  Channels keep concurrent exchanges
+// apart: channel 0 is the one-CTA exchange of the last-CTA reductions (first PEER_SLOT doubles of a rank slot),
+// channels 1..PEER_CTAS belong to CTA c-1 of the V-side cluster kernel, which exchange their slices of the step's
+// vector in parallel (PEER_CH_SLOT doubles each, in the second half of the rank slot).
 constexpr int PEER_MAX = 8;
-constexpr int PEER_SLOT = 4096;  // doubles per rank slot: larger vectors go through NCCL
+constexpr int PEER_SLOT = 4096;    // doubles per rank slot on channel 0: larger vectors go through NCCL
+constexpr int PEER_CTAS = 8;       // cluster CTAs with a channel of their own
+constexpr int PEER_CH = 1 + PEER_CTAS;
+constexpr int PEER_CH_SLOT = PEER_SLOT / PEER_CTAS;  // 512 doubles per cluster-CTA channel
+constexpr unsigned long long PEER_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;  // a peer that is 20 s late is dead
 struct PeerComm {
   int world = 1, rank = 0;
   double* data[PEER_MAX] = {};     // mailbox of every rank (peer pointers through CUDA IPC)
-  unsigned* flags[PEER_MAX] = {};  // [2][world] sequence flags, 128 bytes apart
-  unsigned* seq = nullptr;         // this rank's sequence counter (device)
+  unsigned* flags[PEER_MAX] = {};  // [2][world][PEER_CH] sequence flags, 128 bytes apart
+  unsigned* seq = nullptr;         // [PEER_CH] this rank's sequence counters (device)
+  int* err = nullptr;              // raised when a peer did not answer within PEER_TIMEOUT_NS (the kernel goes on
+                                   // with garbage instead of hanging the GPU; the host turns it into an error)
 };
 
 }  // namespace adobo
@@ -247,42 +255,62 @@ __device__ __forceinline__ int warp_sum(int v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-// ---- fused all-reduce over peer memory: called by ALL threads of ONE CTA; vec is in global memory ----
-__device__ __forceinline__ void peer_allreduce_block(const PeerComm& pc, double* vec, int count) {
+// ---- fused all-reduce over peer memory: called by ALL threads of ONE CTA ------------------------------------
+// `vec` (global or shared memory of the calling CTA, `count` doubles) is replaced by its sum over the ranks.
+// ch = 0: one CTA per rank exchanges up to PEER_SLOT doubles; ch = 1..PEER_CTAS: up to PEER_CH_SLOT doubles.
+__device__ __forceinline__ unsigned long long peer_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+template <bool SMEM = false>  // SMEM: vec is shared memory of the calling CTA (else global, read through L2)
+__device__ __forceinline__ void peer_allreduce_block(const PeerComm& pc, double* vec, int count, int ch = 0) {
   __shared__ unsigned s_seq;
   const int W = pc.world, me = pc.rank;
-  if (threadIdx.x == 0) s_seq = *pc.seq + 1u;
+  if (threadIdx.x == 0) s_seq = pc.seq[ch] + 1u;
   __syncthreads();
   const unsigned seq = s_seq;
   const int par = (int)(seq & 1u);
+  const size_t choff = ch == 0 ? 0 : (size_t)PEER_SLOT + (size_t)(ch - 1) * PEER_CH_SLOT;
   // phase 1: my vector into my slot of every rank's mailbox (NVLink stores), then release the flag
   for (int r = 0; r < W; ++r) {
-    double* dst = pc.data[r] + ((size_t)(par * W + me)) * PEER_SLOT;
-    for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = __ldcg(vec + i);
+    double* dst = pc.data[r] + ((size_t)(par * W + me)) * (2 * PEER_SLOT) + choff;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = SMEM ? vec[i] : __ldcg(vec + i);
   }
   __threadfence_system();
   __syncthreads();
   if ((int)threadIdx.x < W) {
-    unsigned* f = pc.flags[threadIdx.x] + (size_t)(par * W + me) * 32;
+    unsigned* f = pc.flags[threadIdx.x] + ((size_t)(par * W + me) * PEER_CH + ch) * 32;
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(seq) : "memory");
   }
-  // phase 2: wait for every rank's contribution in MY mailbox, sum in rank order
+  // phase 2: wait for every rank's contribution in MY mailbox (bounded), sum in rank order
   if ((int)threadIdx.x < W) {
-    const unsigned* f = pc.flags[me] + (size_t)(par * W + threadIdx.x) * 32;
+    const unsigned* f = pc.flags[me] + ((size_t)(par * W + threadIdx.x) * PEER_CH + ch) * 32;
     unsigned v;
-    do {
+    unsigned long long t0 = 0;
+    unsigned polls = 0;
+    for (;;) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-    } while (v != seq);
+      if (v == seq) break;
+      if ((++polls & 1023u) == 0) {
+        const unsigned long long now = peer_now_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > PEER_TIMEOUT_NS) {
+          if (pc.err) atomicExch(pc.err, 1 + (int)threadIdx.x);
+          break;
+        }
+      }
+    }
   }
   __syncthreads();
-  const double* mine = pc.data[me] + (size_t)(par * W) * PEER_SLOT;
+  const double* mine = pc.data[me] + (size_t)(par * W) * (2 * PEER_SLOT) + choff;
   for (int i = threadIdx.x; i < count; i += blockDim.x) {
     double s = 0;
-    for (int r = 0; r < W; ++r) s += __ldcv(mine + (size_t)r * PEER_SLOT + i);
+    for (int r = 0; r < W; ++r) s += __ldcv(mine + (size_t)r * (2 * PEER_SLOT) + i);
     vec[i] = s;
   }
   __syncthreads();
-  if (threadIdx.x == 0) *pc.seq = seq;
+  if (threadIdx.x == 0) pc.seq[ch] = seq;
 }
 
 // (c, s) of the Jacobi rotation that orthogonalises two columns with squared norms nx, ny and inner

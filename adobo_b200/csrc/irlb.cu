@@ -121,14 +121,15 @@ __device__ __forceinline__ void deposit_lane8(double (&acc)[NQ]) {
 constexpr int SP_PARTS = 8, SP_PER = 19;  // 8 x 19 >= 148 CTAs: a part's loads are issued as one batch
 // the part sum of one column: CTAs part, part + SP_PARTS, ... in ascending order
 template <int PER = SP_PER>
-__device__ __forceinline__ double sum_partials_part(const double* __restrict__ src, int part, int nparts, int nblk) {
+__device__ __forceinline__ double sum_partials_part(const double* __restrict__ src, int part, int nparts, int nblk,
+                                                    int stride = MAXB) {
   double p = 0;
   for (int base = part; base < nblk; base += nparts * PER) {  // one trip for <= nparts x PER CTAs
     double v[PER];
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
       const int b = base + nparts * i;
-      v[i] = b < nblk ? __ldcg(src + (size_t)b * MAXB) : 0.0;
+      v[i] = b < nblk ? __ldcg(src + (size_t)b * stride) : 0.0;
     }
 #pragma unroll
     for (int i = 0; i < PER; ++i) p += v[i];
@@ -425,239 +426,6 @@ __global__ void __launch_bounds__(256, 5) spmvT_csc(const i64* __restrict__ cptr
   TL_EXIT(128 + (wf.W ? wf.jn : 127));
 }
 
-// ---- spmvT_csc_mg (opt-in, ADOBO_B200_MGSPLIT; NOT yet run on hardware): split reduction with several GPUs ------
-// With several GPUs w_step3 still ends in a serial last CTA (fence, atomic, 4.6 us of sums, NVLink exchange) before
-// spmvT_csc may start.  Here w_step3 stops at its per-CTA partials on every rank and this kernel's CTA 0 -- an extra
-// CTA without a column -- sums the local partials of all j + 2 columns, exchanges the vector with its peers
-// (peer_allreduce_block: the sums land in rank order on every rank, bit-identical) and raises a flag; the column CTAs
-// compute their dot products meanwhile and only wait for the flag before the epilogue that needs ||y||.  The last CTA
-// to finish resets the flag and exchanges t as before.  Only for folded W finishes (wf.W != nullptr).
-template <typename VT>
-__global__ void __launch_bounds__(256, 5) spmvT_csc_mg(const i64* __restrict__ cptr, const int* __restrict__ ridx,
-                                                    const VT* __restrict__ cval, const double* __restrict__ u,
-                                                    double* __restrict__ t, int h, unsigned* __restrict__ counter,
-                                                    const PeerComm pc, const WFinish wf, const int* __restrict__ halt,
-                                                    unsigned* __restrict__ flag) {
-  __shared__ double red[8];
-  __shared__ double ps2[2][MAXB];
-  __shared__ bool last_cta;
-  const int col = (int)blockIdx.x - 1;  // CTA 0: the exchange; CTA c + 1: column c
-  i64 b = 0, e1 = 0;
-  int ri[ST_EPF];
-  VT cv[ST_EPF];
-  if (col >= 0) {
-    b = __ldg(cptr + col), e1 = __ldg(cptr + col + 1);
-#pragma unroll
-    for (int q = 0; q < ST_EPF; ++q) {
-      const i64 e = b + threadIdx.x + 256 * q;
-      ri[q] = e < e1 ? __ldg(ridx + e) : 0;
-      cv[q] = e < e1 ? __ldg(cval + e) : VT(0);
-    }
-  }
-  pdl_sync();
-  if (halt && *halt) return;
-  const int nv = wf.jn + 2;  // g (jn columns), ||y||^2, sum y
-  if (col < 0) {
-    // local sums, thread = (column, part of 2), then the exchange, then the flag
-    const int c = threadIdx.x & (MAXB - 1), part = threadIdx.x >> 7;
-    ps2[part][c] = c < nv ? sum_partials_part(wf.parts + c, part, 2, wf.nblk) : 0.0;
-    __syncthreads();
-    if ((int)threadIdx.x < nv) wf.gout[threadIdx.x] = ps2[0][threadIdx.x] + ps2[1][threadIdx.x];
-    __syncthreads();
-    peer_allreduce_block(pc, wf.gout, nv);
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const double n2 = __ldcg(wf.gout + wf.jn), sy = __ldcg(wf.gout + wf.jn + 1);
-      const double nrm = sqrt(n2), sinv = inv_or_zero(nrm);
-      wf.sc[SC_S] = nrm;
-      wf.sc[SC_SU] = sinv * sy;
-      wf.B[(size_t)wf.jn * wf.m_b + wf.jn] = nrm;  // irlb.py:196 / 221
-      __threadfence();
-      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(1u) : "memory");
-    }
-  } else {
-    double uv[ST_EPF];
-#pragma unroll
-    for (int q = 0; q < ST_EPF; ++q) uv[q] = (b + threadIdx.x + 256 * q < e1) ? u[ri[q]] : 0.0;
-    double s = 0;
-#pragma unroll
-    for (int q = 0; q < ST_EPF; ++q) s += (double)cv[q] * uv[q];
-#pragma unroll 4
-    for (i64 e = b + threadIdx.x + 256 * ST_EPF; e < e1; e += 256) s += (double)__ldg(cval + e) * u[__ldg(ridx + e)];
-    s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-    if (threadIdx.x == 0) {  // the global ||y||^2 is there once CTA 0 has raised the flag
-      unsigned v;
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-      } while (v == 0u);
-    }
-    __syncthreads();
-    const double sinv = inv_or_zero(sqrt(__ldcg(wf.gout + wf.jn)));
-    const i64 ncol = (i64)gridDim.x - 1;
-    const i64 chunk = (wf.n + ncol - 1) / ncol, lo = (i64)col * chunk, hi = min(wf.n, lo + chunk);
-    for (i64 r = lo + threadIdx.x; r < hi; r += 256) wf.W[(size_t)r * wf.ldw + wf.jn] = sinv * u[r];
-    if (threadIdx.x == 0) {
-      double tt = 0;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) tt += red[w];
-      t[col] = tt * sinv;
-    }
-  }
-  // every CTA (the exchange CTA too) checks out; the last one resets the flag and sums t over the ranks
-  if (threadIdx.x == 0) {
-    __threadfence();
-    last_cta = (atomicAdd(counter, 1u) == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (last_cta) {
-    if (threadIdx.x == 0) *flag = 0u;
-    peer_allreduce_block(pc, t, h);
-    if (threadIdx.x == 0) *counter = 0;
-  }
-}
-
-// ---- K5 for short shards: u staged in shared memory, columns dealt to CTAs by length -------------------
-// Two things bound spmvT_csc when the whole problem sits in L2 (20 k cells: 11-12 us per launch):
-//  * the gather u[ridx]: rows of a column are ~10 apart, so every 8-byte gather moves its own 32-byte sector and
-//    costs an L1 tag cycle -- when the shard's u fits in shared memory (n <= 25 k rows) each of the one-per-SM
-//    CTAs copies it once with coalesced loads and the gathers become LDS;
-//  * column lengths: HVG columns range from a few hundred to n non-zeros, and a kernel that gives every column
-//    the same number of threads ends when its longest column does (median CTA done after 3.3 us, last after
-//    11.8 us, measured).  Here a CTA owns up to STS_MAXC columns and ALL its threads walk each of them; the host
-//    deals the columns, sorted by length, to the CTAs in snake order (perm), so CTAs carry about equal non-zeros.
-// The first STS_EPF x 512 entries of every owned column are fetched before the grid-dependency wait.
-// (Holding this kernel and w_step2 to 64 registers so that their CTAs co-reside under programmatic launch was
-// measured and rejected: the row loop of w_step2 went from 6.4 to 14.6 us.)
-constexpr int STS_THREADS = 512, STS_MAXC = 8, STS_EPF = 4;
-template <typename VT>
-__global__ void __launch_bounds__(STS_THREADS, 1)
-    spmvT_csc_sm(const i64* __restrict__ cptr, const int* __restrict__ ridx, const VT* __restrict__ cval,
-                 const double* __restrict__ u, double* __restrict__ t, int h, unsigned* __restrict__ counter,
-                 const PeerComm pc, const WFinish wf, const int* __restrict__ halt, int n, const int* __restrict__ perm,
-                 int cpb) {
-  extern __shared__ __align__(16) double us[];  // [n]
-  __shared__ double red[STS_THREADS / 32][STS_MAXC];
-  __shared__ double s_n2[2];
-  __shared__ bool last_cta;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  TL_ENTRY_REG();
-#ifdef ADOBO_B200_TIMELINE
-  const bool tl_on = wf.W && wf.jn == wf.m_b - 2;  // a programmatically launched instance
-  TL_CTAK(0, 5);
-#endif
-  // prologue: static CSC arrays of the owned columns
-  int colk[STS_MAXC], bk[STS_MAXC], lenk[STS_MAXC];
-  int ri[STS_MAXC][STS_EPF];
-  VT cv[STS_MAXC][STS_EPF];
-#pragma unroll
-  for (int k = 0; k < STS_MAXC; ++k) {  // slot descriptors (column, first entry, length), laid out by the host
-    colk[k] = -1, bk[k] = 0, lenk[k] = 0;
-    if (k < cpb) {
-      const int* d = perm + 3 * (size_t)(blockIdx.x + gridDim.x * k);
-      colk[k] = __ldg(d);  // -1: empty slot
-      bk[k] = __ldg(d + 1);
-      lenk[k] = __ldg(d + 2);
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < STS_MAXC; ++k)
-#pragma unroll
-    for (int q = 0; q < STS_EPF; ++q) {
-      const int e = tid + STS_THREADS * q;
-      ri[k][q] = e < lenk[k] ? __ldg(ridx + bk[k] + e) : 0;
-      cv[k][q] = e < lenk[k] ? __ldg(cval + bk[k] + e) : VT(0);
-    }
-  TL_CTAK(0, 6);
-  pdl_sync();
-  if (halt && *halt) return;
-  TL_SYNC(128 + (wf.W ? wf.jn : 127));
-  TL_CTAK(0, 0);
-  if (wf.W && tid < 32) {
-    double t0, t1;
-    if (wf.parts)
-      sum_partials_two(wf.parts, wf.nblk, wf.jn, t0, t1);
-    else
-      t0 = wf.n2p[0], t1 = wf.n2p[1];
-    if (tid == 0) {
-      s_n2[0] = t0, s_n2[1] = t1;
-      if (wf.gout && blockIdx.x == 0) wf.gout[wf.jn] = t0, wf.gout[wf.jn + 1] = t1;
-    }
-  }
-  if (wf.W && wf.gout && warp == 1)  // g = W^T y for v_step: CTA b sums column b of w_step's partials
-    for (int gc = blockIdx.x; gc < wf.jn; gc += gridDim.x) {
-      const double g = sum_partials_warp(wf.parts + gc, wf.nblk);
-      if (lane == 0) wf.gout[gc] = g;
-    }
-  {
-    const double2* u2 = reinterpret_cast<const double2*>(u);
-    double2* us2 = reinterpret_cast<double2*>(us);
-#pragma unroll 4
-    for (int i = tid; i < (n >> 1); i += STS_THREADS) us2[i] = __ldcg(u2 + i);
-    if ((n & 1) && tid == 0) us[n - 1] = __ldcg(u + n - 1);
-  }
-  TL_CTAK(0, 1);
-  __syncthreads();
-  TL_CTAK(0, 2);
-  double sinv = 1.0;
-  if (wf.W) {  // W[:, jn] = u / ||u|| for this CTA's slice of rows (see spmvT_csc)
-    const double nrm = sqrt(s_n2[0]);
-    sinv = inv_or_zero(nrm);
-    const int chunk = (n + gridDim.x - 1) / gridDim.x, lo = blockIdx.x * chunk, hi = min(n, lo + chunk);
-    for (int r = lo + tid; r < hi; r += STS_THREADS) wf.W[(size_t)r * wf.ldw + wf.jn] = sinv * us[r];
-    if (blockIdx.x == 0 && tid == 0) {
-      wf.sc[SC_S] = nrm;
-      wf.sc[SC_SU] = sinv * s_n2[1];
-      wf.B[(size_t)wf.jn * wf.m_b + wf.jn] = nrm;  // irlb.py:196 / 221
-    }
-  }
-  TL_CTAK(0, 3);
-  double sk[STS_MAXC];
-#pragma unroll
-  for (int k = 0; k < STS_MAXC; ++k) {
-    double s = 0;
-#pragma unroll
-    for (int q = 0; q < STS_EPF; ++q)
-      if (tid + STS_THREADS * q < lenk[k]) s += (double)cv[k][q] * us[ri[k][q]];
-#pragma unroll 2
-    for (int e = tid + STS_THREADS * STS_EPF; e < lenk[k]; e += STS_THREADS)
-      s += (double)__ldg(cval + bk[k] + e) * us[__ldg(ridx + bk[k] + e)];
-    sk[k] = s;
-  }
-#pragma unroll
-  for (int k = 0; k < STS_MAXC; ++k) {
-    if (k < cpb) {  // uniform
-      const double s = warp_sum(sk[k]);
-      if (lane == 0) red[warp][k] = s;
-    }
-  }
-  __syncthreads();
-  if (warp < cpb) {  // warp k finishes column k: fixed butterfly over the 16 warp partials
-    double v = lane < STS_THREADS / 32 ? red[lane][warp] : 0.0;
-    v = warp_sum(v);
-    int mycol = -1;
-#pragma unroll
-    for (int k = 0; k < STS_MAXC; ++k)
-      if (k == warp) mycol = colk[k];
-    if (lane == 0 && mycol >= 0) t[mycol] = v * sinv;
-  }
-  TL_CTAK(0, 4);
-  if (pc.world > 1) {  // the last CTA to finish sums t over ranks (fused NVLink exchange)
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence();
-      last_cta = (atomicAdd(counter, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (last_cta) {
-      peer_allreduce_block(pc, t, h);
-      if (tid == 0) *counter = 0;
-    }
-  }
-  TL_EXIT(128 + (wf.W ? wf.jn : 127));
-}
-
 // ---- F = A_s^T w - s V[:,j]  and  c = V[:, :nd]^T F  (irlb.py:182-190, first half of orthog) ----
 __global__ void __launch_bounds__(RT_THREADS, 1) v_prep_dots(const double* __restrict__ t, const double* __restrict__ mu,
                                                    const double* __restrict__ rs, const double* __restrict__ sc,
@@ -891,232 +659,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) update_norm(const double* __res
 // dependents only AFTER its own grid-dependency wait, so "two kernels back" has completed).  The first row's
 // whole load chain therefore overlaps the tail of v_step.  W is read with ld.global.cg: no line of it may sit
 // in L1 across the dependency.
-constexpr int WS_EPF = 4;  // entries per lane held in registers for the row in flight (128 per row)
-template <typename VT, int NQ>
-__device__ __forceinline__ void ws_load_row(bool ok, i64 r, int b, int e1, const int* __restrict__ cidx,
-                                            const VT* __restrict__ rval, const double* __restrict__ W, int ldw,
-                                            int jprev, int nd, int lane, int (&ci)[WS_EPF], VT (&va)[WS_EPF],
-                                            double (&wv)[NQ], double& wp) {
-#pragma unroll
-  for (int q = 0; q < WS_EPF; ++q) {
-    const int e = b + lane + 32 * q;
-    const bool in = ok && e < e1;
-    ci[q] = in ? __ldg(cidx + e) : 0;
-    va[q] = in ? __ldg(rval + e) : VT(0);
-  }
-  const double* wr = W + (size_t)(ok ? r : 0) * ldw;
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) wv[q] = (ok && lane + 32 * q < nd) ? __ldcg(wr + lane + 32 * q) : 0.0;
-  wp = (ok && jprev >= 0) ? __ldcg(wr + jprev) : 0.0;
-}
-// NQ = columns per lane: 3 (basis <= 94 wide + the two scalars) or 4; entry offsets are 32-bit (subset nnz < 2^31)
-template <typename VT, int NQ>
-__global__ void __launch_bounds__(RT_THREADS, 1)
-    w_step(const i64* __restrict__ rptr, const int* __restrict__ cidx, const VT* __restrict__ rval,
-           const double* __restrict__ xs, const double* __restrict__ sc, const double* __restrict__ W, int ldw, int jprev,
-           int nd, i64 n, const double* __restrict__ cvec, double* __restrict__ ybuf, double* __restrict__ partials,
-           double* __restrict__ gout, unsigned* __restrict__ counter, const PeerComm pc, const int* __restrict__ halt) {
-  const int lane = threadIdx.x & 31;
-  const i64 warps = ((i64)gridDim.x * blockDim.x) >> 5;
-  i64 r = (((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  TL_ENTRY_REG();
-  // ---- prologue (independent of the previous kernel) ----
-  int b = 0, e1 = 0, nb = 0, ne = 0;
-  if (r < n) {
-    b = (int)__ldg(rptr + r);
-    e1 = (int)__ldg(rptr + r + 1);
-  }
-  if (r + warps < n) {
-    nb = (int)__ldg(rptr + r + warps);
-    ne = (int)__ldg(rptr + r + warps + 1);
-  }
-  int ci[WS_EPF];
-  VT va[WS_EPF];
-  double wv[NQ], wp;
-  ws_load_row<VT, NQ>(r < n, r, b, e1, cidx, rval, W, ldw, jprev, nd, lane, ci, va, wv, wp);
-  pdl_sync();
-  if (halt && *halt) return;
-  TL_SYNC(nd);
-#ifdef ADOBO_B200_TIMELINE
-  if (threadIdx.x == 0 && blockIdx.x < 256) tl_cta[0][blockIdx.x] = tl_e0;
-#endif
-  TL_CTA(1);
-  const double mvs = sc[SC_MVS], fn = sc[SC_FN];
-  double creg[NQ], acc[4] = {0, 0, 0, 0};
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) creg[q] = (lane + 32 * q < nd) ? cvec[lane + 32 * q] : 0.0;
-  double n2 = 0, ax = 0;
-  for (; r < n; r += warps) {
-    const i64 rn = r + warps, rnn = rn + warps;
-    int nnb = 0, nne = 0;
-    if (rnn < n) {  // pointers two rows ahead
-      nnb = (int)__ldg(rptr + rnn);
-      nne = (int)__ldg(rptr + rnn + 1);
-    }
-    int ci2[WS_EPF];
-    VT va2[WS_EPF];
-    double wv2[NQ], wp2;
-    ws_load_row<VT, NQ>(rn < n, rn, nb, ne, cidx, rval, W, ldw, jprev, nd, lane, ci2, va2, wv2, wp2);  // next row in flight
-    double a = 0;
-#pragma unroll
-    for (int q = 0; q < WS_EPF; ++q)
-      if (b + lane + 32 * q < e1) a += (double)va[q] * xs[ci[q]];
-#pragma unroll 2
-    for (int e = b + 32 * WS_EPF + lane; e < e1; e += 32) a += (double)__ldg(rval + e) * xs[__ldg(cidx + e)];
-    double p = (wv[0] * creg[0] + wv[1] * creg[1]) + wv[2] * creg[2];
-    if (NQ == 4) p += wv[NQ - 1] * creg[NQ - 1];
-    a = warp_sum(a);
-    p = warp_sum(p);
-    double w = a - mvs;
-    if (jprev >= 0) w -= fn * wp;
-    w -= p;
-    if (lane == 0) ybuf[r] = w;
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) acc[q] += wv[q] * w;
-    n2 += w * w;
-    ax += w;
-    b = nb, e1 = ne, nb = nnb, ne = nne, wp = wp2;
-#pragma unroll
-    for (int q = 0; q < WS_EPF; ++q) ci[q] = ci2[q], va[q] = va2[q];
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) wv[q] = wv2[q];
-  }
-  TL_CTA(2);
-  // the two scalars ride in columns nd, nd + 1 of the vector (w is warp-uniform: one lane deposits them)
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int col = lane + 32 * q;
-    if (col == nd) acc[q] = n2;
-    if (col == nd + 1) acc[q] = ax;
-  }
-  reduce_vec_blocks(acc, nd + 2, partials, gout, counter, pc);
-  TL_CTA(7);
-  TL_EXIT(nd);
-}
-
-// ---- w_step2: the same pass, written for instruction count ------------------------------------------
-// ncu on w_step at 20 k cells: neither L2 (7 % of peak) nor memory latency bounds it but ISSUE -- 520 SASS
-// instructions per row (64-bit index arithmetic and predicate logic for every strided row, register rotation,
-// two 64-bit warp reductions), 2.5 IPC per SM for 9 us.  Here a warp owns a CONTIGUOUS block of rows, so row
-// pointers chain (one load per row), W advances by pointer bumps, indices are 32-bit, the two warp sums are one
-// (sum over lanes of a_lane - p_lane), and the two-deep pipeline is unrolled over two register sets instead of
-// rotated.  512-thread CTAs (128 registers per thread: nothing spills or is re-read from the constant bank).
-constexpr int W2_THREADS = 512, W2_EPF = 4;
-template <typename VT, int NQ>
-struct W2Row {
-  int ci[W2_EPF];
-  VT va[W2_EPF];
-  double wv[NQ], wp;
-  int b, len;
-};
-template <typename VT, int NQ>
-__device__ __forceinline__ void w2_load(W2Row<VT, NQ>& R, bool ok, int b, int e1, const int* __restrict__ cl,
-                                        const VT* __restrict__ vl, const double* __restrict__ wr, int jprev,
-                                        const bool (&cm)[NQ], int lane) {
-  R.b = b;
-  R.len = ok ? e1 - b : 0;
-#pragma unroll
-  for (int q = 0; q < W2_EPF; ++q) {
-    const bool in = lane + 32 * q < R.len;
-    R.ci[q] = in ? __ldg(cl + b + 32 * q) : 0;
-    R.va[q] = in ? __ldg(vl + b + 32 * q) : VT(0);
-  }
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) R.wv[q] = (ok && cm[q]) ? __ldcg(wr + 32 * q) : 0.0;
-  R.wp = (ok && jprev >= 0) ? __ldcg(wr - lane + jprev) : 0.0;
-}
-// (Two CTAs per SM at 64 registers for long shards was measured and rejected: 83 against 67 us per launch at
-// 160 k cells -- the row loop is bound by SM throughput, ~90 cycles per row, not by rows in flight.  The next step
-// for long shards is a half-warp per row: their subset rows hold ~50 entries, half of the 128 lane slots.)
-template <typename VT, int NQ>
-__global__ void __launch_bounds__(W2_THREADS, 1)
-    w_step2(const i64* __restrict__ rptr, const int* __restrict__ cidx, const VT* __restrict__ rval,
-            const double* __restrict__ xs, const double* __restrict__ sc, const double* __restrict__ W, int ldw, int jprev,
-            int nd, int n, const double* __restrict__ cvec, double* __restrict__ ybuf, double* __restrict__ partials,
-            double* __restrict__ gout, unsigned* __restrict__ counter, const PeerComm pc, const int* __restrict__ halt,
-            int h, int split) {
-  extern __shared__ __align__(16) double xsm[];  // [h]: the gathers x[cidx] as LDS (32 scattered 8-byte global loads
-                                                 // cost one L1 tag cycle each -- what bounded the row loop)
-  const int lane = threadIdx.x & 31;
-  const int nwarps = (int)((gridDim.x * blockDim.x) >> 5), wg = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  const int per = (n + nwarps - 1) / nwarps;
-  int r = min(n, wg * per);
-  const int rend = min(n, r + per);
-  TL_ENTRY_REG();
-  // ---- prologue (independent of the previous kernel): pointers of the first three rows, first row's loads ----
-  bool cm[NQ];
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) cm[q] = lane + 32 * q < nd;
-  const int* cl = cidx + lane;
-  const VT* vl = rval + lane;
-  const double* wr = W + (size_t)r * ldw + lane;
-  int p0 = 0, p1 = 0, p2 = 0;
-  if (r < rend) {
-    p0 = (int)__ldg(rptr + r);
-    p1 = (int)__ldg(rptr + r + 1);
-    p2 = (int)__ldg(rptr + min(r + 2, n));
-  }
-  W2Row<VT, NQ> RA, RB;
-  w2_load<VT, NQ>(RA, r < rend, p0, p1, cl, vl, wr, jprev, cm, lane);
-  pdl_sync();
-  if (halt && *halt) return;
-  TL_SYNC(nd);
-#ifdef ADOBO_B200_TIMELINE
-  if (threadIdx.x == 0 && blockIdx.x < 256) tl_cta[0][blockIdx.x] = tl_e0;
-#endif
-  TL_CTA(1);
-  for (int i = threadIdx.x; i < h; i += W2_THREADS) xsm[i] = xs[i];
-  const double mvs = sc[SC_MVS], fn = (jprev >= 0) ? sc[SC_FN] : 0.0;
-  double creg[NQ], acc[4] = {0, 0, 0, 0};
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) creg[q] = cm[q] ? cvec[lane + 32 * q] : 0.0;
-  double n2 = 0, ax = 0;
-  __syncthreads();
-  // one row: issue the loads of the next row (into NX), then reduce the current one (CU)
-  auto step = [&](W2Row<VT, NQ>& CU, W2Row<VT, NQ>& NX) {
-    const int p3 = (r + 2 < rend) ? (int)__ldg(rptr + r + 3) : 0;  // pointer three rows ahead closes row r + 2
-    wr += ldw;
-    w2_load<VT, NQ>(NX, r + 1 < rend, p1, p2, cl, vl, wr, jprev, cm, lane);
-    double a = 0;
-#pragma unroll
-    for (int q = 0; q < W2_EPF; ++q)
-      if (lane + 32 * q < CU.len) a += (double)CU.va[q] * xsm[CU.ci[q]];
-    for (int e = 32 * W2_EPF + lane; e < CU.len; e += 32) a += (double)__ldg(vl + CU.b + e - lane) * xsm[__ldg(cl + CU.b + e - lane)];
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) a -= CU.wv[q] * creg[q];
-    a = warp_sum(a);
-    const double w = (a - mvs) - fn * CU.wp;
-    if (lane == 0) ybuf[r] = w;
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) acc[q] += CU.wv[q] * w;
-    n2 += w * w;
-    ax += w;
-    p1 = p2;
-    p2 = p3;
-    ++r;
-  };
-  while (r < rend) {
-    step(RA, RB);
-    if (r >= rend) break;
-    step(RB, RA);
-  }
-  TL_CTA(2);
-  // the two scalars ride in columns nd, nd + 1 of the vector (w is warp-uniform: one lane deposits them)
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int col = lane + 32 * q;
-    if (col == nd) acc[q] = n2;
-    if (col == nd + 1) acc[q] = ax;
-  }
-  if (split) {
-    deposit_lane32(acc);
-    reduce_vec_partials(nd + 2, partials);
-  } else {
-    reduce_vec_blocks(acc, nd + 2, partials, gout, counter, pc);
-  }
-  TL_CTA(7);
-  TL_EXIT(nd);
-}
+constexpr int W2_THREADS = 512;  // CTA of the one-pass W-side kernels
 
 // ---- w_step3: w_step2 with a HALF-WARP per row --------------------------------------------------------
 // A subset row holds 50-90 entries and 70-96 basis columns: a full warp per row leaves a third of its entry
@@ -1785,6 +1328,8 @@ __global__ void w_finish(const double* __restrict__ ybuf, const double* __restri
   TL_ENTRY(387);
   TL_EXIT(387);
 }
+
+#include "irlb_step.cuh"
 
 // ---- one-sided Jacobi SVD of B (m x m, row-major, m <= 128) in one CTA ---------------------------
 // G = B, column-major in shared memory (column stride LD = 16 R rows, zero padded; an extra zero
@@ -2462,18 +2007,86 @@ static cudaError_t launch_k(void (*kern)(KA...), dim3 grid, dim3 block, size_t s
   return cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);
 }
 
+#ifdef ADOBO_B200_TIMELINE
+// diagnostic build: the timeline of the last replay of the iteration graph (CTA 0's stamps per kernel and column)
+static void dump_timeline() {
+  static unsigned long long tl[6][1024];
+  cudaMemcpyFromSymbol(tl, tl_buf, sizeof(tl));
+  struct Ev { unsigned long long t0, t1, t2; char name[24]; };
+  std::vector<Ev> evs;
+  auto add = [&](int slot, const char* nm, int j) {
+    if (!tl[0][slot]) return;
+    Ev e{tl[0][slot], tl[1][slot], tl[2][slot], {}};
+    snprintf(e.name, sizeof(e.name), "%s[%d]", nm, j);
+    evs.push_back(e);
+  };
+  for (int j = 0; j < 128; ++j) add(j, "w_step", j), add(128 + j, "spmvT", j), add(256 + j, "v_step", j);
+  add(384, "rotate", 0), add(385, "set_restart", 0), add(386, "conv_check", 0), add(387, "w_finish", 0);
+  std::sort(evs.begin(), evs.end(), [](const Ev& a, const Ev& b) { return a.t0 < b.t0; });
+  const size_t from = evs.size() > 24 ? evs.size() - 24 : 0;
+  const unsigned long long base = evs.empty() ? 0 : evs[from].t0;
+  fprintf(stderr, "timeline of the last kernels (us from the first, %%globaltimer)\n");
+  for (size_t q = from; q < evs.size(); ++q)
+    fprintf(stderr, "%-16s entry %8.2f sync %8.2f exit %8.2f\n", evs[q].name, (evs[q].t0 - base) * 1e-3,
+            evs[q].t1 ? (evs[q].t1 - base) * 1e-3 : -1.0, (evs[q].t2 - base) * 1e-3);
+}
+#endif
+
+// Test / diagnosis hooks of the driver: ONE environment variable, ADOBO_B200_IRLB="hook,hook,...".  Every hook
+// selects a fallback that exists for a reason (a size the fast path does not cover, or the synchronous form of an
+// asynchronous mechanism); tests/test_gpu_parity.py::test_irlb_alternative_paths runs each of them.
+enum : unsigned {
+  HK_SVD_JACOBI = 1u << 0,       // generic Jacobi SVD of B for every restart (default: first iteration + fallback)
+  HK_SVD_FALLBACK = 1u << 1,     // exercise the fallback that runs when svd_arrow rejects its own result
+  HK_NO_GRAPH = 1u << 2,         // launch kernel by kernel instead of replaying CUDA graphs
+  HK_NO_FORK = 1u << 3,          // SVD of B in the main stream instead of beside the last step
+  HK_ROTATE_STREAMED = 1u << 4,  // rotate_basis (long shards) whatever the shard length
+  HK_NO_FUSEDT = 1u << 5,        // three-kernel step (w_step3 + spmvT_csc + v_step*): the path for h > 1024
+  HK_NO_VONE = 1u << 6,          // v_step instead of v_step_one: the path for 1024 < h <= 8192
+  HK_NO_ZPATH = 1u << 7,         // two-pass Gram-Schmidt kernels: the path for h > 8192 or m_b > 126
+  HK_NO_VSTEP = 1u << 8,         // grid-wide V-side kernels: the path for h > 8192
+  HK_NO_WFOLD = 1u << 9,         // separate w_finish launch for every column
+  HK_NO_SPLIT = 1u << 10,        // last-CTA reduction of w_step3's vector (what several GPUs use on that path)
+  HK_NO_PDL = 1u << 11,          // no programmatic dependent launch
+  HK_NO_RUNAHEAD = 1u << 12,     // wait for every convergence read-back
+  HK_TRACE = 1u << 13,           // one line per outer iteration on stderr
+};
+static unsigned irlb_hooks() {
+  static const struct { const char* name; unsigned bit; } names[] = {
+      {"svd_jacobi", HK_SVD_JACOBI}, {"svd_fallback", HK_SVD_FALLBACK}, {"no_graph", HK_NO_GRAPH},
+      {"no_fork", HK_NO_FORK}, {"rotate_streamed", HK_ROTATE_STREAMED}, {"no_fusedt", HK_NO_FUSEDT},
+      {"no_vone", HK_NO_VONE}, {"no_zpath", HK_NO_ZPATH}, {"no_vstep", HK_NO_VSTEP}, {"no_wfold", HK_NO_WFOLD},
+      {"no_split", HK_NO_SPLIT}, {"no_pdl", HK_NO_PDL}, {"no_runahead", HK_NO_RUNAHEAD}, {"trace", HK_TRACE}};
+  const char* e = getenv("ADOBO_B200_IRLB");
+  unsigned bits = 0;
+  if (!e) return 0;
+  std::string s(e);
+  size_t pos = 0;
+  while (pos <= s.size()) {
+    size_t end = s.find(',', pos);
+    if (end == std::string::npos) end = s.size();
+    const std::string tok = s.substr(pos, end - pos);
+    bool known = tok.empty();
+    for (auto& nm : names)
+      if (tok == nm.name) bits |= nm.bit, known = true;
+    REQUIRE(known, ADOBO_ERR_ARG, "ADOBO_B200_IRLB: unknown hook '%s'", tok.c_str());
+    pos = end + 1;
+  }
+  return bits;
+}
+
 // Workspace of the Lanczos driver.  It lives in the context across calls so that (a) repeated PCA
 // calls on same-shaped data do not re-allocate and (b) the CUDA graphs of one outer iteration --
-// keyed by (first iteration?, k) -- stay valid and are replayed: one graph launch and one 16-byte
-// read-back per restart instead of ~150 kernel launches.
+// keyed by (first iteration?, k) -- stay valid and are replayed: one graph launch and one 32-byte
+// read-back per restart instead of ~70 kernel launches.
 struct IrlbWs {
   const void* sig_ptr[8] = {};
   i64 sig_n = -1;
   int sig_i[6] = {};
   double sig_tol = 0;
-  DevBuf<double> V, W, B, sc, tbuf, ybuf_h, ybuf_n, fbuf, xs, wcur, cvec, partials, Su, Sv, svd_s, R, murs, St, Z, sumW, gout, crot;
-  DevBuf<unsigned> counter, mgflag;
-  DevBuf<int> info, perm;
+  DevBuf<double> V, W, B, sc, tbuf, ybuf_h, ybuf_n, fbuf, xs, wcur, cvec, partials, tpart, Su, Sv, svd_s, R, murs, St, Z, sumW, gout, crot;
+  DevBuf<unsigned> counter;
+  DevBuf<int> info;
   std::map<int, cudaGraphExec_t> graphs;
   std::map<int, i64> graph_launches;
   cudaEvent_t ev[4] = {};  // completion of the outer iterations in flight (run-ahead)
@@ -2503,9 +2116,12 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   REQUIRE(m_b <= MAXB, ADOBO_ERR_LIMIT, "lanczos: working dimension %d exceeds %d (ncomp too large)", m_b, MAXB);
   REQUIRE(nu <= m_b, ADOBO_ERR_ARG, "lanczos: nval %d exceeds the working dimension %d", nu, m_b);
   REQUIRE(m_b >= 4, ADOBO_ERR_ARG, "lanczos: working dimension %d too small (need >= 4 columns)", m_b);
+  REQUIRE(n < (i64(1) << 31) && A.nnz < (i64(1) << 31), ADOBO_ERR_LIMIT, "lanczos: shard too large for 32-bit offsets");
   const int ld = (m_b + 15) & ~15;
   const bool centered = (mu != nullptr);
   cudaStream_t st = c->stream;
+  const unsigned hooks = irlb_hooks();
+  auto hook = [&](unsigned bit) { return (hooks & bit) != 0; };
 
   if (!c->irlb_ws) {
     c->irlb_ws = new IrlbWs();
@@ -2514,14 +2130,8 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   IrlbWs& ws = *(IrlbWs*)c->irlb_ws;
   {
     const void* sp[8] = {A.rptr.p, A.cidx.p, A.rval.p, A.cptr.p, A.ridx.p, A.cval.p, mu, rs};
-    // test hooks read from the environment change what a captured iteration contains
-    const int hooks = (getenv("ADOBO_B200_SVD_JACOBI") ? 1 : 0) | (getenv("ADOBO_B200_NO_FORK") ? 2 : 0) |
-                      (getenv("ADOBO_B200_ROTATE_STREAMED") ? 4 : 0) | (getenv("ADOBO_B200_NO_VSTEP") ? 8 : 0) | (getenv("ADOBO_B200_NO_WFOLD") ? 1024 : 0) | (getenv("ADOBO_B200_NO_ZPATH") ? 2048 : 0) | (getenv("ADOBO_B200_NO_PDL") ? 4096 : 0) |
-                      (getenv("ADOBO_B200_NO_RUNAHEAD") ? 8192 : 0) | (getenv("ADOBO_B200_NO_VONE") ? 16384 : 0) | (getenv("ADOBO_B200_WSTEP_V1") ? (1 << 18) : 0) | (getenv("ADOBO_B200_MGSPLIT") ? (1 << 23) : 0) | (getenv("ADOBO_B200_WSTEP2") ? (1 << 17) : 0) | (getenv("ADOBO_B200_ROTSPLIT") ? (1 << 20) : 0) |
-                      (getenv("ADOBO_B200_STSM") ? (1 << 21) : 0) | (getenv("ADOBO_B200_NO_SPLIT") ? (1 << 19) : 0) |
-                      (getenv("ADOBO_B200_IRLB_TRACE") ? 32768 : 0) | (getenv("ADOBO_B200_SVD_FORCE_FALLBACK") ? 65536 : 0) |
-                      (svd_arrow_cluster() << 4);
-    const int si[6] = {h, nu, m_b, c->world, (int)sizeof(VT), hooks};
+    // hooks change what a captured iteration contains
+    const int si[6] = {h, nu, m_b, c->world, (int)sizeof(VT), (int)(hooks | ((unsigned)svd_arrow_cluster() << 20))};
     bool same = ws.sig_n == n && ws.sig_tol == tol;
     for (int q = 0; q < 8; ++q) same = same && ws.sig_ptr[q] == sp[q];
     for (int q = 0; q < 6; ++q) same = same && ws.sig_i[q] == si[q];
@@ -2535,12 +2145,31 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   }
   DevBuf<double>&V = ws.V, &W = ws.W, &B = ws.B, &sc = ws.sc, &tbuf = ws.tbuf, &ybuf_h = ws.ybuf_h, &ybuf_n = ws.ybuf_n,
   &fbuf = ws.fbuf, &xs = ws.xs, &wcur = ws.wcur, &cvec = ws.cvec, &partials = ws.partials, &Su = ws.Su, &Sv = ws.Sv,
-  &svd_s = ws.svd_s, &R = ws.R, &murs = ws.murs;
+  &svd_s = ws.svd_s, &R = ws.R, &murs = ws.murs, &Z = ws.Z, &sumW = ws.sumW, &gout = ws.gout, &tpart = ws.tpart;
   DevBuf<unsigned>& counter = ws.counter;
   DevBuf<int>& info = ws.info;
+
+  // ---- which step kernels ----
+  const bool pdl = !hook(HK_NO_PDL);  // programmatic dependent launch of the step kernels
+  const bool fused = c->world > 1 && c->peer.world == c->world;  // exchanges inside the kernels (peer mailboxes)
+  const bool fused_t = fused && h <= PEER_SLOT;
+  // Z formulation of the W side (one pass over W, see w_step3): needs the cluster V kernel and two spare columns
+  const bool use_vstep = h <= 8192 && !hook(HK_NO_VSTEP);
+  const bool zpath = use_vstep && m_b + 2 <= MAXB && !hook(HK_NO_ZPATH);
+  // one batch of rows per warp and the CTA's rows of Z staged in shared memory: v_step_one / v_step_t
+  const int vs_per = (h + VS_CLUSTER - 1) / VS_CLUSTER;
+  const size_t vs_one_smem = sizeof(double) * ((size_t)(VS_WARPS + 8) * MAXB + (zpath ? (size_t)vs_per * ld : 0));
+  const bool vs_one = use_vstep && vs_per <= VS_WARPS * VS_ROWS && vs_one_smem <= 200 * 1024 && !hook(HK_NO_VONE);
+  // the two-kernel step (irlb_step.cuh): every BASELINE configuration (h = 1000) on one or several GPUs
+  const int hp = (h + 15) & ~15;
+  const bool fusedt = zpath && vs_one && h <= WT_HMAX && (c->world == 1 || fused) && !hook(HK_NO_FUSEDT);
+  // three-kernel step: split reduction of w_step3's vector (single GPU: the consuming spmvT_csc sums the partials)
+  const bool fold_wt_ok = !hook(HK_NO_WFOLD);
+  const bool split = !fusedt && c->world == 1 && zpath && vs_one && fold_wt_ok && !hook(HK_NO_SPLIT);
+  const bool wide_rows = n >= 65536;  // two-pass kernels: enough rows per resident warp to prefer throughput
   {
     // a re-allocation moves a buffer: graphs that captured the old pointer must go
-    const double* before[4] = {V.p, W.p, partials.p, murs.p};
+    const double* before[6] = {V.p, W.p, partials.p, murs.p, Z.p, tpart.p};
     V.ensure((size_t)h * ld);
     W.ensure((size_t)std::max<i64>(n, 1) * ld);
     B.ensure((size_t)MAXB * MAXB);
@@ -2560,12 +2189,20 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     counter.ensure(2);
     info.ensure(8);
     murs.ensure((size_t)h);
-    const double* after[4] = {V.p, W.p, partials.p, murs.p};
-    for (int q = 0; q < 4; ++q)
+    ws.St.ensure((size_t)2 * MAXB * MAXB);
+    ws.crot.ensure((size_t)2 * MAXB);
+    if (zpath) {
+      Z.ensure((size_t)h * ld);
+      sumW.ensure(MAXB);
+      gout.ensure(MAXB);
+    }
+    if (fusedt) tpart.ensure((size_t)c->sm_count * hp);
+    const double* after[6] = {V.p, W.p, partials.p, murs.p, Z.p, tpart.p};
+    for (int q = 0; q < 6; ++q)
       if (before[q] != after[q]) ws.clear_graphs();
   }
+  DevBuf<double>& St = ws.St;
   const unsigned gb_n = red_blocks(c, n), gb_h = red_blocks(c, h);
-  const bool wide_rows = n >= 65536;  // enough rows per resident warp to prefer throughput over latency
   // spmv_dots (wide): 512-thread CTAs, two per SM, four rows per warp
   const unsigned gb_sd = (unsigned)std::max<i64>(1, std::min<i64>((n + 63) / 64, 2 * (i64)c->sm_count));
   CUDA_CHECK(cudaMemsetAsync(V.p, 0, sizeof(double) * (size_t)h * ld, st));
@@ -2575,6 +2212,11 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   CUDA_CHECK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned) * 2, st));
   CUDA_CHECK(cudaMemsetAsync(cvec.p, 0, sizeof(double) * MAXB, st));
   CUDA_CHECK(cudaMemsetAsync(info.p, 0, sizeof(int) * 8, st));
+  if (zpath) {
+    CUDA_CHECK(cudaMemsetAsync(Z.p, 0, sizeof(double) * (size_t)h * ld, st));
+    CUDA_CHECK(cudaMemsetAsync(sumW.p, 0, sizeof(double) * MAXB, st));
+    CUDA_CHECK(cudaMemsetAsync(gout.p, 0, sizeof(double) * MAXB, st));
+  }
   if (centered) LAUNCH(c, "mul_vec", (mul_vec<<<(h + 255) / 256, 256, 0, st>>>(mu, rs, murs.p, h)));
   // SVD kernel resources
   const size_t svd_smem = sizeof(double) * ((size_t)(m_b + 1) * JL * jacobi_rows_per_lane(m_b) + 260);
@@ -2585,53 +2227,29 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   const int rot_nbuf = (rot_s + 2 * rot_q <= 225 * 1024) ? 2 : 1;
   const size_t rot_smem = rot_s + rot_nbuf * rot_q;
   CUDA_CHECK(cudaFuncSetAttribute(rotate_basis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rot_smem));
-  ws.St.ensure((size_t)2 * MAXB * MAXB);
-  ws.crot.ensure((size_t)2 * MAXB);
-  DevBuf<double>& St = ws.St;
-  // V[:, :kc] (or outv) = V Sv[:, :kc]  and  W[:, :kc] (or outw) = W Su[:, :kc], one launch each for the
-  // transposes and for the two tall-skinny GEMMs
-  const bool rot_streamed = getenv("ADOBO_B200_ROTATE_STREAMED") != nullptr;  // test hook: force rotate_basis
-  const bool rot_split = getenv("ADOBO_B200_ROTSPLIT") != nullptr;  // opt-in: measured slower (36.6 against 31.4 us per restart)
-  // Z formulation of the W side (w_step): needs the cluster V kernel and two spare columns in the reduced vector
-  const bool zpath = h <= 8192 && m_b + 2 <= MAXB && getenv("ADOBO_B200_NO_VSTEP") == nullptr &&
-                     getenv("ADOBO_B200_NO_ZPATH") == nullptr;
-  if (zpath) {
-    const double* before[1] = {ws.Z.p};
-    ws.Z.ensure((size_t)h * ld);
-    ws.sumW.ensure(MAXB);
-    ws.gout.ensure(MAXB);
-    if (before[0] != ws.Z.p) ws.clear_graphs();
-    CUDA_CHECK(cudaMemsetAsync(ws.Z.p, 0, sizeof(double) * (size_t)h * ld, st));
-    CUDA_CHECK(cudaMemsetAsync(ws.sumW.p, 0, sizeof(double) * MAXB, st));
-    CUDA_CHECK(cudaMemsetAsync(ws.gout.p, 0, sizeof(double) * MAXB, st));
-  }
-  DevBuf<double>&Z = ws.Z, &sumW = ws.sumW, &gout = ws.gout;
-  const bool pdl = getenv("ADOBO_B200_NO_PDL") == nullptr;  // programmatic dependent launch of the step kernels
-  const bool use_vstep = h <= 8192 && getenv("ADOBO_B200_NO_VSTEP") == nullptr;
-  // one batch of rows per warp and the CTA's rows of Z staged in shared memory: v_step_one
-  const int vs_per = (h + VS_CLUSTER - 1) / VS_CLUSTER;
-  const size_t vs_one_smem = sizeof(double) * ((size_t)(VS_WARPS + 8) * MAXB + (zpath ? (size_t)vs_per * ld : 0));
-  const bool vs_one = use_vstep && vs_per <= VS_WARPS * VS_ROWS && vs_one_smem <= 200 * 1024 &&
-                      getenv("ADOBO_B200_NO_VONE") == nullptr;
-  const bool wstep2 = n < (i64(1) << 31) && getenv("ADOBO_B200_WSTEP_V1") == nullptr;
-  // split reduction of w_step's vector (see reduce_vec_partials): single GPU, lean kernels on both sides
-  const bool split = c->world == 1 && zpath && vs_one && wstep2 && getenv("ADOBO_B200_NO_SPLIT") == nullptr &&
-                     getenv("ADOBO_B200_NO_WFOLD") == nullptr;  // the consuming spmvT_csc sums g: needs the folded finish
-  // the same with several GPUs (spmvT_csc_mg): opt-in until it has been run on hardware
-  const bool mgsplit = c->world > 1 && c->peer.world == c->world && h <= PEER_SLOT && zpath && vs_one && wstep2 &&
-                       getenv("ADOBO_B200_NO_WFOLD") == nullptr && getenv("ADOBO_B200_MGSPLIT") != nullptr;
-  if (mgsplit) {
-    ws.mgflag.ensure(1);
-    CUDA_CHECK(cudaMemsetAsync(ws.mgflag.p, 0, sizeof(unsigned), st));
-  }
-  const bool wstep3 = getenv("ADOBO_B200_WSTEP2") == nullptr;  // half-warp per row; w_step2 kept as a test hook
-  auto w2_fn = wstep3 ? (m_b + 1 <= 96 ? w_step3<VT, 6> : w_step3<VT, 8>) : (m_b + 1 <= 96 ? w_step2<VT, 3> : w_step2<VT, 4>);
-  if (wstep2) CUDA_CHECK(cudaFuncSetAttribute(w2_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * h)));
-  // under programmatic launch w_step2's CTAs start while v_step still holds VS_CLUSTER SMs: a CTA that had to wait
-  // for one of those runs its whole prologue after everybody else's -- leave them out of the grid
+  // W-side kernels of the one-pass formulations; under programmatic launch their CTAs start while the V-side
+  // cluster still holds VS_CLUSTER SMs: a CTA that had to wait for one of those would run its whole prologue after
+  // everybody else's -- leave them out of the grid
+  auto w3_fn = m_b + 1 <= 96 ? w_step3<VT, 6> : w_step3<VT, 8>;
+  auto wt_fn = m_b + 1 <= 96 ? w_step_t<VT, 6> : w_step_t<VT, 8>;
+  const size_t wt_smem = sizeof(double) * (size_t)(1 + WT_WARPS) * hp;
+  if (zpath && !fusedt) CUDA_CHECK(cudaFuncSetAttribute(w3_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * h)));
+  if (fusedt) CUDA_CHECK(cudaFuncSetAttribute(wt_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wt_smem));
   const i64 w2_sms = (pdl && use_vstep && c->sm_count > 4 * VS_CLUSTER) ? c->sm_count - VS_CLUSTER : c->sm_count;
   const unsigned gb_w2 = (unsigned)std::max<i64>(1, std::min<i64>(w2_sms, (n + W2_THREADS / 32 - 1) / (W2_THREADS / 32)));
-  const int* hp = nullptr;  // halt flag handed to the kernels of an outer iteration (run-ahead), else none
+  if (use_vstep) {  // static + dynamic shared memory of the cluster kernels exceeds the 48 KB default
+    CUDA_CHECK(cudaFuncSetAttribute(v_step<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (VS_WARPS + 8) * MAXB)));
+    CUDA_CHECK(cudaFuncSetAttribute(v_step<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (VS_WARPS + 8) * MAXB)));
+    if (vs_one) {
+      CUDA_CHECK(cudaFuncSetAttribute(v_step_one<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vs_one_smem));
+      CUDA_CHECK(cudaFuncSetAttribute(v_step_one<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vs_one_smem));
+      CUDA_CHECK(cudaFuncSetAttribute(v_step_t<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vs_one_smem));
+      CUDA_CHECK(cudaFuncSetAttribute(v_step_t<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vs_one_smem));
+    }
+  }
+  const int* hp_halt = nullptr;  // halt flag handed to the kernels of an outer iteration (run-ahead), else none
+  // V[:, :kc] (or outv) = V Sv[:, :kc]  and  W[:, :kc] (or outw) = W Su[:, :kc]: one launch for the tall-skinny GEMMs
+  // (and Z = A^T W, which follows W at a restart)
   auto rotate2 = [&](int kc, double* outv, double* outw, int ldo, const double* scale_w, bool st_ready) {
     const int kcp = (kc + 7) & ~7;
     if (!st_ready)  // restarts: conv_check has laid the two matrices out already
@@ -2653,42 +2271,35 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     const i64 per = std::max<i64>(((i64)h + bv - 1) / bv, (n + bw - 1) / bw);  // rows per CTA
     const size_t s_bytes = sizeof(double) * (size_t)m_b * kcp;
     const int r_fit = (int)std::min<i64>(5, (((i64)(225 * 1024 - s_bytes) / (8 * m_b)) - 1) / 32);
-    if (!rot_streamed && r_fit >= 1 && per <= 2 * 32 * r_fit) {
+    if (!hook(HK_ROTATE_STREAMED) && r_fit >= 1 && per <= 2 * 32 * r_fit) {
       const i64 ntile = (per + 32 * r_fit - 1) / (32 * r_fit);
       const int Rr = (int)std::min<i64>(r_fit, ((per + ntile - 1) / ntile + 31) / 32);
-      // two row groups of warps (768 threads) when the column groups leave room for them and the wider tile fits
-      const int R2 = std::max(2, (Rr + 1) / 2);
-      const size_t smem2 = s_bytes + sizeof(double) * (size_t)m_b * (64 * R2 + 1);
-      const bool split_rows = rot_split && Rr >= 3 && kcp / 8 <= 12 && smem2 <= 225 * 1024;
-      const size_t smem = split_rows ? smem2 : s_bytes + sizeof(double) * (size_t)m_b * (32 * Rr + 1);
-      rotate_rows_fn fn = split_rows ? rotate_rows_for(R2, 2) : rotate_rows_for(Rr);
+      const size_t smem = s_bytes + sizeof(double) * (size_t)m_b * (32 * Rr + 1);
+      rotate_rows_fn fn = rotate_rows_for(Rr);
       CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      LAUNCH(c, "rotate_basis", (fn<<<nbv + nbz + nbw, 32 * (kcp / 8) * (split_rows ? 2 : 1), smem, st>>>(jv, jz, jw, (int)nbv, (int)nbz, ld,
-                                                                                                   m_b, kc, hp)));
+      LAUNCH(c, "rotate_basis", (fn<<<nbv + nbz + nbw, 32 * (kcp / 8), smem, st>>>(jv, jz, jw, (int)nbv, (int)nbz, ld, m_b, kc, hp_halt)));
     } else {
       LAUNCH(c, "rotate_basis", (rotate_basis<<<nbv + nbz + nbw, 32 * (kcp / 8), rot_smem, st>>>(jv, jz, jw, (int)nbv, (int)nbz,
-                                                                                           ld, m_b, kc, rot_nbuf, hp)));
+                                                                                           ld, m_b, kc, rot_nbuf, hp_halt)));
     }
   };
-  const bool use_arrow = getenv("ADOBO_B200_SVD_JACOBI") == nullptr;
-  const bool force_fallback = getenv("ADOBO_B200_SVD_FORCE_FALLBACK") != nullptr;  // test hook
+  const bool use_arrow = !hook(HK_SVD_JACOBI);
+  const bool force_fallback = hook(HK_SVD_FALLBACK);
   if (use_arrow) svd_arrow_prepare(m_b);
   const unsigned fin_h = (unsigned)((h + 255) / 256), fin_n = (unsigned)std::max<i64>(1, (n + 255) / 256);
   int* h_info = (int*)c->pinned;
 
   // ---- start vector (irlb.py:151-153): V[:,0] = v0 / ||v0|| ----
   CUDA_CHECK(cudaMemcpyAsync(ybuf_h.p, v0_host, sizeof(double) * h, cudaMemcpyHostToDevice, st));
-  // fused NVLink all-reduce inside the reducing kernels (peer mailboxes); NCCL when it is unavailable
-  const bool fused = c->world > 1 && c->peer.world == c->world;
-  const PeerComm pcw = fused ? c->peer : PeerComm();
+  PeerComm pcw = fused ? c->peer : PeerComm();
+  pcw.err = info.p + 6;
   const PeerComm pc1;  // replicated (V-side) reductions
-  const bool fused_t = fused && h <= PEER_SLOT;
   // the finish step (normalise + store) runs in the last CTA of the norm reduction when one CTA can do it
   // in about a launch latency; larger vectors keep the separate grid-wide kernels
   const bool fold_v = h <= 16384, fold_w = !wide_rows && n <= 8192 && !(c->world > 1 && !fused);
   // otherwise the W finish rides in the spmvT_csc that consumes the column -- except for the last column, whose
   // norm completes B for the SVD that is forked off before that spmvT_csc
-  const bool fold_wt = (zpath || !fold_w) && getenv("ADOBO_B200_NO_WFOLD") == nullptr;
+  const bool fold_wt = (zpath || !fold_w) && fold_wt_ok;
   auto v_fin = [&](int jn, int j) {
     Finish f;
     if (!fold_v) return f;
@@ -2709,27 +2320,25 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     LAUNCH(c, "v_finish", (v_finish<<<fin_h, 256, 0, st>>>(ybuf_h.p, rs, sc.p, V.p, ld, 0, m_b, h, fbuf.p, xs.p, B.p, -1,
                                                          centered ? 1 : 0)));
 
+  // algorithmic bytes of the step kernels: one pass over the subset CSR and over W[:, :nd]
+  auto w_bytes = [&](int nd, int jprev) {
+    return (double)A.nnz * (4.0 + sizeof(VT)) + 8.0 * (n + 1) + 8.0 * n * (nd + (jprev >= 0 ? 1 : 0) + 1) + 8.0 * h;
+  };
+  // ---- W side of a step on the three-kernel / two-pass paths ----
   auto w_column = [&](int jprev, int nd, int jn) {
     // W[:, jn] = normalise( orthog( A_s x - fn W[:, jprev], W[:, :nd] ) )
+    WORK(c, w_bytes(nd, jprev));
     if (zpath) {  // one pass: the coefficients were left in cvec by v_step (set_restart after a restart)
-      WORK(c, (double)A.nnz * (4.0 + sizeof(VT)) + 8.0 * (n + 1) + 8.0 * n * (nd + (jprev >= 0 ? 1 : 0) + 1) + 8.0 * h);
       // programmatic launch behind v_step; the first column after a restart follows ordinary kernels
-      if (wstep2)
-        LAUNCH(c, "w_step", CUDA_CHECK(launch_k(w2_fn, dim3(gb_w2), dim3(W2_THREADS),
-                                                sizeof(double) * h, st, pdl && jprev >= 0, 1, A.rptr.p, A.cidx.p, A.rval.p, xs.p,
-                                                sc.p, W.p, ld, jprev, nd, (int)n, cvec.p, ybuf_n.p, partials.p, gout.p, counter.p,
-                                                pcw, hp, h, (split || (mgsplit && jn != m_b - 1)) ? 1 : 0)));
-      else
-        LAUNCH(c, "w_step", CUDA_CHECK(launch_k(m_b + 1 <= 96 ? w_step<VT, 3> : w_step<VT, 4>, dim3(gb_n), dim3(RT_THREADS), 0, st,
-                                                pdl && jprev >= 0, 1, A.rptr.p, A.cidx.p, A.rval.p, xs.p, sc.p, W.p, ld, jprev, nd, n,
-                                                cvec.p, ybuf_n.p, partials.p, gout.p, counter.p, pcw, hp)));
-      if (!fused) allreduce_sum_f64(c, gout.p, (size_t)nd + 2);
+      LAUNCH(c, "w_step", CUDA_CHECK(launch_k(w3_fn, dim3(gb_w2), dim3(W2_THREADS), sizeof(double) * h, st, pdl && jprev >= 0, 1,
+                                              A.rptr.p, A.cidx.p, A.rval.p, xs.p, sc.p, W.p, ld, jprev, nd, (int)n, cvec.p,
+                                              ybuf_n.p, partials.p, gout.p, counter.p, pcw, hp_halt, h, split ? 1 : 0)));
+      if (c->world > 1 && !fused) allreduce_sum_f64(c, gout.p, (size_t)nd + 2);
       if (!(fold_wt && jn != m_b - 1))
-        LAUNCH(c, "w_finish", (w_finish<<<fin_n, 256, 0, st>>>(ybuf_n.p, gout.p + nd, sc.p, W.p, ld, jn, n, wcur.p, B.p, m_b, hp,
+        LAUNCH(c, "w_finish", (w_finish<<<fin_n, 256, 0, st>>>(ybuf_n.p, gout.p + nd, sc.p, W.p, ld, jn, n, wcur.p, B.p, m_b, hp_halt,
                                                                split ? partials.p : nullptr, (int)gb_w2, gout.p)));
       return;
     }
-    WORK(c, (double)A.nnz * (4.0 + sizeof(VT)) + 8.0 * (n + 1) + 8.0 * n * (nd + (jprev >= 0 ? 1 : 0) + 1) + 8.0 * h);
     if (!wide_rows)
       LAUNCH(c, "spmv_dots", (spmv_dots_w32<VT><<<gb_n, RT_THREADS, 0, st>>>(A.rptr.p, A.cidx.p, A.rval.p, xs.p, sc.p, W.p, ld,
                                                                     jprev, nd, n, ybuf_n.p, partials.p, cvec.p,
@@ -2742,7 +2351,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
       LAUNCH(c, "spmv_dots", (spmv_dots<VT, 16><<<gb_sd, SD_THREADS, 0, st>>>(A.rptr.p, A.cidx.p, A.rval.p, xs.p, sc.p, W.p, ld,
                                                                      jprev, nd, n, ybuf_n.p, partials.p, cvec.p,
                                                                      counter.p, pcw)));
-    if (nd > 0 && !fused) allreduce_sum_f64(c, cvec.p, (size_t)nd);
+    if (nd > 0 && c->world > 1 && !fused) allreduce_sum_f64(c, cvec.p, (size_t)nd);
     WORK(c, 8.0 * n * (nd + 2));
     if (wide_rows)
       LAUNCH(c, "update_norm", (update_norm<<<gb_n, RT_THREADS, 0, st>>>(W.p, ld, nd, cvec.p, ybuf_n.p, nullptr, n, partials.p,
@@ -2751,9 +2360,10 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
       LAUNCH(c, "update_norm", (update_norm_w32<<<gb_n, RT_THREADS, 0, st>>>(W.p, ld, nd, cvec.p, ybuf_n.p, nullptr, n,
                                                                     partials.p, sc.p + SC_NRM2, counter.p, pcw,
                                                                     w_fin(jn))));
-    if (!fused) allreduce_sum_f64(c, sc.p + SC_NRM2, 2);
-    if ((wide_rows || !fold_w) && !(fold_wt && jn != m_b - 1)) LAUNCH(c, "w_finish", (w_finish<<<fin_n, 256, 0, st>>>(ybuf_n.p, sc.p + SC_NRM2, sc.p, W.p, ld, jn, n, wcur.p, B.p,
-                                                                                       m_b, nullptr, nullptr, 0, nullptr)));
+    if (c->world > 1 && !fused) allreduce_sum_f64(c, sc.p + SC_NRM2, 2);
+    if ((wide_rows || !fold_w) && !(fold_wt && jn != m_b - 1))
+      LAUNCH(c, "w_finish", (w_finish<<<fin_n, 256, 0, st>>>(ybuf_n.p, sc.p + SC_NRM2, sc.p, W.p, ld, jn, n, wcur.p, B.p, m_b, nullptr,
+                                                             nullptr, 0, nullptr)));
   };
   // restart update (irlb.py:238-246): Ritz vectors into the leading k columns, V[:,k] = F, new B
   auto restart_update = [&](int k) {
@@ -2761,97 +2371,72 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     LAUNCH(c, "set_restart", (set_restart<<<(std::max(h, m_b * m_b) + 255) / 256, 256, 0, st>>>(V.p, ld, h, fbuf.p, B.p,
                                                                                             m_b, k, svd_s.p, R.p,
                                                                                             zpath ? cvec.p : nullptr, sumW.p,
-                                                                                            ws.crot.p, hp)));
+                                                                                            ws.crot.p, hp_halt)));
   };
-  // one outer iteration (irlb.py:155-231) up to the convergence read-back
-  const bool use_graphs = !c->profiling && getenv("ADOBO_B200_NO_GRAPH") == nullptr;
+  const bool use_graphs = !c->profiling && !hook(HK_NO_GRAPH);
   // SVD of B (irlb.py:224): restarts have the diag + spike + bidiagonal-tail structure (svd_arrow), the first
   // iteration is a plain bidiagonal matrix (Jacobi).  B is complete once the last column of W is normalised,
-  // so under graph capture the single-CTA SVD is forked onto the side stream and overlaps the last F.
+  // so under graph capture the SVD is forked onto the side stream and overlaps the last V step.
   auto enqueue_svd = [&](bool first, int k, cudaStream_t s) {
     if (!first && use_arrow && svd_arrow_supported(m_b, k))
       launch_svd_arrow(c, B.p, m_b, k, Su.p, svd_s.p, Sv.p, info.p, s);
     else
       LAUNCH(c, "jacobi_svd", (jacobi<<<1, JTHREADS, svd_smem, s>>>(B.p, m_b, Su.p, svd_s.p, Sv.p, info.p)));
   };
-  const bool fork_svd = use_graphs && getenv("ADOBO_B200_NO_FORK") == nullptr;
+  const bool fork_svd = use_graphs && !hook(HK_NO_FORK);
+  auto fork_svd_here = [&](bool first, int k) {
+    CUDA_CHECK(cudaEventRecord(c->fork_ev, st));
+    CUDA_CHECK(cudaStreamWaitEvent(c->side, c->fork_ev, 0));
+    enqueue_svd(first, k, c->side);
+    CUDA_CHECK(cudaEventRecord(c->join_ev, c->side));
+  };
   constexpr int RUN_DEPTH = 3, CC_BLOCKS = 16;
-  const bool trace = getenv("ADOBO_B200_IRLB_TRACE") != nullptr;  // diagnostic: one line per outer iteration
+  const bool trace = hook(HK_TRACE);
   const bool runahead = use_graphs && zpath && (c->world == 1 || (fused && fused_t)) && !trace && !force_fallback &&
-                        getenv("ADOBO_B200_NO_RUNAHEAD") == nullptr;
-  // V side of a step as one cluster kernel (short V), or three grid-wide kernels (very long V)
-  if (use_vstep) {  // static + dynamic shared memory of v_step exceeds the 48 KB default
-    CUDA_CHECK(cudaFuncSetAttribute(v_step<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (VS_WARPS + 8) * MAXB)));
-    CUDA_CHECK(cudaFuncSetAttribute(v_step<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (VS_WARPS + 8) * MAXB)));
-    if (vs_one) {
-      CUDA_CHECK(cudaFuncSetAttribute(v_step_one<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vs_one_smem));
-      CUDA_CHECK(cudaFuncSetAttribute(v_step_one<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vs_one_smem));
-    }
-  }
-  // short shards: A^T u with u staged in shared memory, one CTA per SM
-  const size_t st_smem = sizeof(double) * (size_t)std::max<i64>(n, 2);
-  const int st_cpb = (h + c->sm_count - 1) / c->sm_count;  // columns per CTA
-  const bool st_sm = n >= 2 && n < (1 << 30) && st_smem <= 200 * 1024 && st_cpb <= STS_MAXC && A.nnz < (i64(1) << 31) &&
-                     getenv("ADOBO_B200_STSM") != nullptr;  // opt-in: measured equal to spmvT_csc in the replayed graph (12.9 us
-                                                            // against 11-13 us) and slower from a cold cache (35 against 20 us)
-  const unsigned st_grid = (unsigned)((h + st_cpb - 1) / st_cpb);
-  if (st_sm) {
-    // deal the columns to the CTAs by length: sorted descending, snake order, slot k of CTA b at perm[b + grid k]
-    std::vector<i64> hc((size_t)h + 1);
-    CUDA_CHECK(cudaMemcpyAsync(hc.data(), A.cptr.p, sizeof(i64) * (h + 1), cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    std::vector<int> order(h), permh((size_t)3 * st_grid * st_cpb, 0);
-    for (size_t q = 0; q < (size_t)st_grid * st_cpb; ++q) permh[3 * q] = -1;
-    for (int q = 0; q < h; ++q) order[q] = q;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return hc[a + 1] - hc[a] > hc[b + 1] - hc[b]; });
-    for (int q = 0; q < h; ++q) {
-      const int k = q / (int)st_grid, pos = q % (int)st_grid, col = order[q];
-      int* d = &permh[3 * ((size_t)k * st_grid + ((k & 1) ? (int)st_grid - 1 - pos : pos))];
-      d[0] = col, d[1] = (int)hc[col], d[2] = (int)(hc[col + 1] - hc[col]);
-    }
-    {
-      const int* before = ws.perm.p;
-      ws.perm.ensure(permh.size());
-      if (before != ws.perm.p) ws.clear_graphs();
-    }
-    CUDA_CHECK(cudaMemcpyAsync(ws.perm.p, permh.data(), sizeof(int) * permh.size(), cudaMemcpyHostToDevice, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));  // permh goes out of scope
-  }
-  if (st_sm) CUDA_CHECK(cudaFuncSetAttribute(spmvT_csc_sm<VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem));
-  // One shared-memory carve-out preference for every kernel of the iteration -- only with the opt-in shared-memory
-  // spmvT_csc_sm (an SM that alternates between a small and a 160 KB carve-out is reconfigured at each switch).
-  // Not by default: with L1 at its minimum the gathers of spmvT_csc lose their line reuse (160 k-cell shard: 70
-  // against 41 us per launch; 20 k cells: 30.2 against 29.8 ms per pass).
-  {
-    const int carve = (st_sm && getenv("ADOBO_B200_NO_CARVEOUT") == nullptr) ? (int)cudaSharedmemCarveoutMaxShared
-                                                                              : (int)cudaSharedmemCarveoutDefault;
-    auto prefer = [&](const void* fn) {
-      CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+                        !hook(HK_NO_RUNAHEAD);
+  auto zargs = [&](int j) {
+    ZArgs za;
+    if (zpath)
+      za.Z = Z.p, za.sumW = sumW.p, za.gprev = gout.p, za.cvec = cvec.p, za.ncc = (j < m_b - 1) ? j + 1 : m_b,
+      za.prev = (j < m_b - 1) ? 1 : 0;
+    return za;
+  };
+  // ---- one outer iteration (irlb.py:155-231) up to the convergence read-back: two-kernel steps ----
+  auto enqueue_steps_fused = [&](bool first, int k) {
+    auto w_launch = [&](int jprev, int nd) {
+      WORK(c, w_bytes(nd, jprev));
+      LAUNCH(c, "w_step_t", CUDA_CHECK(launch_k(wt_fn, dim3(gb_w2), dim3(W2_THREADS), wt_smem, st, pdl && jprev >= 0, 1, A.rptr.p,
+                                                A.cidx.p, A.rval.p, xs.p, sc.p, W.p, ld, jprev, nd, (int)n, cvec.p, ybuf_n.p,
+                                                partials.p, tpart.p, hp_halt, h, hp)));
     };
-    prefer((const void*)w_step<VT, 3>), prefer((const void*)w_step<VT, 4>);
-    prefer((const void*)w_step2<VT, 3>), prefer((const void*)w_step2<VT, 4>);
-    prefer((const void*)w_step3<VT, 6>), prefer((const void*)w_step3<VT, 8>);
-    prefer((const void*)spmvT_csc<VT>), prefer((const void*)spmvT_csc_sm<VT>);
-    prefer((const void*)v_step<3>), prefer((const void*)v_step<4>);
-    prefer((const void*)v_step_one<3>), prefer((const void*)v_step_one<4>);
-    prefer((const void*)w_finish), prefer((const void*)set_restart), prefer((const void*)conv_check);
-    prefer((const void*)rotate_basis);
-    for (int R = 1; R <= 5; ++R) prefer((const void*)rotate_rows_for(R));
-    prefer((const void*)rotate_rows_for(2, 2)), prefer((const void*)rotate_rows_for(3, 2));
-    prefer((const void*)jacobi);
-  }
-  auto enqueue_iteration = [&](bool first, int k) {
-    hp = runahead ? info.p + 4 : nullptr;
-    if (!first) restart_update(k);
+    int j = first ? 0 : k;
+    w_launch(-1, j);
+    while (j < m_b) {
+      const bool last = j == m_b - 1;
+      if (last) {
+        // W[:, m_b-1] and B[m_b-1, m_b-1] now: B is complete and its SVD runs beside the last V step
+        if (c->world > 1)
+          LAUNCH(c, "w_norm_exchange", (w_norm_exchange<<<1, 256, 0, st>>>(partials.p, (int)gb_w2, j, gout.p + j, hp_halt, pcw)));
+        LAUNCH(c, "w_finish", (w_finish<<<fin_n, 256, 0, st>>>(ybuf_n.p, gout.p + j, sc.p, W.p, ld, j, n, wcur.p, B.p, m_b, hp_halt,
+                                                               c->world > 1 ? nullptr : partials.p, (int)gb_w2, gout.p)));
+        if (fork_svd) fork_svd_here(first, k);
+      }
+      WORK(c, 8.0 * gb_w2 * (hp + j + 2.0) + 8.0 * h * (2.0 * (j + 1) + 8));
+      LAUNCH(c, "v_step_t", CUDA_CHECK(launch_k(m_b <= 96 ? v_step_t<3> : v_step_t<4>, dim3(VS_CLUSTER), dim3(VS_THREADS),
+                                                vs_one_smem, st, pdl && !last, VS_CLUSTER, (const double*)tpart.p, hp,
+                                                (const double*)partials.p, (int)gb_w2, mu, rs,
+                                                (const double*)(centered ? murs.p : nullptr), sc.p, V.p, ld, j, m_b, h,
+                                                ybuf_h.p, fbuf.p, xs.p, B.p, zargs(j), hp_halt, pcw)));
+      if (!last) w_launch(j, j + 1);
+      ++j;
+    }
+  };
+  // ---- the same on the three-kernel / two-pass paths ----
+  auto enqueue_steps = [&](bool first, int k) {
     int j = first ? 0 : k;
     w_column(-1, j, j);
     while (j < m_b) {
-      if (j == m_b - 1 && fork_svd) {
-        CUDA_CHECK(cudaEventRecord(c->fork_ev, st));
-        CUDA_CHECK(cudaStreamWaitEvent(c->side, c->fork_ev, 0));
-        enqueue_svd(first, k, c->side);
-        CUDA_CHECK(cudaEventRecord(c->join_ev, c->side));
-      }
+      if (j == m_b - 1 && fork_svd) fork_svd_here(first, k);
       WORK(c, (double)A.nnz * (4.0 + sizeof(VT)) + 8.0 * (h + 1) + 8.0 * h + 8.0 * n);
       {
         // column j of W arrives normalised (w_finish / folded finish) or as ybuf + ||w||^2 (finish folded in here)
@@ -2862,39 +2447,24 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
           wf.n2p = zpath ? gout.p + j : sc.p + SC_NRM2,  // column j came from w_step with nd = j
           wf.parts = split ? partials.p : nullptr, wf.nblk = (int)gb_w2, wf.gout = split ? gout.p : nullptr;
         const bool spdl = pdl && infold && zpath && (fused || c->world == 1);
-        if (mgsplit && infold) {
-          wf.parts = partials.p, wf.nblk = (int)gb_w2, wf.gout = gout.p;
-          LAUNCH(c, "spmvT_csc", CUDA_CHECK(launch_k(spmvT_csc_mg<VT>, dim3(h + 1), dim3(256), 0, st, spdl, 1, A.cptr.p, A.ridx.p,
-                                                     A.cval.p, (const double*)ybuf_n.p, tbuf.p, h, counter.p + 1, pcw, wf, hp,
-                                                     ws.mgflag.p)));
-        } else if (st_sm)
-          LAUNCH(c, "spmvT_csc", CUDA_CHECK(launch_k(spmvT_csc_sm<VT>, dim3(st_grid), dim3(STS_THREADS), st_smem, st, spdl, 1, A.cptr.p,
-                                                     A.ridx.p, A.cval.p, (const double*)(infold ? ybuf_n.p : wcur.p), tbuf.p, h,
-                                                     counter.p + 1, fused_t ? pcw : pc1, wf, hp, (int)n, (const int*)ws.perm.p,
-                                                     st_cpb)));
-        else
-          LAUNCH(c, "spmvT_csc", CUDA_CHECK(launch_k(spmvT_csc<VT>, dim3(h), dim3(256), 0, st, spdl, 1, A.cptr.p, A.ridx.p, A.cval.p,
-                                                     (const double*)(infold ? ybuf_n.p : wcur.p), tbuf.p, h, counter.p + 1,
-                                                     fused_t ? pcw : pc1, wf, hp)));
+        LAUNCH(c, "spmvT_csc", CUDA_CHECK(launch_k(spmvT_csc<VT>, dim3(h), dim3(256), 0, st, spdl, 1, A.cptr.p, A.ridx.p, A.cval.p,
+                                                   (const double*)(infold ? ybuf_n.p : wcur.p), tbuf.p, h, counter.p + 1,
+                                                   fused_t ? pcw : pc1, wf, hp_halt)));
       }
-      if (!fused_t) allreduce_sum_f64(c, tbuf.p, (size_t)h);
+      if (c->world > 1 && !fused_t) allreduce_sum_f64(c, tbuf.p, (size_t)h);
       if (use_vstep) {
         WORK(c, 8.0 * h * (2.0 * (j + 1) + 8));
-        ZArgs za;
-        if (zpath)
-          za.Z = Z.p, za.sumW = sumW.p, za.gprev = gout.p, za.cvec = cvec.p, za.ncc = (j < m_b - 1) ? j + 1 : m_b,
-          za.prev = (j < m_b - 1) ? 1 : 0;
         const bool vpdl = pdl && (fused_t || c->world == 1);
         if (vs_one)
           LAUNCH(c, "v_step", CUDA_CHECK(launch_k(m_b <= 96 ? v_step_one<3> : v_step_one<4>, dim3(VS_CLUSTER), dim3(VS_THREADS),
                                                   vs_one_smem, st, vpdl, VS_CLUSTER, (const double*)tbuf.p, mu, rs,
                                                   (const double*)(centered ? murs.p : nullptr), sc.p, V.p, ld, j, m_b, h,
-                                                  ybuf_h.p, fbuf.p, xs.p, B.p, za, hp)));
+                                                  ybuf_h.p, fbuf.p, xs.p, B.p, zargs(j), hp_halt)));
         else
           LAUNCH(c, "v_step", CUDA_CHECK(launch_k(m_b <= 96 ? v_step<3> : v_step<4>, dim3(VS_CLUSTER), dim3(VS_THREADS),
                                                   sizeof(double) * (VS_WARPS + 8) * MAXB, st, vpdl, VS_CLUSTER,
                                                   (const double*)tbuf.p, mu, rs, (const double*)(centered ? murs.p : nullptr),
-                                                  sc.p, V.p, ld, j, m_b, h, ybuf_h.p, fbuf.p, xs.p, B.p, za, hp)));
+                                                  sc.p, V.p, ld, j, m_b, h, ybuf_h.p, fbuf.p, xs.p, B.p, zargs(j), hp_halt)));
       } else {
         WORK(c, 8.0 * h * (j + 1 + 4));
         LAUNCH(c, "v_prep_dots", (v_prep_dots<<<gb_h, RT_THREADS, 0, st>>>(tbuf.p, mu, rs, sc.p, V.p, ld, j, j + 1, h, ybuf_h.p,
@@ -2910,6 +2480,14 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
       if (j < m_b - 1) w_column(j, j + 1, j + 1);
       ++j;
     }
+  };
+  auto enqueue_iteration = [&](bool first, int k) {
+    hp_halt = runahead ? info.p + 4 : nullptr;
+    if (!first) restart_update(k);
+    if (fusedt)
+      enqueue_steps_fused(first, k);
+    else
+      enqueue_steps(first, k);
     const bool arrow = !first && use_arrow && svd_arrow_supported(m_b, k);
     if (fork_svd)
       CUDA_CHECK(cudaStreamWaitEvent(st, c->join_ev, 0));
@@ -2919,7 +2497,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
                                                                  info.p, arrow ? 1 : 0, 0, Sv.p, St.p,
                                                                  zpath ? cvec.p : nullptr, sumW.p, ws.crot.p)));
     CUDA_CHECK(cudaMemcpyAsync(h_info, info.p, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
-    hp = nullptr;
+    hp_halt = nullptr;
   };
   // fallback when svd_arrow rejected its own result: generic Jacobi SVD of the same B
   auto svd_fallback = [&](bool first, int k) {
@@ -2988,6 +2566,8 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
       CUDA_CHECK(cudaEventSynchronize(ws.ev[it % RUN_DEPTH]));
     else
       CUDA_CHECK(cudaStreamSynchronize(st));
+    REQUIRE(h_info[6] == 0, ADOBO_ERR_NCCL, "lanczos: rank %d did not answer an exchange over NVLink peer memory within %d s",
+            h_info[6] - 1, (int)(PEER_TIMEOUT_NS / 1000000000ull));
     if (runahead && h_info[4] != 0) {
       // something stopped: drain the (no-op) iterations behind it and read the final state
       CUDA_CHECK(cudaStreamSynchronize(st));
@@ -3019,82 +2599,14 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   rotate2(nu, outV.p, outU.p, nu, var_weigh ? svd_s.p : nullptr, false);
   CUDA_CHECK(cudaMemcpyAsync(outS.p, svd_s.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));
   CUDA_CHECK(cudaStreamSynchronize(st));
-#ifdef ADOBO_B200_VSTAMPS
-  if (getenv("ADOBO_B200_VSTAMPS")) {
-    long long hs[16];
-    cudaMemcpyFromSymbol(hs, vs_stamps, sizeof(hs));
-    fprintf(stderr, "v_step stamps (cycles):");
-    for (int q = 1; q <= 10; ++q) fprintf(stderr, " %d:%lld", q, hs[q] - hs[q - 1]);
-    fprintf(stderr, " total %lld\n", hs[10] - hs[0]);
-  }
-#endif
 #ifdef ADOBO_B200_TIMELINE
-  if (getenv("ADOBO_B200_TIMELINE")) {
-    static unsigned long long tl[6][1024];
-    cudaMemcpyFromSymbol(tl, tl_buf, sizeof(tl));
-    struct Ev { unsigned long long t0, t1, t2, c0, c1, c2; char name[24]; };
-    std::vector<Ev> evs;
-    auto add = [&](int slot, const char* nm, int j) {
-      if (!tl[0][slot]) return;
-      Ev e{tl[0][slot], tl[1][slot], tl[2][slot], tl[3][slot], tl[4][slot], tl[5][slot], {}};
-      snprintf(e.name, sizeof(e.name), "%s[%d]", nm, j);
-      evs.push_back(e);
-    };
-    for (int j = 0; j < 128; ++j) add(j, "w_step", j), add(128 + j, "spmvT", j), add(256 + j, "v_step", j);
-    add(384, "rotate", 0), add(385, "set_restart", 0), add(386, "conv_check", 0), add(387, "w_finish", 0);
-    {
-      static unsigned long long tc[8][256];
-      cudaMemcpyFromSymbol(tc, tl_cta, sizeof(tc));
-      unsigned long long b0 = ~0ull;
-      const unsigned nbw = wstep2 ? gb_w2 : gb_n;
-      for (unsigned q = 0; q < nbw; ++q) b0 = std::min(b0, tc[1][q]);
-      const char* nm[8] = {"entry", "sync", "rows done", "deposit+sync", "partials", "fence+sync", "atomic", "exit"};
-      fprintf(stderr, "last w_step, per-CTA stamps relative to the earliest sync return (us): min / median / max\n");
-      for (int i = 0; i < 8; ++i) {
-        std::vector<double> v;
-        if (!tc[i][0]) continue;
-        for (unsigned q = 0; q < nbw && q < 256; ++q) v.push_back(((double)tc[i][q] - (double)b0) * 1e-3);
-        std::sort(v.begin(), v.end());
-        fprintf(stderr, "  %-14s %8.2f %8.2f %8.2f   (p90 %8.2f)\n", nm[i], v.front(), v[v.size() / 2], v.back(), v[v.size() * 9 / 10]);
-      }
-    }
-    {
-      static unsigned long long tk[2][8][256];
-      cudaMemcpyFromSymbol(tk, tl_ctak, sizeof(tk));
-      const char* nm0[8] = {"sync", "u issued", "u synced", "W stored", "columns", "entry", "prologue issued", ""};
-      const char* nm1[8] = {"sync", "phase A", "Z landed", "c pushed", "cluster sync 1", "phase B pushed", "cluster sync 2", "exit"};
-      for (int kq = 0; kq < 2; ++kq) {
-        const unsigned nb = kq == 0 ? st_grid : (unsigned)VS_CLUSTER;
-        unsigned long long b0 = ~0ull;
-        for (unsigned q = 0; q < nb; ++q) b0 = std::min(b0, tk[kq][0][q]);
-        fprintf(stderr, "last %s, per-CTA stamps relative to the earliest sync return (us): min / median / max\n",
-                kq == 0 ? "spmvT_csc_sm" : "v_step_one");
-        for (int i = 0; i < 8; ++i) {
-          if (!tk[kq][i][0]) continue;
-          std::vector<double> v;
-          for (unsigned q = 0; q < nb && q < 256; ++q) v.push_back(((double)tk[kq][i][q] - (double)b0) * 1e-3);
-          std::sort(v.begin(), v.end());
-          fprintf(stderr, "  %-16s %8.2f %8.2f %8.2f\n", kq == 0 ? nm0[i] : nm1[i], v.front(), v[v.size() / 2], v.back());
-        }
-      }
-    }
-    std::sort(evs.begin(), evs.end(), [](const Ev& a, const Ev& b) { return a.t0 < b.t0; });
-    const size_t from = evs.size() > 24 ? evs.size() - 24 : 0;
-    const unsigned long long base = evs.empty() ? 0 : evs[from].t0, cbase = evs.empty() ? 0 : evs[from].c0;
-    fprintf(stderr, "timeline of the last kernels (us from the first; globaltimer | clock64 / 1.965 GHz)\n");
-    for (size_t q = from; q < evs.size(); ++q) {
-      const Ev& e = evs[q];
-      fprintf(stderr, "%-16s entry %8.2f sync %8.2f exit %8.2f | entry %8.2f sync %8.2f exit %8.2f\n", e.name,
-              (e.t0 - base) * 1e-3, e.t1 ? (e.t1 - base) * 1e-3 : -1.0, (e.t2 - base) * 1e-3,
-              ((long long)(e.c0 - cbase)) / 1965.0, e.c1 ? ((long long)(e.c1 - cbase)) / 1965.0 : -1.0,
-              ((long long)(e.c2 - cbase)) / 1965.0);
-    }
-  }
+  if (getenv("ADOBO_B200_TIMELINE")) dump_timeline();
 #endif
   res.steps = it;
   res.nmult = nmult;
   if (getenv("ADOBO_B200_DEBUG"))
-    fprintf(stderr, "[adobo_b200] irlb: %d restarts, %d mat-vecs, %d structured-SVD fallbacks\n", it, nmult, res.svd_fallbacks);
+    fprintf(stderr, "[adobo_b200] irlb: %d restarts, %d mat-vecs, %d structured-SVD fallbacks, %s step\n", it, nmult,
+            res.svd_fallbacks, fusedt ? "two-kernel" : (zpath ? "three-kernel" : "two-pass"));
   return res;
 }
 

@@ -1,5 +1,5 @@
 """Per-restart trace (k, converged count) of the IRLB on the C2 bench matrix, for comparison with the CPU
-restatement's trace (tests/explore_restart_sensitivity.py).  ADOBO_B200_IRLB_TRACE=1 python profiles/trace_irlb.py"""
+restatement's trace (tests/explore_restart_sensitivity.py).  ADOBO_B200_IRLB=trace python profiles/trace_irlb.py"""
 import os
 import sys
 import numpy as np

@@ -50,16 +50,16 @@ def main():
     ex_comp, ex_contr, _ = P.exact_pca(case['norm_csr'], case['hvg_ordered'], case['ncomp'])
     P.assert_pca_close(r['comp'], r['contr'], case['comp'][lo:hi], case['contr'], ex_comp[lo:hi], ex_contr)
     np.testing.assert_allclose(r['s'], case['s'], rtol=1e-6)
-    if os.environ.get('CHECK_MGSPLIT'):
-        # opt-in split reduction with several GPUs (spmvT_csc_mg, ADOBO_B200_MGSPLIT): same PCA as the default path
-        os.environ['ADOBO_B200_MGSPLIT'] = '1'
-        eng.upload_normalized(case['norm_csr'][lo:hi])
-        r2 = eng.irlb(case['hvg_ordered'], ncomp=case['ncomp'], seed=42)
-        del os.environ['ADOBO_B200_MGSPLIT']
-        P.assert_pca_close(r2['comp'], r2['contr'], case['comp'][lo:hi], case['contr'], ex_comp[lo:hi], ex_contr)
-        np.testing.assert_allclose(r2['s'], r['s'], rtol=1e-7)
-        if rank == 0:
-            print('mgsplit ok: steps %d (default path %d)' % (r2['steps'], r['steps']))
+    # the three-kernel step (the path for h > 1024: two exchanges per step in the last CTAs) must give the same PCA as
+    # the default two-kernel step (one exchange per step, by the eight CTAs of the V-side cluster)
+    os.environ['ADOBO_B200_IRLB'] = 'no_fusedt'
+    eng.upload_normalized(case['norm_csr'][lo:hi])
+    r2 = eng.irlb(case['hvg_ordered'], ncomp=case['ncomp'], seed=42)
+    del os.environ['ADOBO_B200_IRLB']
+    P.assert_pca_close(r2['comp'], r2['contr'], case['comp'][lo:hi], case['contr'], ex_comp[lo:hi], ex_contr)
+    np.testing.assert_allclose(r2['s'], r['s'], rtol=1e-7)
+    if rank == 0:
+        print('three-kernel step ok: restarts %d (two-kernel step %d)' % (r2['steps'], r['steps']))
     # every rank must hold bit-identical replicated results
     sig = torch.tensor([float(np.abs(r['contr']).sum()), float(r['s'].sum()), float(r['steps'])], dtype=torch.float64, device='cuda')
     ref = sig.clone()
