@@ -63,6 +63,9 @@ SIGNATURES = {
     'adobo_l2_flush': (C.c_int, [ctx_p]),
     'adobo_upload_counts': (C.c_int, [ctx_p, C.c_int64, C.c_int32, _arr(_i64), _arr(_i32), _arr(_i32)]),
     'adobo_upload_normalized': (C.c_int, [ctx_p, C.c_int64, C.c_int32, _arr(_i64), _arr(_i32), _arr(_f64)]),
+    'adobo_synth_counts': (C.c_int, [ctx_p, C.c_int64, C.c_int32, C.c_int64, C.c_uint64, _arr(_f32, 2), C.c_int32,
+                                     C.POINTER(C.c_int64)]),
+    'adobo_download_counts': (C.c_int, [ctx_p, _OptArr(_i64), _OptArr(_i32), _OptArr(_i32)]),
     'adobo_normalize': (C.c_int, [ctx_p, C.c_double, C.c_int, C.c_double, _OptArr(_i64), _OptArr(_f64)]),
     'adobo_gene_moments': (C.c_int, [ctx_p, _OptArr(_f64), _OptArr(_f64)]),
     'adobo_hvg_seurat': (C.c_int, [ctx_p, C.c_int32, C.c_int32, _OptArr(_i32), C.POINTER(C.c_int32), _OptArr(_f64)]),
@@ -73,6 +76,7 @@ SIGNATURES = {
                                     C.c_double, C.c_int32, _arr(_f64), _OptArr(_f64, 2), _OptArr(_f64),
                                     _OptArr(_f64, 2), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     'adobo_knn': (C.c_int, [ctx_p, _OptArr(_f64, 2), C.c_int64, C.c_int32, C.c_int32, _OptArr(_i64, 2)]),
+    'adobo_upload_embedding': (C.c_int, [ctx_p, _arr(_f64, 2), C.c_int64, C.c_int32]),
     'adobo_snn': (C.c_int, [ctx_p, _OptArr(_i64, 2), C.c_int64, C.c_int32, C.c_double, C.POINTER(C.c_int64),
                             C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     'adobo_snn_fetch': (C.c_int, [ctx_p, _arr(_i32), _arr(_i32)]),

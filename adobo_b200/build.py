@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, 'csrc')
 # ADOBO_B200_LIB_SUFFIX: diagnostic variants (e.g. _tl with ADOBO_B200_CFLAGS=-DADOBO_B200_TIMELINE) beside the product
 SUFFIX = os.environ.get('ADOBO_B200_LIB_SUFFIX', '')
 OUT = os.path.join(HERE, 'libadobo_b200%s.so' % SUFFIX)
-SOURCES = ['api.cu', 'normalize.cu', 'moments.cu', 'gather.cu', 'irlb.cu', 'svd_arrow.cu', 'knn.cu', 'knn_tc.cu', 'snn.cu']
+SOURCES = ['api.cu', 'normalize.cu', 'moments.cu', 'gather.cu', 'irlb.cu', 'svd_arrow.cu', 'knn.cu', 'knn_tc.cu', 'snn.cu', 'synth.cu']
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr',
          '-Xptxas', '-v']

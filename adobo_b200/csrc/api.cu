@@ -25,6 +25,8 @@ void set_error(const char* fmt, ...) {
 }
 
 void upload_normalized_values(adobo_ctx* c, const double* values);  // normalize.cu
+void run_synth_counts(adobo_ctx* c, i64 n_rows, int g, i64 row_begin, uint64_t seed, const float* table_host, int n_clusters,
+                      i64* out_nnz);  // synth.cu
 
 // ---- caching device allocator ---------------------------------------------------------------------
 namespace {
@@ -539,6 +541,30 @@ int adobo_upload_counts(adobo_ctx* c, int64_t n, int32_t g, const int64_t* indpt
   API_END
 }
 
+int adobo_synth_counts(adobo_ctx* c, int64_t n_rows, int32_t n_genes, int64_t row_begin, uint64_t seed,
+                       const float* lam_table, int32_t n_clusters, int64_t* out_nnz) {
+  API_BEGIN
+  CUDA_CHECK(cudaSetDevice(c->device));
+  i64 nnz = 0;
+  run_synth_counts(c, n_rows, n_genes, row_begin, seed, lam_table, n_clusters, &nnz);
+  c->have_counts = true;
+  c->have_norm = c->have_moments = c->have_pca = c->have_knn = false;
+  refresh_partition(c);
+  if (out_nnz) *out_nnz = nnz;
+  API_END
+}
+
+int adobo_download_counts(adobo_ctx* c, int64_t* indptr, int32_t* indices, int32_t* counts) {
+  API_BEGIN
+  CUDA_CHECK(cudaSetDevice(c->device));
+  REQUIRE(c->have_counts, ADOBO_ERR_STATE, "download_counts: no count matrix on the device");
+  if (indptr) CUDA_CHECK(cudaMemcpyAsync(indptr, c->indptr.p, sizeof(i64) * (c->n + 1), cudaMemcpyDeviceToHost, c->stream));
+  if (indices && c->nnz) CUDA_CHECK(cudaMemcpyAsync(indices, c->indices.p, sizeof(int) * c->nnz, cudaMemcpyDeviceToHost, c->stream));
+  if (counts && c->nnz) CUDA_CHECK(cudaMemcpyAsync(counts, c->counts.p, sizeof(int) * c->nnz, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  API_END
+}
+
 int adobo_upload_normalized(adobo_ctx* c, int64_t n, int32_t g, const int64_t* indptr, const int32_t* indices,
                             const double* values) {
   API_BEGIN
@@ -641,6 +667,21 @@ int adobo_knn(adobo_ctx* c, const double* comp, int64_t n, int32_t p, int32_t k,
     run_knn(c, c->comp.p, c->n, c->p, k);
   }
   if (out_idx) nn_to_host(c, out_idx);
+  API_END
+}
+
+int adobo_upload_embedding(adobo_ctx* c, const double* comp, int64_t n, int32_t p) {
+  API_BEGIN
+  CUDA_CHECK(cudaSetDevice(c->device));
+  REQUIRE(comp && n >= 1 && p >= 1, ADOBO_ERR_ARG, "upload_embedding: bad arguments");
+  c->comp.ensure((size_t)n * p);
+  CUDA_CHECK(cudaMemcpyAsync(c->comp.p, comp, sizeof(double) * n * p, cudaMemcpyHostToDevice, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  c->n = n;
+  c->p = p;
+  c->have_pca = true;
+  c->h_sub_genes.clear();
+  refresh_partition(c);
   API_END
 }
 

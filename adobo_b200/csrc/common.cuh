@@ -139,7 +139,8 @@ struct adobo_ctx {
   adobo::DevBuf<float> vals;  // normalized values, fp32, same pattern
   bool have_counts = false, have_norm = false;
   // ---- HVG ----
-  adobo::DevBuf<double> gsum, gsq;  // per gene sum x, sum x^2 (all ranks after all-reduce)
+  adobo::DevBuf<i64> gsum, gsq;     // per gene sum x 2^e1, sum x^2 2^e2, fixed point (all ranks after all-reduce)
+  double val_bound = 0;             // max |normalized value| when known analytically (0: measure it)
   bool have_moments = false;
   std::vector<double> h_mean, h_var;
   std::vector<int> hvg_order;  // reference output order

@@ -13,12 +13,18 @@
 
 namespace adobo {
 
-// One warp per cell; lanes stride the row (coalesced 128 B requests of ids and values); fp64
-// reductions straight into L2 (RED.ADD.F64, no return value).
+// Fixed-point accumulation.  x 2^e1 is an exact integer for every fp32 value the path produces (e1 is chosen from the
+// bound of the values), x^2 2^e2 is rounded once per term, and integer addition is associative: the two sums per gene
+// do not depend on the order of the atomics, on the launch configuration or on how the cells are sharded over GPUs
+// -- run-to-run and 1-vs-8-GPU bit-identical moments, hence identical HVG lists.  (An fp64 atomicAdd gives neither.)
+// One warp per cell; lanes stride the row (coalesced 128 B requests of ids and values); 64-bit integer reductions
+// straight into L2 (RED.E.ADD.64, no return value).
 __global__ void __launch_bounds__(256) csr_gene_moments(const i64* __restrict__ indptr,
                                                         const int* __restrict__ indices,
-                                                        const float* __restrict__ vals, double* __restrict__ gsum,
-                                                        double* __restrict__ gsq, i64 n) {
+                                                        const float* __restrict__ vals,
+                                                        unsigned long long* __restrict__ gsum,
+                                                        unsigned long long* __restrict__ gsq, i64 n, double scale1,
+                                                        double scale2) {
   const int lane = threadIdx.x & 31;
   const i64 warps = ((i64)gridDim.x * blockDim.x) >> 5;
   for (i64 row = (((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < n; row += warps) {
@@ -27,39 +33,82 @@ __global__ void __launch_bounds__(256) csr_gene_moments(const i64* __restrict__ 
     for (i64 e = start + lane; e < end; e += 32) {
       const int g = __ldg(indices + e);
       const double x = (double)__ldg(vals + e);
-      atomicAdd(gsum + g, x);
-      atomicAdd(gsq + g, x * x);
+      atomicAdd(gsum + g, (unsigned long long)__double2ll_rn(x * scale1));          // two's complement: signed sums
+      atomicAdd(gsq + g, (unsigned long long)__double2ll_rn(x * x * scale2));
     }
   }
+}
+
+__global__ void max_abs_f32(const float* __restrict__ v, i64 n, unsigned* __restrict__ out) {
+  unsigned m = 0;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+    m = max(m, __float_as_uint(fabsf(v[i])));  // non-negative floats order like their bit patterns
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 }
 
 void run_moments(adobo_ctx* c) {
   REQUIRE(c->have_norm, ADOBO_ERR_STATE, "gene moments: run adobo_normalize / adobo_upload_normalized first");
   c->gsum.ensure((size_t)c->g);
   c->gsq.ensure((size_t)c->g);
-  CUDA_CHECK(cudaMemsetAsync(c->gsum.p, 0, sizeof(double) * c->g, c->stream));
-  CUDA_CHECK(cudaMemsetAsync(c->gsq.p, 0, sizeof(double) * c->g, c->stream));
+  CUDA_CHECK(cudaMemsetAsync(c->gsum.p, 0, sizeof(i64) * c->g, c->stream));
+  CUDA_CHECK(cudaMemsetAsync(c->gsq.p, 0, sizeof(i64) * c->g, c->stream));
+  // bound of |x| over ALL ranks -> the two binary scales (every rank must use the same ones)
+  if (!(c->val_bound > 0)) {
+    DevBuf<i64> mx;
+    mx.ensure(1);
+    CUDA_CHECK(cudaMemsetAsync(mx.p, 0, sizeof(i64), c->stream));
+    if (c->nnz > 0) LAUNCH(c, "max_abs_f32", (max_abs_f32<<<c->sm_count * 4, 256, 0, c->stream>>>(c->vals.p, c->nnz, (unsigned*)mx.p)));
+    unsigned bits = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&bits, mx.p, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    float f;
+    memcpy(&f, &bits, sizeof(f));
+    c->val_bound = std::max((double)f, 1e-30);
+  }
+  double bound = c->val_bound;
+  if (c->world > 1) {  // max over ranks through a sum of one-hot exponents would be overkill: all-gather the bounds
+    std::vector<i64> all;
+    i64 mine;
+    memcpy(&mine, &bound, sizeof(mine));
+    allgather_i64_host(c, mine, all);
+    for (i64 v : all) {
+      double d;
+      memcpy(&d, &v, sizeof(d));
+      bound = std::max(bound, d);
+    }
+  }
+  // sum |x| 2^e1 <= n bound 2^e1 < 2^62 and bound 2^e1 <= 2^40 (exact for fp32 inputs above bound 2^-16)
+  const double nt = (double)std::max<i64>(c->n_total, 1);
+  int eb, en;
+  frexp(bound, &eb);  // bound < 2^eb
+  frexp(nt, &en);
+  const int e1 = std::min(40 - eb, 62 - eb - en), e2 = std::min(40 - 2 * eb, 62 - 2 * eb - en);
+  const double scale1 = ldexp(1.0, e1), scale2 = ldexp(1.0, e2);
   if (c->n > 0) {
     i64 blocks = std::min<i64>((c->n + 7) / 8, (i64)c->sm_count * 8);
     WORK(c, (double)c->nnz * 8.0 + 16.0 * c->g + 8.0 * (c->n + 1));
     LAUNCH(c, "csr_gene_moments", (csr_gene_moments<<<(unsigned)blocks, 256, 0, c->stream>>>(
-                                      c->indptr.p, c->indices.p, c->vals.p, c->gsum.p, c->gsq.p, c->n)));
+                                      c->indptr.p, c->indices.p, c->vals.p, (unsigned long long*)c->gsum.p,
+                                      (unsigned long long*)c->gsq.p, c->n, scale1, scale2)));
   }
-  allreduce_sum_f64(c, c->gsum.p, (size_t)c->g);
-  allreduce_sum_f64(c, c->gsq.p, (size_t)c->g);
-  std::vector<double> s1(c->g), s2(c->g);
-  CUDA_CHECK(cudaMemcpyAsync(s1.data(), c->gsum.p, sizeof(double) * c->g, cudaMemcpyDeviceToHost, c->stream));
-  CUDA_CHECK(cudaMemcpyAsync(s2.data(), c->gsq.p, sizeof(double) * c->g, cudaMemcpyDeviceToHost, c->stream));
+  allreduce_sum_i64(c, c->gsum.p, (size_t)c->g);
+  allreduce_sum_i64(c, c->gsq.p, (size_t)c->g);
+  std::vector<i64> s1(c->g), s2(c->g);
+  CUDA_CHECK(cudaMemcpyAsync(s1.data(), c->gsum.p, sizeof(i64) * c->g, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(s2.data(), c->gsq.p, sizeof(i64) * c->g, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  const double n = (double)c->n_total;
+  const long double n = (long double)c->n_total, i1 = ldexpl(1.0L, -e1), i2 = ldexpl(1.0L, -e2);
   c->h_mean.resize(c->g);
   c->h_var.resize(c->g);
   for (int i = 0; i < c->g; ++i) {
-    double m = s1[i] / n;  // hvg.py:60: mean over ALL cells
-    double ss = s2[i] - n * m * m;
+    const long double sx = (long double)s1[i] * i1, sxx = (long double)s2[i] * i2;  // 64-bit mantissas: exact
+    const long double m = sx / n;                                                    // hvg.py:60: mean over ALL cells
+    long double ss = sxx - sx * m;
     if (ss < 0) ss = 0;
-    c->h_mean[i] = m;
-    c->h_var[i] = ss / (n - 1.0);  // ddof = 1 (pandas var), NaN for a single cell like pandas
+    c->h_mean[i] = (double)m;
+    c->h_var[i] = (double)(ss / (n - 1.0L));  // ddof = 1 (pandas var), NaN for a single cell like pandas
   }
   c->have_moments = true;
 }

@@ -124,6 +124,12 @@ void run_normalize(adobo_ctx* c, double scaling, int log_mode, double small_cons
   }
   c->have_norm = true;
   c->have_moments = false;
+  {  // bound of the values for the fixed-point gene moments: count / S <= 1
+    const double top = scaling;
+    c->val_bound = log_mode == ADOBO_LOG_2 ? log2(top + small_const) : log_mode == ADOBO_LOG_E ? log(top + small_const)
+                 : log_mode == ADOBO_LOG_10 ? log10(top + small_const) : top;
+    if (!(c->val_bound > 0)) c->val_bound = 0;  // measured instead
+  }
   if (out_lib) CUDA_CHECK(cudaMemcpyAsync(out_lib, lib.p, sizeof(i64) * c->n, cudaMemcpyDeviceToHost, c->stream));
   if (out_vals)
     CUDA_CHECK(cudaMemcpyAsync(out_vals, v64.p, sizeof(double) * c->nnz, cudaMemcpyDeviceToHost, c->stream));
@@ -140,6 +146,7 @@ void upload_normalized_values(adobo_ctx* c, const double* values) {
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
   c->have_norm = true;
   c->have_moments = false;
+  c->val_bound = 0;  // unknown values: run_moments measures max |x|
 }
 
 }  // namespace adobo

@@ -137,6 +137,26 @@ class Engine:
         self._pattern = (indptr, indices)
         self.resident_key = key
 
+    def synth_counts(self, model, row_begin, n_rows):
+        """Generates cells [row_begin, row_begin + n_rows) of the seeded synthetic matrix of `model`
+        (adobo_b200.synth.CountModel) ON the device, resident like after upload_counts.  Returns nnz."""
+        table = np.ascontiguousarray(model.lam_table(), dtype=np.float32)
+        nnz = C.c_int64()
+        check(self.lib.adobo_synth_counts(self.h, int(n_rows), int(model.n_genes), int(row_begin), int(model.seed) & (2**64 - 1),
+                                          table, int(table.shape[0]), C.byref(nnz)))
+        self.n, self.g, self.nnz = int(n_rows), int(model.n_genes), int(nnz.value)
+        self._pattern = None
+        self.resident_key = None
+        return self.nnz
+
+    def download_counts(self):
+        """The resident count shard as scipy CSR (int64 indptr, int32 indices / counts) -- for the CPU checkers."""
+        indptr = np.empty(self.n + 1, dtype=np.int64)
+        indices = np.empty(self.nnz, dtype=np.int32)
+        data = np.empty(self.nnz, dtype=np.int32)
+        check(self.lib.adobo_download_counts(self.h, indptr, indices, data))
+        return sp.csr_matrix((data, indices, indptr), shape=(self.n, self.g))
+
     # ---- stages ----
     def normalize(self, scaling_factor=10000, log_mode=LOG_2, small_const=1.0, want_values=True):
         lib = np.empty(self.n, dtype=np.int64)
@@ -144,6 +164,9 @@ class Engine:
         check(self.lib.adobo_normalize(self.h, float(scaling_factor), int(log_mode), float(small_const), lib, vals))
         if not want_values:
             return None, lib
+        if self._pattern is None:                        # matrix generated on the device
+            m = self.download_counts()
+            self._pattern = (np.ascontiguousarray(m.indptr, dtype=np.int64), np.ascontiguousarray(m.indices, dtype=np.int32))
         indptr, indices = self._pattern
         return sp.csr_matrix((vals, indices, indptr), shape=(self.n, self.g)), lib
 
@@ -202,6 +225,13 @@ class Engine:
         out = np.empty((n, k), dtype=np.int64) if fetch else None
         check(self.lib.adobo_knn(self.h, comp, n, p, int(k), out))
         return out
+
+    def upload_embedding(self, comp):
+        """This rank's rows of an embedding (n x p float64) left on the device for knn(None, k)."""
+        comp = np.ascontiguousarray(comp, dtype=np.float64)
+        check(self.lib.adobo_upload_embedding(self.h, comp, comp.shape[0], comp.shape[1]))
+        self.n = comp.shape[0]
+        self.resident_key = None
 
     def snn(self, nn_idx=None, k=10, prune_snn=0.067, fetch=True):
         ne, pr, tot = C.c_int64(), C.c_int64(), C.c_int64()

@@ -39,6 +39,11 @@ class CountModel:
                 hi = mid
         self.off = 0.5 * (lo + hi)
 
+    def lam_table(self):
+        """Expected count per (cluster, gene) before the per-cell size factor: the table the device generator
+        (csrc/synth.cu, Engine.synth_counts) draws from."""
+        return np.exp(self.base[None, :] + self.off + self.lfc).astype(np.float32)
+
     def block(self, b, n_rows):
         """Dense int32 counts of cell block `b` (n_rows <= BLOCK rows)."""
         rng = np.random.default_rng([self.seed, 1 + b])

@@ -82,6 +82,16 @@ int adobo_upload_counts(adobo_ctx* ctx, int64_t n_cells, int32_t n_genes, const 
 int adobo_upload_normalized(adobo_ctx* ctx, int64_t n_cells, int32_t n_genes, const int64_t* indptr,
                             const int32_t* indices, const double* values);
 
+/* Test / bench data source (no counterpart in the reference): seeded synthetic counts generated on the device,
+ * model of SURVEY.md 8(d) -- count ~ Poisson(lam_table[cluster(cell)][gene] * size(cell) * Gamma(2, 1/2)), every draw a
+ * pure function of (seed, global cell index, gene).  Generates cells [row_begin, row_begin + n_rows) of the
+ * conceptual matrix and leaves them in the context exactly as adobo_upload_counts would (any rank can generate its
+ * own shard).  lam_table: float32 [n_clusters x n_genes] (host).  adobo_download_counts copies the resident count
+ * matrix back (indptr int64[n+1], indices / counts int32[nnz]; any may be NULL) for the CPU checkers. */
+int adobo_synth_counts(adobo_ctx* ctx, int64_t n_rows, int32_t n_genes, int64_t row_begin, uint64_t seed,
+                       const float* lam_table, int32_t n_clusters, int64_t* out_nnz);
+int adobo_download_counts(adobo_ctx* ctx, int64_t* indptr, int32_t* indices, int32_t* counts);
+
 /* ---- normalize.standard + log step (adobo/normalize.py:285-287, 559-560) ------------------- */
 /* y = log_f((c / S_cell) * scaling_factor + small_const) on the non-zeros; zeros stay zero.
  * out_libsize int64[n] and out_values float64[nnz] may be NULL (device-resident use). */
@@ -124,6 +134,11 @@ int adobo_lanczos_csr(adobo_ctx* ctx, int64_t rows, int32_t cols, const int64_t*
  * [n x p] row-major, or NULL to use the embedding left on the device by adobo_irlb.
  * out_idx int64[n x k] (this rank's cells; indices are global). */
 int adobo_knn(adobo_ctx* ctx, const double* comp, int64_t n, int32_t p, int32_t k, int64_t* out_idx);
+
+/* Leaves a caller-supplied embedding (this rank's cells, float64 [n x p] row-major) on the device as if adobo_irlb had
+ * produced it: adobo_knn(ctx, NULL, ...) then runs on it (obj.norm_data[..]['dr']['pca']['comp'] of an earlier
+ * session, clustering.py:337-341; the kNN / SNN sweep of bench.py). */
+int adobo_upload_embedding(adobo_ctx* ctx, const double* comp, int64_t n, int32_t p);
 
 /* ---- clustering.snn (adobo/clustering.py:55-128) ------------------------------------------- */
 /* Shared-nearest-neighbour graph: M has ones at (nn_idx[i,0]-1, nn_idx[i,c]-1), c>=1, and on the

@@ -125,3 +125,32 @@ def knn_dist_rows(x, rows, idx1):
 def edges_sorted(e):
     e = np.asarray(e, dtype=np.int64).reshape(-1, 2)
     return e[np.lexsort((e[:, 1], e[:, 0]))]
+
+
+# ---- golden vectors at BASELINE.json's own shapes (tests/golden/make_golden_configs.py) -------------------------
+CONFIG_CASES = ['c1', 'c2']
+
+
+def load_config_case(name):
+    """c1 / c2: everything downstream of the count matrix as the unmodified reference produced it; the matrix is
+    regenerated from its seed (and checked against the stored nnz / checksums)."""
+    from adobo_b200.synth import synth_counts
+    G = dict(np.load(os.path.join(GOLDEN_DIR, name + '.npz')))
+    n, g, ngenes, ncomp, k = (int(x) for x in G['shape'])
+    G.update(n=n, g=g, ngenes=ngenes, ncomp=ncomp, k=k)
+    counts = synth_counts(n, g, float(G['density']), int(G['data_seed']))
+    assert counts.nnz == int(G['nnz']) and int(counts.data.astype(np.int64).sum()) == int(G['counts_sum']) \
+        and int(counts.indices.astype(np.int64).sum()) == int(G['indices_sum']), 'regenerated count matrix differs'
+    G['counts_csr'] = counts
+    G['nn_idx'] = G['nn_idx'].astype(np.int64)
+    G['edges'] = G['edges'].astype(np.int64)
+    return G
+
+
+def pca_report(comp, ref_comp, ref_own_err, tol=1e-4, slack=2.5):
+    """Per-component error against the reference and the two counts DESIGN.md quotes: components further than
+    `tol` from the reference's, and components further than max(tol, slack x the reference's own error against the
+    exact SVD of its input) -- the latter must be zero."""
+    e = component_err(comp, ref_comp)
+    lim = np.maximum(tol, slack * np.asarray(ref_own_err))
+    return e, int(np.sum(e > tol)), np.flatnonzero(e > lim)
