@@ -80,6 +80,8 @@ SIGNATURES = {
     'adobo_snn': (C.c_int, [ctx_p, _OptArr(_i64, 2), C.c_int64, C.c_int32, C.c_double, C.POINTER(C.c_int64),
                             C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     'adobo_snn_fetch': (C.c_int, [ctx_p, _arr(_i32), _arr(_i32)]),
+    'adobo_snn_fetch_counts': (C.c_int, [ctx_p, _arr(_i32)]),
+    'adobo_result_sizes': (C.c_int, [ctx_p, _arr(_i64)]),
     'adobo_embed_path': (C.c_int, [ctx_p, C.c_double, C.c_int32, C.c_int32, _arr(_f64), C.c_int32, C.c_double,
                                    C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     'adobo_fetch_pca': (C.c_int, [ctx_p, _OptArr(_f64, 2), _OptArr(_f64), _OptArr(_f64, 2), _OptArr(_i32)]),

@@ -723,6 +723,29 @@ int adobo_snn_fetch(adobo_ctx* c, int32_t* out_source, int32_t* out_target) {
   API_END
 }
 
+int adobo_snn_fetch_counts(adobo_ctx* c, int32_t* out_v) {
+  API_BEGIN
+  CUDA_CHECK(cudaSetDevice(c->device));
+  REQUIRE(out_v, ADOBO_ERR_ARG, "snn_fetch_counts: out_v is NULL");
+  if (c->n_edges > 0) CUDA_CHECK(cudaMemcpyAsync(out_v, c->e_v.p, sizeof(int) * c->n_edges, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  API_END
+}
+
+int adobo_result_sizes(adobo_ctx* c, int64_t* out8) {
+  API_BEGIN
+  REQUIRE(out8, ADOBO_ERR_ARG, "result_sizes: out is NULL");
+  out8[0] = c->n;
+  out8[1] = c->have_pca ? c->p : 0;
+  out8[2] = c->have_pca ? (int64_t)c->h_sub_genes.size() : 0;
+  out8[3] = c->have_knn ? c->k : 0;
+  out8[4] = c->have_knn ? c->knn_n : 0;
+  out8[5] = c->n_edges;
+  out8[6] = c->nnz;
+  out8[7] = c->g;
+  API_END
+}
+
 int adobo_embed_path(adobo_ctx* c, double scaling_factor, int32_t ngenes, int32_t ncomp, const double* v0, int32_t k,
                      double prune_snn, int32_t* out_steps, int32_t* out_nmult, int64_t* out_n_edges) {
   API_BEGIN

@@ -159,7 +159,7 @@ struct adobo_ctx {
   i64 knn_n = 0;
   adobo::DevBuf<int> nn;  // knn_n x k, 0-based global ids
   bool have_knn = false;
-  adobo::DevBuf<int> e_src, e_dst;
+  adobo::DevBuf<int> e_src, e_dst, e_v;  // kept edges and their shared-neighbour counts V_ij
   i64 n_edges = 0;
   // ---- plumbing ----
   adobo::Comm* comm = nullptr;

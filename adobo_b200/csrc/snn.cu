@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(T == 32 ? 128 : 256) snn_rows(
     const int* __restrict__ rrow, i64 row_begin, i64 row_end, const int* __restrict__ list, int nlist, int k,
     double prune, i64* __restrict__ rowkept, i64* __restrict__ rowmiss, unsigned long long* __restrict__ totals,
     int* __restrict__ biglist, int* __restrict__ nbig, const i64* __restrict__ eptr, const i64* __restrict__ mptr,
-    i64 e_regular, int* __restrict__ e_src, int* __restrict__ e_dst, int* __restrict__ err) {
+    i64 e_regular, int* __restrict__ e_src, int* __restrict__ e_dst, int* __restrict__ e_v, int* __restrict__ err) {
   extern __shared__ unsigned sbuf[];
   constexpr int GROUPS = (T == 32) ? 4 : 1;
   const int grp = (T == 32) ? (threadIdx.x >> 5) : 0;
@@ -126,11 +126,12 @@ __global__ void __launch_bounds__(T == 32 ? 128 : 256) snn_rows(
         const int idx = base + lane;
         bool head = false, keep = false;
         unsigned b = 0;
+        int v = 0;
         if (idx < (int)total) {
           b = buf[idx];
           head = (idx == 0) || (buf[idx - 1] != b);
           if (head) {
-            int v = 1;
+            v = 1;
             while (idx + v < (int)total && buf[idx + v] == b) ++v;
             const double strength = (double)v / (double)(k + (k - v));  // clustering.py:108
             keep = strength > prune;                                     // clustering.py:109
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(T == 32 ? 128 : 256) snn_rows(
           const i64 pos = ebase + kept + __popc(km & ((1u << lane) - 1u));
           e_src[pos] = (int)a;
           e_dst[pos] = (int)b;
+          e_v[pos] = v;  // V_ab = (M M^T)_ab, clustering.py:99
         }
         uniq += __popc(hm);
         kept += __popc(km);
@@ -154,6 +156,7 @@ __global__ void __launch_bounds__(T == 32 ? 128 : 256) snn_rows(
         } else if (kept == 0) {  // node without any kept edge -> self loop, clustering.py:114-118
           e_src[e_regular + mptr[la]] = (int)a;
           e_dst[e_regular + mptr[la]] = (int)a;
+          e_v[e_regular + mptr[la]] = 0;  // not an entry of V that passed the threshold
         }
       }
     }
@@ -214,7 +217,7 @@ void run_snn(adobo_ctx* c, const int* nn, i64 n, i64 row_begin, i64 row_end, int
   if (nloc > 0) {
     LAUNCH(c, "snn_rows", (snn_rows<32, WCAP, false><<<wb, 128, wsmem, st>>>(
                               fptr.p, fcol.p, rptr.p, rrow.p, row_begin, row_end, nullptr, 0, k, prune, rowkept.p,
-                              rowmiss.p, totals.p, biglist.p, flags.p + 1, nullptr, nullptr, 0, nullptr, nullptr,
+                              rowmiss.p, totals.p, biglist.p, flags.p + 1, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
                               flags.p + 2)));
     CUDA_CHECK(cudaMemcpyAsync(h_flags, flags.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
@@ -223,7 +226,7 @@ void run_snn(adobo_ctx* c, const int* nn, i64 n, i64 row_begin, i64 row_end, int
       LAUNCH(c, "snn_rows_big", (snn_rows<256, CCAP, false><<<(unsigned)nbig, 256, csmem, st>>>(
                                     fptr.p, fcol.p, rptr.p, rrow.p, row_begin, row_end, biglist.p, nbig, k, prune,
                                     rowkept.p, rowmiss.p, totals.p, nullptr, nullptr, nullptr, nullptr, 0, nullptr,
-                                    nullptr, flags.p + 2)));
+                                    nullptr, nullptr, flags.p + 2)));
       CUDA_CHECK(cudaMemcpyAsync(h_flags, flags.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
       CUDA_CHECK(cudaStreamSynchronize(st));
       REQUIRE(h_flags[2] == 0, ADOBO_ERR_LIMIT, "snn: a cell has more than %d shared-neighbour candidates", CCAP);
@@ -240,16 +243,17 @@ void run_snn(adobo_ctx* c, const int* nn, i64 n, i64 row_begin, i64 row_end, int
   const i64 E = e_regular + n_missing;
   c->e_src.ensure((size_t)std::max<i64>(E, 1));
   c->e_dst.ensure((size_t)std::max<i64>(E, 1));
+  c->e_v.ensure((size_t)std::max<i64>(E, 1));
   if (nloc > 0) {
     LAUNCH(c, "snn_rows", (snn_rows<32, WCAP, true><<<wb, 128, wsmem, st>>>(
                               fptr.p, fcol.p, rptr.p, rrow.p, row_begin, row_end, nullptr, 0, k, prune, nullptr, nullptr,
-                              nullptr, nullptr, nullptr, eptr.p, mptr.p, e_regular, c->e_src.p, c->e_dst.p,
+                              nullptr, nullptr, nullptr, eptr.p, mptr.p, e_regular, c->e_src.p, c->e_dst.p, c->e_v.p,
                               flags.p + 2)));
     if (nbig > 0)
       LAUNCH(c, "snn_rows_big", (snn_rows<256, CCAP, true><<<(unsigned)nbig, 256, csmem, st>>>(
                                     fptr.p, fcol.p, rptr.p, rrow.p, row_begin, row_end, biglist.p, nbig, k, prune,
                                     nullptr, nullptr, nullptr, nullptr, nullptr, eptr.p, mptr.p, e_regular, c->e_src.p,
-                                    c->e_dst.p, flags.p + 2)));
+                                    c->e_dst.p, c->e_v.p, flags.p + 2)));
   }
   CUDA_CHECK(cudaStreamSynchronize(st));
   c->n_edges = E;

@@ -260,24 +260,46 @@ class Engine:
                                         float(prune_snn), C.byref(steps), C.byref(nmult), C.byref(ne)))
         return dict(steps=steps.value, nmult=nmult.value, n_edges=ne.value)
 
-    def fetch_pca(self, h, ncomp):
-        comp = np.empty((self.n, ncomp))
+    def result_sizes(self):
+        """What the context holds: sizes for the fetch buffers (never the caller's own numbers)."""
+        out = np.zeros(8, dtype=np.int64)
+        check(self.lib.adobo_result_sizes(self.h, out))
+        return dict(zip(('n', 'ncomp', 'h', 'k', 'knn_n', 'n_edges', 'nnz', 'g'), (int(v) for v in out)))
+
+    def fetch_pca(self, h=None, ncomp=None):
+        sz = self.result_sizes()
+        if (h is not None and h != sz['h']) or (ncomp is not None and ncomp != sz['ncomp']):
+            raise Exception('fetch_pca: the device holds %d genes x %d components, not %s x %s' % (sz['h'], sz['ncomp'], h, ncomp))
+        h, ncomp = sz['h'], sz['ncomp']
+        comp = np.empty((sz['n'], ncomp))
         contr = np.empty((h, ncomp))
         s = np.empty(ncomp)
         genes = np.empty(h, dtype=np.int32)
         check(self.lib.adobo_fetch_pca(self.h, comp, s, contr, genes))
         return dict(comp=comp, contr=contr, s=s, genes=genes.astype(np.int64))
 
-    def fetch_knn(self, k):
-        out = np.empty((self.n, k), dtype=np.int64)
+    def fetch_knn(self, k=None):
+        sz = self.result_sizes()
+        if k is not None and k != sz['k']:
+            raise Exception('fetch_knn: the device holds k=%d neighbours, not %d' % (sz['k'], k))
+        out = np.empty((sz['knn_n'], sz['k']), dtype=np.int64)
         check(self.lib.adobo_fetch_knn(self.h, out))
         return out
 
-    def fetch_edges(self, ne):
+    def fetch_edges(self, ne=None, counts=False):
+        """Edge list of the last SNN (E x 2 int32); with counts=True also V_ij per edge."""
+        have = self.result_sizes()['n_edges']
+        if ne is not None and ne != have:
+            raise Exception('fetch_edges: the device holds %d edges, not %d' % (have, ne))
+        ne = have
+        if counts:
+            v = np.empty(max(ne, 1), dtype=np.int32)
+            check(self.lib.adobo_snn_fetch_counts(self.h, v))
         src = np.empty(max(ne, 1), dtype=np.int32)
         dst = np.empty(max(ne, 1), dtype=np.int32)
         check(self.lib.adobo_snn_fetch(self.h, src, dst))
-        return np.stack([src[:ne], dst[:ne]], axis=1)
+        e = np.stack([src[:ne], dst[:ne]], axis=1)
+        return (e, v[:ne]) if counts else e
 
 
 _default = None

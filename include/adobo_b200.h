@@ -149,6 +149,14 @@ int adobo_upload_embedding(adobo_ctx* ctx, const double* comp, int64_t n, int32_
 int adobo_snn(adobo_ctx* ctx, const int64_t* nn_idx, int64_t n, int32_t k, double prune_snn,
               int64_t* out_n_edges, int64_t* out_pruned, int64_t* out_total_links);
 int adobo_snn_fetch(adobo_ctx* ctx, int32_t* out_source, int32_t* out_target);
+/* The integer edge weights the reference computes and then drops (clustering.py:99-112 keeps only the
+ * coordinates): out_v[e] = V_ij = (M M^T)_ij of edge e of adobo_snn_fetch, 1..k; 0 for the self loops appended for
+ * nodes without a kept edge. */
+int adobo_snn_fetch_counts(adobo_ctx* ctx, int32_t* out_v);
+/* Sizes of what the context holds, so that callers can size the buffers of the fetch calls:
+ * out8 = { local cells, PCA components, PCA genes h, k of the kNN result, rows of the kNN result, SNN edges,
+ *          non-zeros of the matrix shard, genes }. */
+int adobo_result_sizes(adobo_ctx* ctx, int64_t* out8);
 
 /* ---- whole path, device resident (bench `value`) ------------------------------------------- */
 /* normalize -> moments -> seurat -> irlb -> knn -> snn without leaving the device.  v0 has
