@@ -9,6 +9,6 @@ All numerics run in libadobo_b200.so (hand-written CUDA, C-ABI in include/adobo_
 package imports without a GPU, but every computing call raises when no CUDA device / library
 is available -- there is no CPU fallback.
 """
-from . import data, normalize, hvg, dr, irlbpy, clustering, engine, synth  # noqa: F401
+from . import data, normalize, hvg, dr, irlbpy, clustering, preproc, plotting, engine, synth  # noqa: F401
 
 __version__ = '0.1.0'

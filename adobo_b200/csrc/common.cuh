@@ -141,6 +141,7 @@ struct adobo_ctx {
   // ---- HVG ----
   adobo::DevBuf<i64> gsum, gsq;     // per gene sum x 2^e1, sum x^2 2^e2, fixed point (all ranks after all-reduce)
   double val_bound = 0;             // max |normalized value| when known analytically (0: measure it)
+  double zero_level = 0;            // value of the implicit zeros of the normalized matrix: vals hold y - zero_level
   bool have_moments = false;
   std::vector<double> h_mean, h_var;
   std::vector<int> hvg_order;  // reference output order

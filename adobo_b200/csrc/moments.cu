@@ -107,7 +107,7 @@ void run_moments(adobo_ctx* c) {
     const long double m = sx / n;                                                    // hvg.py:60: mean over ALL cells
     long double ss = sxx - sx * m;
     if (ss < 0) ss = 0;
-    c->h_mean[i] = (double)m;
+    c->h_mean[i] = (double)(m + (long double)c->zero_level);  // the zeros of the matrix stand for zero_level
     c->h_var[i] = (double)(ss / (n - 1.0L));  // ddof = 1 (pandas var), NaN for a single cell like pandas
   }
   c->have_moments = true;

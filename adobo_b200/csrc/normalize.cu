@@ -8,6 +8,9 @@
 //           fp64 log never limits the kernel (it is HBM bound: 4 B in + 4 B out per non-zero);
 //   pass 2  re-reads the row (L2 hit), writes fp32 values with 128-bit stores (and fp64 values for
 //           the host-facing API when asked).
+// The device copy holds y - z0 with z0 = log(small_const), the value every implicit zero takes (0 for the
+// reference's default small_const = 1; preproc.impute logs raw + 1.01, preproc.py:472): the matrix stays sparse for
+// any small_const, gene means get z0 back (moments.cu), centring removes it from the PCA.
 #include "common.cuh"
 
 namespace adobo {
@@ -27,7 +30,7 @@ __global__ void __launch_bounds__(256) csr_libsize_scale_log(const i64* __restri
                                                              const int* __restrict__ counts,
                                                              float* __restrict__ vals, double* __restrict__ out64,
                                                              i64* __restrict__ libsize, i64 n, double scaling,
-                                                             int log_mode, double small_const) {
+                                                             int log_mode, double small_const, double z0) {
   const int lane = threadIdx.x & 31;
   const i64 warps = ((i64)gridDim.x * blockDim.x) >> 5;
   for (i64 row = (((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < n; row += warps) {
@@ -50,17 +53,17 @@ __global__ void __launch_bounds__(256) csr_libsize_scale_log(const i64* __restri
     const double S = (double)sum;
     // ---- per-row table: lane l holds y(count = l + 1) ----
     const double lut64 = norm_value(lane + 1, S, scaling, log_mode, small_const);
-    const float lut32 = (float)lut64;
+    const float lut32 = (float)(lut64 - z0);
     // ---- pass 2 ----
     // head / tail (at most 3 elements each): direct evaluation
     for (i64 e = start + lane; e < a0; e += 32) {
       double y = norm_value(counts[e], S, scaling, log_mode, small_const);
-      vals[e] = (float)y;
+      vals[e] = (float)(y - z0);
       if (OUT64) out64[e] = y;
     }
     for (i64 e = a1 + lane; e < end; e += 32) {
       double y = norm_value(counts[e], S, scaling, log_mode, small_const);
-      vals[e] = (float)y;
+      vals[e] = (float)(y - z0);
       if (OUT64) out64[e] = y;
     }
     for (i64 base = a0; base < a1; base += 128) {  // warp-uniform trip count: shuffles inside
@@ -78,7 +81,7 @@ __global__ void __launch_bounds__(256) csr_libsize_scale_log(const i64* __restri
         if (OUT64) y64[q] = __shfl_sync(0xffffffffu, lut64, src);
         if (cc[q] < 1 || cc[q] > 32) {  // rare: large count, evaluate directly
           double y = norm_value(cc[q], S, scaling, log_mode, small_const);
-          y32[q] = (float)y;
+          y32[q] = (float)(y - z0);
           if (OUT64) y64[q] = y;
         }
       }
@@ -111,23 +114,27 @@ void run_normalize(adobo_ctx* c, double scaling, int log_mode, double small_cons
   i64 cap = (i64)c->sm_count * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
+  const double z0 = log_mode == ADOBO_LOG_2 ? log2(small_const) : log_mode == ADOBO_LOG_E ? log(small_const)
+                  : log_mode == ADOBO_LOG_10 ? log10(small_const) : 0.0;
+  REQUIRE(z0 == z0 && z0 > -1e300, ADOBO_ERR_ARG, "normalize: small_const must be positive when log is applied");
+  c->zero_level = z0;
   if (c->n > 0) {
     WORK(c, (double)c->nnz * (out_vals ? 16.0 : 8.0) + 8.0 * (c->n + 1));
     if (out_vals)
       LAUNCH(c, "csr_libsize_scale_log", (csr_libsize_scale_log<true><<<(unsigned)blocks, 256, 0, c->stream>>>(
                                              c->indptr.p, c->counts.p, c->vals.p, v64.p, lib.p, c->n, scaling,
-                                             log_mode, small_const)));
+                                             log_mode, small_const, z0)));
     else
       LAUNCH(c, "csr_libsize_scale_log", (csr_libsize_scale_log<false><<<(unsigned)blocks, 256, 0, c->stream>>>(
                                              c->indptr.p, c->counts.p, c->vals.p, nullptr, lib.p, c->n, scaling,
-                                             log_mode, small_const)));
+                                             log_mode, small_const, z0)));
   }
   c->have_norm = true;
   c->have_moments = false;
   {  // bound of the values for the fixed-point gene moments: count / S <= 1
     const double top = scaling;
-    c->val_bound = log_mode == ADOBO_LOG_2 ? log2(top + small_const) : log_mode == ADOBO_LOG_E ? log(top + small_const)
-                 : log_mode == ADOBO_LOG_10 ? log10(top + small_const) : top;
+    c->val_bound = (log_mode == ADOBO_LOG_2 ? log2(top + small_const) : log_mode == ADOBO_LOG_E ? log(top + small_const)
+                  : log_mode == ADOBO_LOG_10 ? log10(top + small_const) : top) - z0;
     if (!(c->val_bound > 0)) c->val_bound = 0;  // measured instead
   }
   if (out_lib) CUDA_CHECK(cudaMemcpyAsync(out_lib, lib.p, sizeof(i64) * c->n, cudaMemcpyDeviceToHost, c->stream));
@@ -147,6 +154,7 @@ void upload_normalized_values(adobo_ctx* c, const double* values) {
   c->have_norm = true;
   c->have_moments = false;
   c->val_bound = 0;  // unknown values: run_moments measures max |x|
+  c->zero_level = 0;
 }
 
 }  // namespace adobo

@@ -10,6 +10,66 @@ import pandas as pd
 import scipy.sparse as sp
 
 
+class CsrFrame:
+    """genes x cells matrix held as scipy CSR (cells x genes) with pandas labels -- what stands in for the pandas
+    frame where a frame cannot exist.  A pandas sparse frame keeps one SparseArray object PER CELL (data.py:67):
+    building it takes seconds at 20 k cells and it cannot be built at all at 68 k (18 GB dense input) or 1.3 M cells
+    (SURVEY.md 8f, f1).  It offers the frame surface the hot path touches -- `index`, `columns`, `shape`,
+    `drop(labels, axis=, errors=)` (clean_matrix, normalize.py:413-433), row selection by a boolean mask (dr.py:319),
+    `transpose()` -- and converts to the real thing with `to_frame()` when the matrix is small enough to want one."""
+
+    def __init__(self, csr, genes, cells):
+        self.csr = sp.csr_matrix(csr)
+        if not self.csr.has_sorted_indices:
+            self.csr.sort_indices()
+        self.index = pd.Index(genes)
+        self.columns = pd.Index(cells)
+        assert self.csr.shape == (len(self.columns), len(self.index)), 'CSR is cells x genes'
+
+    @property
+    def shape(self):
+        return (len(self.index), len(self.columns))
+
+    @property
+    def dtypes(self):
+        return pd.Series([pd.SparseDtype(self.csr.dtype, 0)] * min(len(self.columns), 1))
+
+    def drop(self, labels, axis=0, errors='raise'):
+        labels = pd.Index(labels)
+        if axis in (0, 'index'):
+            keep = ~self.index.isin(labels)
+            if errors == 'raise' and keep.sum() != len(self.index) - len(labels):
+                raise KeyError('labels not found in axis')
+            if keep.all():
+                return self
+            return CsrFrame(self.csr[:, np.flatnonzero(keep)], self.index[keep], self.columns)
+        keep = ~self.columns.isin(labels)
+        if errors == 'raise' and keep.sum() != len(self.columns) - len(labels):
+            raise KeyError('labels not found in axis')
+        if keep.all():
+            return self
+        return CsrFrame(self.csr[np.flatnonzero(keep)], self.index, self.columns[keep])
+
+    def __getitem__(self, mask):
+        """frame[bool mask over genes] -> the selected genes (dr.py:319: data[data.index.isin(hvg)])."""
+        mask = np.asarray(mask)
+        if mask.dtype != bool or mask.shape[0] != len(self.index):
+            raise KeyError('CsrFrame supports selection of genes by a boolean mask only')
+        return CsrFrame(self.csr[:, np.flatnonzero(mask)], self.index[mask], self.columns)
+
+    def select_cells(self, mask):
+        """The cells where the boolean mask is set (frame.loc[:, mask] of the reference, plotting.py:298)."""
+        mask = np.asarray(mask, dtype=bool)
+        return CsrFrame(self.csr[np.flatnonzero(mask)], self.index, self.columns[mask])
+
+    def to_frame(self):
+        df = pd.DataFrame.sparse.from_spmatrix(self.csr.T.tocsc(), index=self.index, columns=self.columns)
+        return df.astype(pd.SparseDtype(self.csr.dtype, 0))
+
+    def __repr__(self):
+        return 'CsrFrame(%d genes x %d cells, %d non-zeros, %s)' % (self.shape + (self.csr.nnz, self.csr.dtype))
+
+
 class dataset:
     def __init__(self, raw_mat, desc='no desc set', output_file=None, input_file=None, sparse=True, verbose=False):
         self.sparse = sparse
@@ -17,7 +77,9 @@ class dataset:
         self.output_file = output_file
         self.input_file = input_file
         self._assays = {}
-        if sparse and not all(isinstance(t, pd.SparseDtype) for t in raw_mat.dtypes.unique()):
+        if isinstance(raw_mat, CsrFrame):
+            self.count_data = raw_mat                                        # no pandas frame at all
+        elif sparse and not all(isinstance(t, pd.SparseDtype) for t in raw_mat.dtypes.unique()):
             self.count_data = raw_mat.astype(pd.SparseDtype('int', 0))      # data.py:67
         else:
             self.count_data = raw_mat
@@ -38,14 +100,17 @@ class dataset:
         self.version = 'adobo_b200'
 
     @classmethod
-    def from_csr(cls, counts, genes=None, cells=None, **kw):
-        """counts: scipy CSR cells x genes."""
+    def from_csr(cls, counts, genes=None, cells=None, frame='auto', **kw):
+        """counts: scipy CSR cells x genes.  frame=True builds the pandas sparse frame the reference holds
+        (data.py:67); frame=False keeps the matrix as a CsrFrame -- no per-cell pandas objects, the only way to hold
+        BASELINE's 68 k- and 1.3 M-cell shapes; 'auto' = a pandas frame up to 10,000 cells."""
         counts = sp.csr_matrix(counts)
         genes = genes if genes is not None else ['g%d' % i for i in range(counts.shape[1])]
         cells = cells if cells is not None else ['c%d' % i for i in range(counts.shape[0])]
-        df = pd.DataFrame.sparse.from_spmatrix(counts.T.tocsc(), index=genes, columns=cells)
-        df = df.astype(pd.SparseDtype(counts.dtype, 0))
-        return cls(df, **kw)
+        if frame == 'auto':
+            frame = counts.shape[0] <= 10000
+        cf = CsrFrame(counts, genes, cells)
+        return cls(cf.to_frame() if frame else cf, **kw)
 
     @classmethod
     def from_matrix_market(cls, filename, **kw):
@@ -85,8 +150,10 @@ class dataset:
 
 
 def frame_to_csr(df):
-    """genes x cells frame (pandas sparse or dense) -> scipy CSR cells x genes.  A pandas sparse
+    """genes x cells frame (pandas sparse or dense, or a CsrFrame) -> scipy CSR cells x genes.  A pandas sparse
     frame stores one SparseArray per cell, i.e. it already is CSR(cells x genes)."""
+    if isinstance(df, CsrFrame):
+        return df.csr
     if len(df.dtypes) and all(isinstance(t, pd.SparseDtype) for t in df.dtypes.unique()):
         m = df.sparse.to_coo().T.tocsr()
     else:
@@ -95,8 +162,10 @@ def frame_to_csr(df):
     return m
 
 
-def csr_to_frame(m, genes, cells):
+def csr_to_frame(m, genes, cells, like=None):
     """scipy CSR cells x genes (float64) -> genes x cells frame with Sparse[float64, 0] columns
-    (normalize.py:567-568)."""
+    (normalize.py:567-568); a CsrFrame when `like` is one."""
+    if isinstance(like, CsrFrame):
+        return CsrFrame(m, genes, cells)
     df = pd.DataFrame.sparse.from_spmatrix(sp.csc_matrix(m.T), index=genes, columns=cells)
     return df.astype(pd.SparseDtype('float64', 0))

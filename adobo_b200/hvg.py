@@ -6,13 +6,13 @@ import numpy as np
 
 from . import engine as _engine
 from .data import frame_to_csr
-from .normalize import _frame_key
+from .normalize import ResidentKey
 
 
 def _ensure_resident(eng, data):
-    key = _frame_key(data)
-    if eng.resident_key != key:
-        eng.upload_normalized(frame_to_csr(data), key=key)
+    key = eng.resident_key
+    if not (isinstance(key, ResidentKey) and key.matches(data)):
+        eng.upload_normalized(frame_to_csr(data), key=ResidentKey(data))
 
 
 def seurat(data, ngenes=1000, num_bins=20, eng=None):

@@ -10,7 +10,7 @@ import numpy as np
 import pandas as pd
 
 from . import engine as _engine
-from .data import frame_to_csr, csr_to_frame
+from .data import frame_to_csr, csr_to_frame, CsrFrame
 
 _LOG_MODES = {np.log2: (_engine.LOG_2, 0.0), np.log: (_engine.LOG_E, 0.0), np.log10: (_engine.LOG_10, 0.0),
               np.log1p: (_engine.LOG_E, 1.0)}
@@ -55,7 +55,7 @@ def standard(data, scaling_factor=10000, eng=None):
     counts = frame_to_csr(data)
     eng.upload_counts(counts)
     vals, _ = eng.normalize(scaling_factor, _engine.LOG_NONE, 1.0)
-    return csr_to_frame(vals, data.index, data.columns)
+    return csr_to_frame(vals, data.index, data.columns, like=data)
 
 
 def norm(obj, method='standard', name=None, use_imputed=False, log=True, log_func=np.log2, small_const=1,
@@ -82,23 +82,54 @@ def norm(obj, method='standard', name=None, use_imputed=False, log=True, log_fun
     counts = frame_to_csr(data)
     eng.upload_counts(counts)
     vals, _ = eng.normalize(scaling_factor, mode, sc)
-    normf = csr_to_frame(vals, data.index, data.columns)
+    normf = csr_to_frame(vals, data.index, data.columns, like=data)
     ne = None
     ercc = obj.meta_genes.ERCC.reindex(normf.index)
     if np.any(ercc == True):  # noqa: E712             # normalize.py:562-566
         flag = (ercc == True).values  # noqa: E712
         ne = normf[flag]
         normf = normf[np.logical_not(flag)]
-    elif not getattr(obj, 'sparse', True):
+    elif not getattr(obj, 'sparse', True) and not isinstance(normf, CsrFrame):
         normf = normf.sparse.to_dense()
     obj.norm_data[name] = {'data': normf, 'method': method, 'log': log, 'norm_ercc': ne, 'dr': {},
                            'clusters': {}, 'slingshot': {}, 'de': {}, 'combat': {}}
     if ne is None:
-        eng.resident_key = _frame_key(normf)          # the matrix on the device is this normalization
+        eng.resident_key = ResidentKey(normf)         # the matrix on the device is this normalization
     obj.set_assay(sys._getframe().f_code.co_name, 'standard')
     if retx:
         return normf
 
 
-def _frame_key(df):
-    return (id(df), df.shape)
+class ResidentKey:
+    """Identifies the normalized frame whose matrix is resident on the device, so that find_hvg / pca after norm
+    skip the upload.  A WEAK reference compared with `is` (CPython re-uses id()s of collected frames: a fresh frame
+    of the same shape -- dr.jackstraw makes one per permutation -- must never be taken for the resident one) plus a
+    content fingerprint of a fixed sample of cells, which catches in-place edits of norm_data[..]['data']."""
+
+    def __init__(self, df):
+        import weakref
+        try:
+            self.ref = weakref.ref(df)
+        except TypeError:
+            self.ref = None
+        self.fp = _fingerprint(df)
+
+    def matches(self, df):
+        return self.ref is not None and self.ref() is df and self.fp == _fingerprint(df)
+
+
+def _fingerprint(df):
+    if isinstance(df, CsrFrame):
+        m = df.csr
+        pos = np.linspace(0, max(m.nnz - 1, 0), num=min(m.nnz, 64), dtype=np.int64)
+        return (df.shape, int(m.nnz), float(m.data[pos].sum()) if m.nnz else 0.0, int(m.indices[pos].sum()) if m.nnz else 0)
+    n = df.shape[1]
+    cols = np.unique(np.linspace(0, max(n - 1, 0), num=min(n, 16), dtype=np.int64)) if n else []
+    acc = [df.shape]
+    for c in cols:
+        a = df.iloc[:, c].array
+        if isinstance(a, pd.arrays.SparseArray):
+            acc.append((int(a.sp_index.npoints), float(np.asarray(a.sp_values).sum())))
+        else:
+            acc.append((len(a), float(np.asarray(a).sum())))
+    return tuple(acc)

@@ -102,3 +102,35 @@ def test_synth_blocks_are_shard_reproducible():
     assert (full[1000:2300] != part).nnz == 0
     assert full.indices.dtype == np.int32 and full.data.dtype == np.int32
     assert np.all(np.asarray(full.sum(axis=1)).ravel() > 0)
+
+
+def test_csr_backed_dataset_matches_frame_backed():
+    """f1: a dataset without any pandas frame (CsrFrame) carries the same metadata and masks as the frame-backed one."""
+    from adobo_b200.data import dataset, CsrFrame, frame_to_csr
+    from adobo_b200.normalize import clean_matrix, ResidentKey
+    from adobo_b200.synth import synth_counts
+    counts = synth_counts(40, 60, 0.15, seed=3)
+    a = dataset.from_csr(counts, frame=True)
+    b = dataset.from_csr(counts, frame=False)
+    assert isinstance(b.count_data, CsrFrame) and b.count_data.shape == a.count_data.shape == (60, 40)
+    assert list(b.count_data.index) == list(a.count_data.index) and list(b.count_data.columns) == list(a.count_data.columns)
+    pd.testing.assert_frame_equal(a.meta_cells, b.meta_cells)
+    pd.testing.assert_frame_equal(a.meta_genes, b.meta_genes)
+    for exp in (a, b):
+        exp.meta_cells.loc[exp.meta_cells.index[3], 'status'] = 'EXCLUDE'
+        exp.meta_genes.loc[exp.meta_genes.index[5], 'status'] = 'EXCLUDE'
+        exp.meta_genes.loc[exp.meta_genes.index[7], 'mitochondrial'] = True
+    ca, cb = clean_matrix(a.count_data, a), clean_matrix(b.count_data, b)
+    assert cb.shape == ca.shape == (58, 39) and list(cb.index) == list(ca.index) and list(cb.columns) == list(ca.columns)
+    assert (frame_to_csr(ca) != frame_to_csr(cb)).nnz == 0
+    sel = cb[cb.index.isin(['g1', 'g9', 'g11'])]
+    assert sel.shape == (3, 39) and (sel.csr != cb.csr[:, cb.index.get_indexer(['g1', 'g9', 'g11'])]).nnz == 0
+    assert (frame_to_csr(cb.to_frame()) != cb.csr).nnz == 0
+    # resident-matrix key: identity, not id(); content changes are seen
+    k = ResidentKey(cb)
+    assert k.matches(cb) and not k.matches(CsrFrame(cb.csr.copy(), cb.index, cb.columns))
+    cb.csr.data[0] += 1
+    assert not k.matches(cb)
+    fa = ca
+    kf = ResidentKey(fa)
+    assert kf.matches(fa) and not kf.matches(fa.copy())

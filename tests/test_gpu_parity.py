@@ -258,3 +258,100 @@ def test_irlb_runahead_is_the_synchronous_loop(eng, maxit, monkeypatch):
     assert (fast['steps'], fast['nmult']) == (slow['steps'], slow['nmult'])
     assert np.array_equal(fast['s'], slow['s'])
     assert np.array_equal(fast['comp'], slow['comp']) and np.array_equal(fast['contr'], slow['contr'])
+
+
+def test_api_on_csr_backed_dataset(eng):
+    """f1: the same calls on a dataset that holds no pandas frame (CsrFrame) give the frame-backed results; find_hvg
+    / pca after norm reuse the matrix left on the device (ResidentKey), a different frame of the same shape does not."""
+    import adobo_b200 as ad
+    from adobo_b200 import engine as E
+    from adobo_b200.data import CsrFrame, frame_to_csr
+    E.set_default_engine(eng)
+    case = P.load_case('small')
+    a = ad.data.dataset.from_csr(case['counts_csr'], frame=True)
+    b = ad.data.dataset.from_csr(case['counts_csr'], frame=False)
+    for exp in (a, b):
+        ad.normalize.norm(exp)
+        ad.hvg.find_hvg(exp, ngenes=case['ngenes'])
+        ad.dr.pca(exp, ncomp=case['ncomp'])
+        ad.clustering.generate(exp, k=case['k'], clust_alg=None)
+    na, nb = a.norm_data['standard'], b.norm_data['standard']
+    assert isinstance(nb['data'], CsrFrame)
+    assert np.array_equal(frame_to_csr(na['data']).data, nb['data'].csr.data)
+    assert list(na['hvg']['genes']) == list(nb['hvg']['genes'])
+    assert np.array_equal(na['dr']['pca']['comp'].values, nb['dr']['pca']['comp'].values)          # same bits
+    assert list(nb['dr']['pca']['contr'].index) == list(na['dr']['pca']['contr'].index)
+    assert na['graph'].equals(nb['graph'])
+    # a fresh frame of the same shape must be uploaded, not mistaken for the resident one
+    other = CsrFrame(nb['data'].csr.power(3), nb['data'].index, nb['data'].columns)
+    g1 = ad.hvg.seurat(nb['data'], case['ngenes'])
+    g2 = ad.hvg.seurat(other, case['ngenes'])
+    g3 = ad.hvg.seurat(nb['data'], case['ngenes'])
+    assert list(g1) == list(g3) and list(g1) == list(nb['hvg']['genes'])
+    assert list(g2) != list(g1)                     # other values: other dispersions, other ranking
+
+
+def test_snn_counts_are_the_reference_matrix_entries(eng):
+    """north_star: 'SNN edge weights bit-exact' -- V_ij = (M M^T)_ij of every kept edge against the oracle's sparse
+    product (the reference computes V and keeps only its coordinates, clustering.py:99-112)."""
+    from oracle import adobo_oracle as O
+    for name in ('ragged', 'medium'):
+        case = P.load_case(name)
+        edges, pruned, total, ne = eng.snn(case['nn_idx'], case['k'], 0.067)
+        e2, v = eng.fetch_edges(counts=True)
+        assert np.array_equal(e2, edges)
+        V = O.snn_counts(case['nn_idx'])
+        ref = np.asarray(V[edges[:, 0], edges[:, 1]]).ravel()
+        appended = (edges[:, 0] == edges[:, 1]) & (v == 0)            # nodes without any kept edge (clustering.py:114-118)
+        assert np.array_equal(v[~appended], ref[~appended]) and v[~appended].min() >= 1 and v.max() <= case['k']
+
+
+def test_impute_subpopulations_front_half(eng):
+    """f4: preproc.impute's subpopulation estimate (preproc.py:461-488) through the GPU path against the oracle run on
+    the DENSE lnorm = log10(cpm + 1.01) the reference forms (every zero becomes log10(1.01))."""
+    import adobo_b200 as ad
+    from oracle import adobo_oracle as O
+    case = P.load_case('small')
+    counts = case['counts_csr']
+    exp = ad.data.dataset.from_csr(counts, frame=False)
+    out = ad.preproc.impute_subpopulations(exp, ncomp=20, seed=11, clust_alg=None, verbose=False, eng=eng)
+    lib = np.asarray(counts.sum(axis=1)).ravel().astype(np.float64)
+    dense = np.log10(np.asarray(counts.todense(), dtype=np.float64) * (10 ** 6 / lib)[:, None] + 1.01)   # preproc.py:470-472
+    lnorm = sp.csr_matrix(dense)
+    mean, var = O.gene_moments(lnorm)
+    z, bins = O.seurat_zscores(mean, var)
+    hv = O.seurat_order(z, bins, 1000)
+    assert sorted(int(g[1:]) for g in out['hvg']) == sorted(hv.tolist())
+    o = O.irlb_pca(lnorm, hv, ncomp=20, seed=11)
+    assert np.max(P.component_err(out['comp'].values, o['comp'])[:12]) < 1e-4
+    P.assert_knn_equal(eng.knn(o['comp'], 10), O.knn(o['comp'], 10), o['comp'])
+    assert list(out['graph'].columns) == ['source_node', 'target_node'] and out['nn_idx'].shape == (case['n'], 10)
+
+
+def test_pca_contributors_table_per_cluster(eng):
+    """f4: plotting.pca_contributors' data half; the per-cluster case re-runs irlb on the cluster's cells
+    (plotting.py:298-303)."""
+    import adobo_b200 as ad
+    import pandas as pd
+    from adobo_b200 import engine as E
+    E.set_default_engine(eng)
+    case = P.load_case('small')
+    exp = ad.data.dataset.from_csr(case['counts_csr'], frame=True)
+    ad.normalize.norm(exp)
+    ad.hvg.find_hvg(exp, ngenes=case['ngenes'])
+    ad.dr.pca(exp, ncomp=case['ncomp'])
+    nd = exp.norm_data['standard']
+    tab = ad.plotting.pca_contributors_table(exp, dim=[0, 3], top=5)
+    s0 = nd['dr']['pca']['contr'][0].sort_values(ascending=False)
+    assert list(tab[0].index) == list(s0.head(5).index) + list(s0.tail(5).index)
+    cl = pd.Series(np.arange(case['n']) % 3, index=nd['data'].columns)
+    nd['clusters']['leiden'] = {'membership': cl}
+    tab1 = ad.plotting.pca_contributors_table(exp, cluster=1, dim=[0], top=5)
+    X_ss = nd['data'].loc[:, (cl == 1).to_numpy()]
+    X_ss = X_ss[X_ss.index.isin(nd['hvg']['genes'])]
+    np.random.seed(None)
+    _, contr = ad.dr.irlb(X_ss, seed=None)
+    # the start vector is random (seed=None, like the reference): compare the leading loadings up to sign
+    a, b = tab1[0], contr[0]
+    assert set(a.index) <= set(b.index)
+    assert np.allclose(np.abs(a.values), np.abs(b.loc[a.index].values), rtol=1e-3, atol=1e-6)
