@@ -72,6 +72,10 @@ SIGNATURES = {
     'adobo_irlb': (C.c_int, [ctx_p, _arr(_i32), C.c_int32, C.c_int32, C.c_double, C.c_int32, _arr(_f64), C.c_int32,
                              C.c_int32, _OptArr(_f64, 2), _OptArr(_f64), _OptArr(_f64, 2), C.POINTER(C.c_int32),
                              C.POINTER(C.c_int32)]),
+    'adobo_gather_subset': (C.c_int, [ctx_p, _arr(_i32), C.c_int32, C.c_int32]),
+    'adobo_irlb_permuted': (C.c_int, [ctx_p, _OptArr(_i32), C.c_int32, C.c_uint64, C.c_int32, C.c_double, C.c_int32, _arr(_f64),
+                                      C.c_int32, _OptArr(_f64, 2), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    'adobo_perm_row': (C.c_int64, [C.c_int64, C.c_uint64, C.c_int32, C.c_int64]),
     'adobo_lanczos_csr': (C.c_int, [ctx_p, C.c_int64, C.c_int32, _arr(_i64), _arr(_i32), _arr(_f64), C.c_int32,
                                     C.c_double, C.c_int32, _arr(_f64), _OptArr(_f64, 2), _OptArr(_f64),
                                     _OptArr(_f64, 2), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

@@ -622,6 +622,43 @@ int adobo_irlb(adobo_ctx* c, const int32_t* gene_idx, int32_t h, int32_t ncomp, 
   API_END
 }
 
+int adobo_gather_subset(adobo_ctx* c, const int32_t* gene_idx, int32_t h, int32_t scale) {
+  API_BEGIN
+  CUDA_CHECK(cudaSetDevice(c->device));
+  REQUIRE(gene_idx && h >= 1, ADOBO_ERR_ARG, "gather_subset: gene_idx missing");
+  std::vector<int> genes(gene_idx, gene_idx + h);
+  std::sort(genes.begin(), genes.end());
+  run_gather_subset(c, genes, scale != 0);
+  API_END
+}
+
+int adobo_irlb_permuted(adobo_ctx* c, const int32_t* perm_cols, int32_t n_perm, uint64_t perm_seed, int32_t ncomp, double tol,
+                        int32_t maxit, const double* v0, int32_t var_weigh, double* out_contr, int32_t* out_steps,
+                        int32_t* out_nmult) {
+  API_BEGIN
+  CUDA_CHECK(cudaSetDevice(c->device));
+  REQUIRE(v0 && n_perm >= 0 && (perm_cols || n_perm == 0), ADOBO_ERR_ARG, "irlb_permuted: bad arguments");
+  const int h = c->sub.cols;
+  // the two-kernel Lanczos step reads the CSR only; the other paths (h > 1024, hooks) also need the CSC copy
+  const bool need_csc = h > 1024 || getenv("ADOBO_B200_IRLB") != nullptr;
+  run_permute_subset(c, perm_cols, n_perm, perm_seed, need_csc);
+  if (!need_csc) {  // never read on this path; keep the signature of the workspace stable across permutations
+    c->perm.cptr.ensure(1), c->perm.ridx.ensure(1), c->perm.cval.ensure(1);
+  }
+  IrlbResult r = run_irlb<float>(c, c->perm, c->sub_scaled ? c->mu.p : nullptr, c->sub_scaled ? c->rs.p : nullptr, ncomp, tol,
+                                 maxit, v0, var_weigh != 0, c->perm_u, c->perm_s, c->perm_v);
+  if (out_contr) CUDA_CHECK(cudaMemcpyAsync(out_contr, c->perm_v.p, sizeof(double) * (size_t)h * ncomp, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (out_steps) *out_steps = r.steps;
+  if (out_nmult) *out_nmult = r.nmult;
+  API_END
+}
+
+int64_t adobo_perm_row(int64_t n_cells, uint64_t perm_seed, int32_t col, int64_t row) {
+  if (n_cells < 1 || row < 0 || row >= n_cells) return -1;
+  return perm_apply(perm_key(perm_seed, col), n_cells, row);
+}
+
 int adobo_lanczos_csr(adobo_ctx* c, int64_t rows, int32_t cols, const int64_t* indptr, const int32_t* indices,
                       const double* values, int32_t nval, double tol, int32_t maxit, const double* v0, double* out_U,
                       double* out_s, double* out_V, int32_t* out_steps, int32_t* out_nmult) {

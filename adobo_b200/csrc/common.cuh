@@ -150,6 +150,9 @@ struct adobo_ctx {
   adobo::DevBuf<int> sub_genes;  // ascending gene ids (h)
   std::vector<int> h_sub_genes;
   adobo::DevBuf<double> mu, rs;  // per-column mean and 1/sigma
+  adobo::SparsePair<float> perm; // dr.jackstraw: the subset with some genes permuted across cells
+  adobo::DevBuf<double> perm_u, perm_s, perm_v;  // its IRLB outputs (the real PCA stays in comp / contr / sv)
+  bool sub_scaled = false;       // statistics of `sub` are those of scale=True
   int p = 0;                     // components of the last PCA
   adobo::DevBuf<double> comp;    // n x p row-major
   adobo::DevBuf<double> contr;   // h x p row-major
@@ -182,6 +185,48 @@ struct adobo_ctx {
 };
 
 namespace adobo {
+
+// ---- dr.jackstraw: keyed bijection of [0, n) (adobo_perm_row) ---------------------------------------------------
+// Four rounds of (odd multiply + add, xor-shift) on the smallest power-of-two domain that holds n, cycle-walked back
+// into [0, n): every step is invertible, so distinct cells go to distinct cells.  Keys come from splitmix64 of
+// (seed, gene); the same code runs on the host (tests, adobo_perm_row) and on the device.
+struct PermKey {
+  unsigned long long mul[4], add[4];
+};
+#ifdef __CUDACC__
+#define ADOBO_HD __host__ __device__ __forceinline__
+#else
+#define ADOBO_HD inline
+#endif
+ADOBO_HD unsigned long long perm_splitmix(unsigned long long& x) {
+  unsigned long long z = (x += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+ADOBO_HD PermKey perm_key(unsigned long long seed, int col) {
+  unsigned long long st = seed ^ (0xD1B54A32D192ED03ull * (unsigned long long)(col + 1));
+  PermKey k;
+  for (int r = 0; r < 4; ++r) {
+    k.mul[r] = perm_splitmix(st) | 1ull;
+    k.add[r] = perm_splitmix(st);
+  }
+  return k;
+}
+ADOBO_HD long long perm_apply(const PermKey& k, long long n, long long row) {
+  int bits = 1;
+  while ((1ll << bits) < n) ++bits;
+  const unsigned long long mask = (1ull << bits) - 1ull;
+  const int sh = bits > 1 ? bits / 2 : 1;
+  unsigned long long x = (unsigned long long)row;
+  do {
+    for (int r = 0; r < 4; ++r) {
+      x = (x * k.mul[r] + k.add[r]) & mask;
+      x ^= x >> sh;
+    }
+  } while ((long long)x >= n);
+  return (long long)x;
+}
 
 // ---- launch bookkeeping ---------------------------------------------------------------------
 void prof_begin(adobo_ctx* c, const char* name);
@@ -216,6 +261,7 @@ void run_normalize(adobo_ctx* c, double scaling, int log_mode, double small_cons
 void run_moments(adobo_ctx* c);
 void run_seurat_host(adobo_ctx* c, int ngenes, int num_bins, std::vector<int>& order, std::vector<double>& z);
 void run_gather_subset(adobo_ctx* c, const std::vector<int>& genes_sorted, bool scale);
+void run_permute_subset(adobo_ctx* c, const int* perm_cols, int n_perm, uint64_t seed, bool need_csc);  // gather.cu
 
 struct IrlbResult {
   int steps = 0, nmult = 0, svd_fallbacks = 0;

@@ -219,6 +219,81 @@ void compute_scale_stats(adobo_ctx* c, SparsePair<float>& A, bool scale, DevBuf<
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
 }
 
+// ---- dr.jackstraw: the subset with some genes permuted across cells (dr.py:606-613) ---------------------------------
+// One CTA per gene column of the CSC copy: entry (row r, gene j) gets the sort key (new row << 32 | j); unselected
+// genes keep their rows.  A radix sort by key is the permuted matrix in CSR order (columns ascending inside a row:
+// the summation order of the mat-vecs stays a pure function of the matrix).
+__global__ void __launch_bounds__(256) perm_keys(const i64* __restrict__ cptr, const int* __restrict__ ridx,
+                                                 const float* __restrict__ cval, const int* __restrict__ selmap,
+                                                 unsigned long long seed, i64 n, unsigned long long* __restrict__ keys,
+                                                 float* __restrict__ vals) {
+  const int col = blockIdx.x;
+  const bool sel = selmap[col] != 0;
+  const PermKey k = perm_key(seed, col);
+  for (i64 e = cptr[col] + threadIdx.x; e < cptr[col + 1]; e += 256) {
+    const i64 r = ridx[e];
+    const i64 nr = sel ? perm_apply(k, n, r) : r;
+    keys[e] = ((unsigned long long)nr << 32) | (unsigned)col;
+    vals[e] = cval[e];
+  }
+}
+
+// sorted (row << 32 | col) keys -> CSR: column ids, and row pointers from the row boundaries (empty rows included)
+__global__ void csr_from_sorted(const unsigned long long* __restrict__ keys, i64 nnz, i64 n, i64* __restrict__ rptr,
+                                int* __restrict__ cidx) {
+  for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (i64)gridDim.x * blockDim.x) {
+    const unsigned long long k = keys[e];
+    const i64 row = (i64)(k >> 32);
+    cidx[e] = (int)(k & 0xffffffffull);
+    const i64 prev = e == 0 ? -1 : (i64)(keys[e - 1] >> 32);
+    for (i64 r = prev + 1; r <= row; ++r) rptr[r] = e;   // rows (prev, row] start at e
+    if (e == nnz - 1)
+      for (i64 r = row + 1; r <= n; ++r) rptr[r] = nnz;
+  }
+}
+
+void run_permute_subset(adobo_ctx* c, const int* perm_cols, int n_perm, uint64_t seed, bool need_csc) {
+  SparsePair<float>& A = c->sub;
+  SparsePair<float>& P = c->perm;
+  REQUIRE(c->world == 1, ADOBO_ERR_STATE, "jackstraw permutations run on one GPU (give every GPU its own permutations)");
+  REQUIRE(A.rows > 0 && A.cols > 0, ADOBO_ERR_STATE, "jackstraw: no gene subset on the device (adobo_gather_subset / adobo_irlb first)");
+  const int h = A.cols;
+  std::vector<int> sel(h, 0);
+  for (int i = 0; i < n_perm; ++i) {
+    REQUIRE(perm_cols[i] >= 0 && perm_cols[i] < h, ADOBO_ERR_ARG, "jackstraw: gene position %d outside 0..%d", perm_cols[i], h - 1);
+    sel[perm_cols[i]] = 1;
+  }
+  DevBuf<int> dsel;
+  dsel.ensure((size_t)h);
+  CUDA_CHECK(cudaMemcpyAsync(dsel.p, sel.data(), sizeof(int) * h, cudaMemcpyHostToDevice, c->stream));
+  P.rows = A.rows;
+  P.cols = h;
+  P.nnz = A.nnz;
+  P.rptr.ensure((size_t)A.rows + 2);
+  P.cidx.ensure((size_t)std::max<i64>(A.nnz, 1));
+  P.rval.ensure((size_t)std::max<i64>(A.nnz, 1));
+  if (A.nnz == 0) {
+    CUDA_CHECK(cudaMemsetAsync(P.rptr.p, 0, sizeof(i64) * (A.rows + 1), c->stream));
+  } else {
+    DevBuf<unsigned long long> k_in, k_out;
+    DevBuf<float> v_in;
+    k_in.ensure((size_t)A.nnz);
+    k_out.ensure((size_t)A.nnz);
+    v_in.ensure((size_t)A.nnz);
+    LAUNCH(c, "perm_keys", (perm_keys<<<h, 256, 0, c->stream>>>(A.cptr.p, A.ridx.p, A.cval.p, dsel.p, seed, A.rows, k_in.p, v_in.p)));
+    int rbits = 1;
+    while ((1ll << rbits) < A.rows) ++rbits;
+    size_t bytes = 0;
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k_in.p, k_out.p, v_in.p, P.rval.p, (int)A.nnz, 0, 32 + rbits, c->stream));
+    c->scratch.ensure(bytes);
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(c->scratch.p, bytes, k_in.p, k_out.p, v_in.p, P.rval.p, (int)A.nnz, 0, 32 + rbits, c->stream));
+    c->launches += 3;
+    LAUNCH(c, "csr_from_sorted", (csr_from_sorted<<<c->sm_count * 4, 256, 0, c->stream>>>(k_out.p, A.nnz, A.rows, P.rptr.p, P.cidx.p)));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));  // temporaries die here
+  }
+  if (need_csc) build_csc<float>(c, P);
+}
+
 void run_gather_subset(adobo_ctx* c, const std::vector<int>& genes_sorted, bool scale) {
   REQUIRE(c->have_norm, ADOBO_ERR_STATE, "pca: no normalized matrix on the device");
   const int h = (int)genes_sorted.size();
@@ -259,6 +334,7 @@ void run_gather_subset(adobo_ctx* c, const std::vector<int>& genes_sorted, bool 
                                  c->indptr.p, c->indices.p, c->vals.p, dmap.p, A.rptr.p, A.cidx.p, A.rval.p, rowof.p, c->n)));
   build_csc_impl<float>(c, A, rowof.p);
   compute_scale_stats(c, A, scale, c->mu, c->rs);
+  c->sub_scaled = scale;
 }
 
 }  // namespace adobo

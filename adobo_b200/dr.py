@@ -109,6 +109,62 @@ def permute_gene_columns(sub_csc, cols, rng):
     return m
 
 
+# ---- the keyed bijection of [0, n) the DEVICE permutes with (csrc/common.cuh perm_key / perm_apply) -------------
+_M64 = (1 << 64) - 1
+
+
+def _splitmix(state):
+    state = (state + 0x9E3779B97F4A7C15) & _M64
+    z = state
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    return state, z ^ (z >> 31)
+
+
+def perm_rows(n, seed, col, rows):
+    """Where the cells `rows` send their entry of gene position `col` under permutation key `seed`: numpy
+    restatement of adobo_perm_row (four rounds of odd multiply + add and xor-shift on the smallest power-of-two
+    domain holding n, cycle-walked into [0, n)) -- used by the host path of jackstraw and by the tests."""
+    st = (int(seed) ^ ((0xD1B54A32D192ED03 * (int(col) + 1)) & _M64)) & _M64
+    mul, add = [], []
+    for _ in range(4):
+        st, z = _splitmix(st)
+        mul.append(z | 1)
+        st, z = _splitmix(st)
+        add.append(z)
+    bits = 1
+    while (1 << bits) < n:
+        bits += 1
+    mask = np.uint64((1 << bits) - 1)
+    sh = np.uint64(bits // 2 if bits > 1 else 1)
+    x = np.asarray(rows, dtype=np.uint64).copy()
+    todo = np.ones(x.shape, dtype=bool)
+    with np.errstate(over='ignore'):
+        while todo.any():
+            y = x[todo]
+            for r in range(4):
+                y = (y * np.uint64(mul[r]) + np.uint64(add[r])) & mask
+                y ^= y >> sh
+            x[todo] = y
+            todo[todo] = y >= np.uint64(n)
+    return x.astype(np.int64)
+
+
+def permute_gene_columns_keyed(sub_csc, cols, seed):
+    """The permutation the device applies (adobo_irlb_permuted), on a host CSC matrix: gene column j in `cols` has the
+    entry of cell r moved to cell perm_rows(n, seed, j, r)."""
+    import scipy.sparse as sp
+    m = sp.csc_matrix(sub_csc, copy=True)
+    n = m.shape[0]
+    for j in cols:
+        lo, hi = m.indptr[j], m.indptr[j + 1]
+        pos = perm_rows(n, seed, j, m.indices[lo:hi])
+        order = np.argsort(pos, kind='stable')
+        m.indices[lo:hi] = pos[order]
+        m.data[lo:hi] = m.data[lo:hi][order]
+    return m
+
+
 def jackstraw(obj, normalization=None, permutations=500, ncomp=None, subset_frac_genes=0.05, score_thr=1e-03,
               fdr=0.01, retx=True, verbose=False, seed=None, eng=None):
     """dr.jackstraw (dr.py:520-654, Chung & Storey 2015): empirical p-values of every HVG's loading on every
@@ -141,20 +197,29 @@ components computed by adobo.dr.pca(...)')
         raise Exception('Run adobo.dr.find_hvg() first.')
     keep = np.flatnonzero(X.index.isin(hvg))                 # dr.py:597: original gene order
     genes = X.index[keep]
-    sub = frame_to_csr(X)[:, keep].tocsc()                   # cells x h, sparse, unscaled
-    h = sub.shape[1]
+    h = keep.shape[0]
     nrand = int(round(h * subset_frac_genes))
     rng = np.random.default_rng(seed)
     eng = eng or _engine.default_engine()
+    on_device = hasattr(eng, 'irlb_permuted')                # the GPU engine permutes and rebuilds the matrix itself
+    if on_device:
+        _ensure_resident(eng, X)
+        eng.gather_subset(keep, scale=True)                  # subset + (mu, sigma) once; every permutation reuses them
+    else:
+        sub = frame_to_csr(X)[:, keep].tocsc()               # cells x h, sparse, unscaled
     perm_loadings = []
     for perm in range(permutations):
         if verbose:
             print('random set %s ' % perm)
         rand = np.sort(rng.choice(h, nrand, replace=False))  # dr.py:606; rows of contr come back in gene order (:616)
-        eng.upload_normalized(permute_gene_columns(sub, rand, rng).tocsr())
-        r = eng.irlb(np.arange(h), ncomp=ncomp, maxit=1000, seed=int(rng.integers(0, 2**31 - 1)), scale=True,
-                     var_weigh=True)
-        perm_loadings.append(np.abs(r['contr'][rand, :ncomp]))
+        pseed = int(rng.integers(0, 2 ** 63 - 1))            # key of this permutation's bijections (one per gene)
+        vseed = int(rng.integers(0, 2 ** 31 - 1))            # IRLB start vector (irlb.py:151-152)
+        if on_device:
+            contr = eng.irlb_permuted(rand, pseed, ncomp=ncomp, maxit=1000, seed=vseed, var_weigh=True)
+        else:
+            eng.upload_normalized(permute_gene_columns_keyed(sub, rand, pseed).tocsr())
+            contr = eng.irlb(np.arange(h), ncomp=ncomp, maxit=1000, seed=vseed, scale=True, var_weigh=True)['contr']
+        perm_loadings.append(np.abs(contr[rand, :ncomp]))
     null = np.concatenate(perm_loadings, axis=0) if perm_loadings else np.zeros((0, ncomp))
     real = np.asarray(loadings)[:, :ncomp]
     # empirical p-value of a loading: share of the null loadings of that component above it (dr.py:621-624)
@@ -178,7 +243,8 @@ components computed by adobo.dr.pca(...)')
     final['p.adj'] = _p_adjust_bh(final[1])
     final.columns = ['PC', 'chi2_p', 'chi2_p_adj']
     final['significant'] = final.chi2_p_adj < fdr
-    eng.resident_key = None                                  # the device holds the last permuted copy, not `X`
+    if not on_device:
+        eng.resident_key = None                              # the device holds the last permuted copy, not `X`
     obj.norm_data[norm]['dr']['jackstraw'] = {'score_mat': res, 'results_by_comp': final}
     if retx:
         return res, final

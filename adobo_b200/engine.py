@@ -198,6 +198,27 @@ class Engine:
                                   1 if var_weigh else 0, comp, s, contr, C.byref(steps), C.byref(nmult)))
         return dict(comp=comp, contr=contr, s=s, steps=steps.value, nmult=nmult.value, genes=np.sort(genes))
 
+    def gather_subset(self, genes, scale=True):
+        """Leaves the column subset `genes` of the resident normalized matrix (and its mu / sigma) on the device."""
+        genes = np.ascontiguousarray(genes, dtype=np.int32)
+        check(self.lib.adobo_gather_subset(self.h, genes, genes.shape[0], 1 if scale else 0))
+        self._subset_h = int(genes.shape[0])
+
+    def irlb_permuted(self, perm_cols, perm_seed, ncomp=75, tol=0.0001, maxit=1000, v0=None, seed=None, var_weigh=True):
+        """One dr.jackstraw permutation on the device (adobo_irlb_permuted): returns contr = V (h x ncomp)."""
+        h = self._subset_h
+        perm_cols = np.ascontiguousarray(perm_cols, dtype=np.int32)
+        if v0 is None:
+            np.random.seed(seed)                 # irlb.py:151-152
+            v0 = np.random.randn(h)
+        v0 = np.ascontiguousarray(v0, dtype=np.float64)
+        contr = np.empty((h, ncomp))
+        steps, nmult = C.c_int32(), C.c_int32()
+        check(self.lib.adobo_irlb_permuted(self.h, perm_cols, perm_cols.shape[0], int(perm_seed) & (2 ** 64 - 1), int(ncomp),
+                                           float(tol), int(maxit), v0, 1 if var_weigh else 0, contr, C.byref(steps),
+                                           C.byref(nmult)))
+        return contr
+
     def lanczos_csr(self, A, nval, tol=0.0001, maxit=50, seed=None, v0=None):
         m = as_csr(A)
         indptr = np.ascontiguousarray(m.indptr, dtype=np.int64)

@@ -128,6 +128,21 @@ int adobo_lanczos_csr(adobo_ctx* ctx, int64_t rows, int32_t cols, const int64_t*
                       int32_t maxit, const double* v0, double* out_U, double* out_s, double* out_V,
                       int32_t* out_steps, int32_t* out_nmult);
 
+/* ---- dr.jackstraw (adobo/dr.py:604-620): the 500 x irlb() multiplier of the hot path ------------------------ */
+/* adobo_gather_subset leaves the HVG column subset (ascending gene order) and its centring / scaling statistics on
+ * the device without running the PCA (what adobo_irlb does first).  adobo_irlb_permuted then runs ONE jackstraw
+ * permutation entirely on the device: the genes at positions perm_cols[0..n_perm) of the subset are permuted across
+ * cells -- gene j's entry of cell r moves to cell adobo_perm_row(n_cells, perm_seed, j, r), a keyed bijection of
+ * [0, n_cells) -- the permuted CSR is rebuilt by a key sort, and IRLB runs on it with the UNPERMUTED statistics (a
+ * permutation keeps a gene's mean and sigma, so this equals dr.py:606-617: permute rows of the scaled matrix, then
+ * irlb(scale=False)).  out_contr float64[h x ncomp] = V.  Single GPU (several GPUs take different permutations). */
+int adobo_gather_subset(adobo_ctx* ctx, const int32_t* gene_idx, int32_t h, int32_t scale);
+int adobo_irlb_permuted(adobo_ctx* ctx, const int32_t* perm_cols, int32_t n_perm, uint64_t perm_seed, int32_t ncomp,
+                        double tol, int32_t maxit, const double* v0, int32_t var_weigh, double* out_contr,
+                        int32_t* out_steps, int32_t* out_nmult);
+/* The bijection itself (host function, same arithmetic as the device): where cell `row`'s entry of gene `col` goes. */
+int64_t adobo_perm_row(int64_t n_cells, uint64_t perm_seed, int32_t col, int64_t row);
+
 /* ---- clustering.knn (adobo/clustering.py:25-52) -------------------------------------------- */
 /* Exact Euclidean k nearest neighbours of every row of comp among all rows (self included),
  * ascending by fp64 distance, 1-BASED like the reference (clustering.py:51).  comp float64

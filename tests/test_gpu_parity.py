@@ -355,3 +355,29 @@ def test_pca_contributors_table_per_cluster(eng):
     a, b = tab1[0], contr[0]
     assert set(a.index) <= set(b.index)
     assert np.allclose(np.abs(a.values), np.abs(b.loc[a.index].values), rtol=1e-3, atol=1e-6)
+
+
+def test_jackstraw_on_the_device_matches_the_oracle_engine(eng):
+    """f3: dr.jackstraw with every permutation made and decomposed on the device (adobo_irlb_permuted: keyed bijection
+    per gene, key sort back to CSR, IRLB with the unpermuted statistics) against the same call answered by the oracle
+    (host permutation with the numpy restatement of the bijection + CPU IRLB), same seed: same p-value table."""
+    import adobo_b200 as ad
+    from adobo_b200 import engine as E
+    from tests.test_jackstraw_host import OracleEngine
+    E.set_default_engine(eng)
+    case = P.load_case('small')
+    exp = ad.data.dataset.from_csr(case['counts_csr'], frame=True)
+    ad.normalize.norm(exp)
+    ad.hvg.find_hvg(exp, ngenes=case['ngenes'])
+    ad.dr.pca(exp, ncomp=8)
+    args = dict(permutations=12, ncomp=8, subset_frac_genes=0.1, score_thr=0.05, fdr=0.05, seed=5)
+    res_d, fin_d = ad.dr.jackstraw(exp, eng=eng, **args)
+    res_h, fin_h = ad.dr.jackstraw(exp, eng=OracleEngine(), **args)
+    nnull = 12 * int(round(case['ngenes'] * 0.1))
+    # empirical p-values are counts / nnull: a loading within 1e-4 of a null loading may fall on either side
+    assert np.max(np.abs(res_d.values - res_h.values)) <= 3.0 / nnull
+    assert np.mean(res_d.values == res_h.values) > 0.98
+    assert list(fin_d['significant']) == list(fin_h['significant'])
+    # the real PCA and the resident matrix survive the permutations
+    pca = eng.fetch_pca()
+    assert np.array_equal(pca['comp'], exp.norm_data['standard']['dr']['pca']['comp'].values)

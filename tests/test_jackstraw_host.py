@@ -43,6 +43,33 @@ def test_sparse_permutation_equals_permuting_the_scaled_dense_rows():
     del rng
 
 
+def test_keyed_bijection_matches_the_library_and_permutes():
+    """The permutation the DEVICE applies (adobo_irlb_permuted) is a keyed bijection of [0, n): its numpy restatement
+    (dr.perm_rows, used by the host path and as the checker) equals the library's own host function bit for bit."""
+    from adobo_b200 import _lib
+    lib = _lib.load()
+    for n in (1, 2, 3, 17, 1000, 20000):
+        for col in (0, 7, 999):
+            rows = np.arange(n)
+            got = dr.perm_rows(n, 0x1234567890ABCDEF, col, rows)
+            assert np.array_equal(np.sort(got), rows)                                   # a permutation of the cells
+            ref = np.array([lib.adobo_perm_row(n, 0x1234567890ABCDEF, col, int(r)) for r in rows[:500]])
+            assert np.array_equal(got[:500], ref)
+    a = dr.perm_rows(20000, 1, 0, np.arange(20000))
+    b = dr.perm_rows(20000, 1, 1, np.arange(20000))
+    c = dr.perm_rows(20000, 2, 0, np.arange(20000))
+    assert np.mean(a == b) < 0.01 and np.mean(a == c) < 0.01 and np.mean(a == np.arange(20000)) < 0.01
+    assert abs(np.corrcoef(a, np.arange(20000))[0, 1]) < 0.05                           # no visible structure
+    m = sp.random(300, 9, density=0.2, random_state=4, format='csc')
+    p = dr.permute_gene_columns_keyed(m, [1, 4], 99)
+    for j in range(9):
+        if j in (1, 4):
+            assert sorted(p[:, j].data.tolist()) == sorted(m[:, j].data.tolist())
+            assert np.array_equal(p[:, j].toarray().ravel()[dr.perm_rows(300, 99, j, np.arange(300))], m[:, j].toarray().ravel())
+        else:
+            assert np.array_equal(p[:, j].toarray(), m[:, j].toarray())
+
+
 def test_bh_adjustment_matches_the_reference_formula():
     p = np.array([0.01, 0.04, 0.03, 0.20, np.nan, 0.5])
     q = dr._p_adjust_bh(p)
