@@ -56,10 +56,13 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc] + ARCH + ['-shared', '-o', OUT] + objs + ['-ldl']
+    # link beside the target and rename: the library on disk is always a complete file (a snapshot of the tree may be
+    # taken for a GPU run at any moment)
+    cmd = [nvcc] + ARCH + ['-shared', '-o', OUT + '.tmp'] + objs + ['-ldl']
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n' + r.stderr[-4000:])
+    os.replace(OUT + '.tmp', OUT)
     if verbose:
         print('built', OUT)
     return OUT

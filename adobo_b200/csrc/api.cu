@@ -231,7 +231,8 @@ static void setup_peer(adobo_ctx* c) {
   const int W = c->world;
   const size_t data_bytes = sizeof(double) * 2 * (size_t)W * (2 * PEER_SLOT);
   const size_t flag_bytes = sizeof(unsigned) * 2 * (size_t)W * PEER_CH * 32;
-  const size_t bytes = data_bytes + flag_bytes + 256;  // + the PEER_CH sequence counters
+  const size_t ll_bytes = sizeof(uint4) * 2 * (size_t)W * PEER_CH * PEER_LL_MAX;
+  const size_t bytes = data_bytes + flag_bytes + 256 + ll_bytes;  // 256: the PEER_CH sequence counters
   void* mb = nullptr;
   CUDA_CHECK(cudaMalloc(&mb, bytes));
   CUDA_CHECK(cudaMemset(mb, 0, bytes));
@@ -253,6 +254,7 @@ static void setup_peer(adobo_ctx* c) {
     if (r != c->rank) CUDA_CHECK(cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess));
     pc.data[r] = (double*)ptr;
     pc.flags[r] = (unsigned*)((char*)ptr + data_bytes);
+    pc.ll[r] = (uint4*)((char*)ptr + data_bytes + flag_bytes + 256);
   }
   pc.seq = (unsigned*)((char*)mb + data_bytes + flag_bytes);
   // nobody may write into a mailbox before every rank has zeroed and mapped it

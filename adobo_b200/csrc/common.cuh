@@ -108,11 +108,13 @@ constexpr int PEER_SLOT = 4096;    // doubles per rank slot on channel 0: larger
 constexpr int PEER_CTAS = 8;       // cluster CTAs with a channel of their own
 constexpr int PEER_CH = 1 + PEER_CTAS;
 constexpr int PEER_CH_SLOT = PEER_SLOT / PEER_CTAS;  // 512 doubles per cluster-CTA channel
+constexpr int PEER_LL_MAX = 256;   // doubles per low-latency message (peer_allreduce_ll)
 constexpr unsigned long long PEER_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;  // a peer that is 20 s late is dead
 struct PeerComm {
   int world = 1, rank = 0;
   double* data[PEER_MAX] = {};     // mailbox of every rank (peer pointers through CUDA IPC)
   unsigned* flags[PEER_MAX] = {};  // [2][world][PEER_CH] sequence flags, 128 bytes apart
+  uint4* ll[PEER_MAX] = {};        // [2][world][PEER_CH][PEER_LL_MAX] flagged words of the low-latency exchange
   unsigned* seq = nullptr;         // [PEER_CH] this rank's sequence counters (device)
   int* err = nullptr;              // raised when a peer did not answer within PEER_TIMEOUT_NS (the kernel goes on
                                    // with garbage instead of hanging the GPU; the host turns it into an error)
@@ -355,6 +357,51 @@ __device__ __forceinline__ void peer_allreduce_block(const PeerComm& pc, double*
   for (int i = threadIdx.x; i < count; i += blockDim.x) {
     double s = 0;
     for (int r = 0; r < W; ++r) s += __ldcv(mine + (size_t)r * (2 * PEER_SLOT) + i);
+    vec[i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) pc.seq[ch] = seq;
+}
+
+// ---- the same exchange without fence and flag round trip: every double travels as ONE 16-byte store {lo, seq, hi, seq}
+// (each 8-byte half carries its own copy of the sequence number, so the message is self-validating however the
+// store is split on the way: the protocol of NCCL's LL).  The receiver polls the words themselves: one NVLink
+// crossing per exchange instead of data + system fence + flag.  vec: shared memory of the calling CTA, count <=
+// PEER_LL_MAX; parity double buffering as above.
+__device__ __forceinline__ void peer_allreduce_ll(const PeerComm& pc, double* vec, int count, int ch) {
+  __shared__ unsigned s_seq_ll;
+  const int W = pc.world, me = pc.rank;
+  if (threadIdx.x == 0) s_seq_ll = pc.seq[ch] + 1u;
+  __syncthreads();
+  const unsigned seq = s_seq_ll;
+  const int par = (int)(seq & 1u);
+  const int i = threadIdx.x;
+  if (i < count) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(vec[i]);
+    const unsigned lo = (unsigned)bits, hi = (unsigned)(bits >> 32);
+    for (int r = 0; r < W; ++r) {
+      uint4* dst = pc.ll[r] + ((size_t)(par * W + me) * PEER_CH + ch) * PEER_LL_MAX + i;
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(lo), "r"(seq), "r"(hi), "r"(seq) : "memory");
+    }
+    double s = 0;
+    unsigned long long t0 = 0;
+    for (int r = 0; r < W; ++r) {  // rank order: the same sum on every rank
+      const uint4* src = pc.ll[me] + ((size_t)(par * W + r) * PEER_CH + ch) * PEER_LL_MAX + i;
+      unsigned a, b, c, d, polls = 0;
+      for (;;) {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(src) : "memory");
+        if (b == seq && d == seq) break;
+        if ((++polls & 1023u) == 0) {
+          const unsigned long long now = peer_now_ns();
+          if (t0 == 0) t0 = now;
+          if (now - t0 > PEER_TIMEOUT_NS) {
+            if (pc.err) atomicExch(pc.err, 1 + r);
+            break;
+          }
+        }
+      }
+      s += __longlong_as_double((long long)(((unsigned long long)c << 32) | a));
+    }
     vec[i] = s;
   }
   __syncthreads();

@@ -186,11 +186,11 @@ __global__ void __launch_bounds__(W2_THREADS, 1)
 // through distributed shared memory) with a new front end: CTA c of the cluster first adds the CTA partials of ITS
 // h / 8 rows of t, of the two scalars (||y||^2, sum y) and of every 8th column of g = W^T y -- 18 coalesced loads per
 // thread, in one batch -- and, with several GPUs, exchanges that slice with the same CTA of every peer over NVLink
-// (channel 1 + c of the mailbox: eight exchanges in flight, ONE round trip per Lanczos step where there were two,
-// each behind a serial last-CTA sum).  Every rank adds the slices in rank order: V, Z, B stay bit-identical.
+// (channel 1 + c of the mailbox, self-validating 16-byte words -- peer_allreduce_ll: eight exchanges in flight, ONE
+// NVLink crossing per Lanczos step where there were two round trips, each behind a serial last-CTA sum).  Every rank adds the slices in rank order: V, Z, B stay bit-identical.
 constexpr int VT_G0 = MAXB;                  // msg[0 .. 128): rows of t;  msg[128], msg[129]: ||y||^2, sum y;
 constexpr int VT_MSG = VT_G0 + 2 + 16;       // msg[130 .. 146): columns c, c + 8, ... of g
-static_assert(VT_MSG <= PEER_CH_SLOT, "a cluster CTA's slice must fit its mailbox channel");
+static_assert(VT_MSG <= PEER_LL_MAX, "a cluster CTA's slice must fit its mailbox channel");
 
 template <int NQ>
 __global__ void __launch_bounds__(VS_THREADS, 1)
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(VS_THREADS, 1)
       msg[tid] = s;
     }
     __syncthreads();
-    if (pc.world > 1) peer_allreduce_block<true>(pc, msg, VT_MSG, 1 + crank);  // ends with a CTA barrier
+    if (pc.world > 1) peer_allreduce_ll(pc, msg, VT_MSG, 1 + crank);  // ends with a CTA barrier
   }
   // the W column this step consumes was left unnormalised: s = ||y||, u = y / s  (irlb.py:176-178, 217-219)
   const double n2w = msg[VT_G0], syw = msg[VT_G0 + 1];
@@ -475,6 +475,6 @@ __global__ void __launch_bounds__(256) w_norm_exchange(const double* __restrict_
     if (threadIdx.x == 0) two[0] = t0, two[1] = t1;
   }
   __syncthreads();
-  if (pc.world > 1) peer_allreduce_block<true>(pc, two, 2, 0);
+  if (pc.world > 1) peer_allreduce_ll(pc, two, 2, 0);
   if (threadIdx.x < 2) out2[threadIdx.x] = two[threadIdx.x];
 }

@@ -8,8 +8,10 @@
 //                              R(g) = rows of column g, as multisets (general in nn_idx[i,0]);
 //   snn_rows                   one warp per row a: gathers R(g) for every g in F(a) into shared
 //                              memory, bitonic-sorts the ids, run lengths are the integer
-//                              shared-neighbour counts V[a, b]; rows whose candidate list exceeds
-//                              the per-warp buffer are redone by a whole CTA (128 KB buffer).
+//                              shared-neighbour counts V[a, b].  Three tiers by candidate count (k^2 on
+//                              average, heavy-tailed: hub cells sit in many neighbour lists): a warp with a
+//                              2048-entry buffer, a CTA with 8192 entries (32 KB: several CTAs per SM --
+//                              at k = 30 a third of the rows land here), a CTA with 32768 entries (128 KB).
 // Two passes (count, then fill) give a compact edge list sorted by (source, target).
 #include "common.cuh"
 
@@ -96,10 +98,10 @@ __global__ void __launch_bounds__(T == 32 ? 128 : 256) snn_rows(
       const int g = fcol[t];
       total += rptr[g + 1] - rptr[g];
     }
-    if (total > CAP) {
-      if (T == 32) {
+    if (total > CAP) {  // too long for this tier: hand the row to the next one (count pass), or give up
+      if (biglist) {
         if (!FILL && tid == 0) biglist[atomicAdd(nbig, 1)] = (int)a;
-      } else if (tid == 0) {
+      } else if (!FILL && tid == 0) {
         *err = 1;
       }
       continue;  // uniform for the whole group
@@ -208,12 +210,14 @@ void run_snn(adobo_ctx* c, const int* nn, i64 n, i64 row_begin, i64 row_end, int
   REQUIRE(h_flags[0] == 0, ADOBO_ERR_ARG, "snn: nn_idx holds an index outside 1..n");
   LAUNCH(c, "snn_fill", (snn_fill<<<gb, 256, 0, st>>>(nn, n, k, fptr.p, rptr.p, fcur.p, rcur.p, fcol.p, rrow.p)));
 
-  constexpr int WCAP = 2048, CCAP = 32768;
-  const size_t wsmem = sizeof(unsigned) * WCAP * 4, csmem = sizeof(unsigned) * CCAP;
+  constexpr int WCAP = 2048, MCAP = 8192, CCAP = 32768;
+  const size_t wsmem = sizeof(unsigned) * WCAP * 4, msmem = sizeof(unsigned) * MCAP, csmem = sizeof(unsigned) * CCAP;
   CUDA_CHECK(cudaFuncSetAttribute(snn_rows<256, CCAP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
   CUDA_CHECK(cudaFuncSetAttribute(snn_rows<256, CCAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
   const unsigned wb = (unsigned)std::max<i64>(1, std::min<i64>((nloc + 3) / 4, (i64)c->sm_count * 16));
-  int nbig = 0;
+  DevBuf<int> hugelist;
+  hugelist.ensure((size_t)std::max<i64>(nloc, 1));
+  int nbig = 0, nhuge = 0;  // flags: [1] rows for the middle tier, [3] rows for the top tier
   if (nloc > 0) {
     LAUNCH(c, "snn_rows", (snn_rows<32, WCAP, false><<<wb, 128, wsmem, st>>>(
                               fptr.p, fcol.p, rptr.p, rrow.p, row_begin, row_end, nullptr, 0, k, prune, rowkept.p,
@@ -223,8 +227,17 @@ void run_snn(adobo_ctx* c, const int* nn, i64 n, i64 row_begin, i64 row_end, int
     CUDA_CHECK(cudaStreamSynchronize(st));
     nbig = h_flags[1];
     if (nbig > 0) {
-      LAUNCH(c, "snn_rows_big", (snn_rows<256, CCAP, false><<<(unsigned)nbig, 256, csmem, st>>>(
+      LAUNCH(c, "snn_rows_mid", (snn_rows<256, MCAP, false><<<(unsigned)nbig, 256, msmem, st>>>(
                                     fptr.p, fcol.p, rptr.p, rrow.p, row_begin, row_end, biglist.p, nbig, k, prune,
+                                    rowkept.p, rowmiss.p, totals.p, hugelist.p, flags.p + 3, nullptr, nullptr, 0, nullptr,
+                                    nullptr, nullptr, flags.p + 2)));
+      CUDA_CHECK(cudaMemcpyAsync(h_flags, flags.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      nhuge = h_flags[3];
+    }
+    if (nhuge > 0) {
+      LAUNCH(c, "snn_rows_big", (snn_rows<256, CCAP, false><<<(unsigned)nhuge, 256, csmem, st>>>(
+                                    fptr.p, fcol.p, rptr.p, rrow.p, row_begin, row_end, hugelist.p, nhuge, k, prune,
                                     rowkept.p, rowmiss.p, totals.p, nullptr, nullptr, nullptr, nullptr, 0, nullptr,
                                     nullptr, nullptr, flags.p + 2)));
       CUDA_CHECK(cudaMemcpyAsync(h_flags, flags.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
@@ -249,9 +262,14 @@ void run_snn(adobo_ctx* c, const int* nn, i64 n, i64 row_begin, i64 row_end, int
                               fptr.p, fcol.p, rptr.p, rrow.p, row_begin, row_end, nullptr, 0, k, prune, nullptr, nullptr,
                               nullptr, nullptr, nullptr, eptr.p, mptr.p, e_regular, c->e_src.p, c->e_dst.p, c->e_v.p,
                               flags.p + 2)));
-    if (nbig > 0)
-      LAUNCH(c, "snn_rows_big", (snn_rows<256, CCAP, true><<<(unsigned)nbig, 256, csmem, st>>>(
+    if (nbig > 0)  // rows that overflow this tier are skipped here (uniformly) and filled by the next launch
+      LAUNCH(c, "snn_rows_mid", (snn_rows<256, MCAP, true><<<(unsigned)nbig, 256, msmem, st>>>(
                                     fptr.p, fcol.p, rptr.p, rrow.p, row_begin, row_end, biglist.p, nbig, k, prune,
+                                    nullptr, nullptr, nullptr, hugelist.p, nullptr, eptr.p, mptr.p, e_regular, c->e_src.p,
+                                    c->e_dst.p, c->e_v.p, flags.p + 2)));
+    if (nhuge > 0)
+      LAUNCH(c, "snn_rows_big", (snn_rows<256, CCAP, true><<<(unsigned)nhuge, 256, csmem, st>>>(
+                                    fptr.p, fcol.p, rptr.p, rrow.p, row_begin, row_end, hugelist.p, nhuge, k, prune,
                                     nullptr, nullptr, nullptr, nullptr, nullptr, eptr.p, mptr.p, e_regular, c->e_src.p,
                                     c->e_dst.p, c->e_v.p, flags.p + 2)));
   }
