@@ -1939,11 +1939,21 @@ static rotate_rows_fn rotate_rows_for(int R, int RS = 1) {
 __global__ void set_restart(double* __restrict__ V, int ldv, int h, const double* __restrict__ fbuf,
                             double* __restrict__ B, int m, int k, const double* __restrict__ sv,
                             const double* __restrict__ R, double* __restrict__ cvec, double* __restrict__ sumW,
-                            const double* __restrict__ crot, const int* __restrict__ halt) {
+                            const double* __restrict__ crot, const int* __restrict__ halt, const LazyArgs lz, int nds) {
   if (halt && *halt) return;
-  if (cvec && blockIdx.x == 0 && threadIdx.x < k) {  // rotated by the conv_check of the previous iteration
-    cvec[threadIdx.x] = crot[threadIdx.x];
-    sumW[threadIdx.x] = crot[MAXB + threadIdx.x];
+  if (cvec && blockIdx.x == 0) {  // rotated by the conv_check of the previous iteration
+    const int t = threadIdx.x;
+    if (t < k) sumW[t] = crot[MAXB + t];
+    if (lz.P0 == nullptr) {
+      if (t < k) cvec[t] = crot[t];
+    } else if (t < nds) {  // lazy rotation: the coefficients in stored space, c_s = [P0 c[:kp] ; c[kp:]]
+      double v = 0.0;
+      if (t < lz.U0)
+        for (int cc = 0; cc < lz.kp; ++cc) v = fma(lz.P0[(size_t)t * lz.ldp + cc], crot[cc], v);
+      else
+        v = crot[lz.kp + t - lz.U0];
+      cvec[t] = v;
+    }
   }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < h) V[(size_t)i * ldv + k] = fbuf[i];
@@ -2050,13 +2060,15 @@ enum : unsigned {
   HK_NO_PDL = 1u << 11,          // no programmatic dependent launch
   HK_NO_RUNAHEAD = 1u << 12,     // wait for every convergence read-back
   HK_TRACE = 1u << 13,           // one line per outer iteration on stderr
+  HK_NO_LAZY = 1u << 14,         // rotate W at every restart (two-kernel step without the lazy rotation)
 };
 static unsigned irlb_hooks() {
   static const struct { const char* name; unsigned bit; } names[] = {
       {"svd_jacobi", HK_SVD_JACOBI}, {"svd_fallback", HK_SVD_FALLBACK}, {"no_graph", HK_NO_GRAPH},
       {"no_fork", HK_NO_FORK}, {"rotate_streamed", HK_ROTATE_STREAMED}, {"no_fusedt", HK_NO_FUSEDT},
       {"no_vone", HK_NO_VONE}, {"no_zpath", HK_NO_ZPATH}, {"no_vstep", HK_NO_VSTEP}, {"no_wfold", HK_NO_WFOLD},
-      {"no_split", HK_NO_SPLIT}, {"no_pdl", HK_NO_PDL}, {"no_runahead", HK_NO_RUNAHEAD}, {"trace", HK_TRACE}};
+      {"no_split", HK_NO_SPLIT}, {"no_pdl", HK_NO_PDL}, {"no_runahead", HK_NO_RUNAHEAD}, {"trace", HK_TRACE},
+      {"no_lazy", HK_NO_LAZY}};
   const char* e = getenv("ADOBO_B200_IRLB");
   unsigned bits = 0;
   if (!e) return 0;
@@ -2085,10 +2097,11 @@ struct IrlbWs {
   int sig_i[6] = {};
   double sig_tol = 0;
   DevBuf<double> V, W, B, sc, tbuf, ybuf_h, ybuf_n, fbuf, xs, wcur, cvec, partials, tpart, Su, Sv, svd_s, R, murs, St, Z, sumW, gout, crot;
+  DevBuf<double> P0, P0t, Pmat;  // lazy rotation of W (irlb_step.cuh)
   DevBuf<unsigned> counter;
   DevBuf<int> info;
-  std::map<int, cudaGraphExec_t> graphs;
-  std::map<int, i64> graph_launches;
+  std::map<i64, cudaGraphExec_t> graphs;  // key: first iteration?, k, state of the lazy rotation
+  std::map<i64, i64> graph_launches;
   cudaEvent_t ev[4] = {};  // completion of the outer iterations in flight (run-ahead)
   void clear_graphs() {
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
@@ -2167,11 +2180,19 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   const bool fold_wt_ok = !hook(HK_NO_WFOLD);
   const bool split = !fusedt && c->world == 1 && zpath && vs_one && fold_wt_ok && !hook(HK_NO_SPLIT);
   const bool wide_rows = n >= 65536;  // two-pass kernels: enough rows per resident warp to prefer throughput
+  // lazy rotation of W (irlb_step.cuh): W_s holds up to Ms stored columns, 16 per basis slot of w_step_t's lanes, two
+  // slots short because the row kernel's vector carries ||y||^2 and sum y behind g_s
+  const int wt_nh = m_b + 1 <= 80 ? 6 : (m_b + 1 <= 96 ? 7 : 8);
+  const bool lazy = fusedt && !hook(HK_NO_LAZY) && 16 * wt_nh - 2 - m_b >= 3;
+  const int wt_nh_used = lazy ? wt_nh : (m_b + 1 <= 96 ? 6 : 8);
+  const int Ms = lazy ? 16 * wt_nh - 2 : m_b;
+  const int ldw = lazy ? 16 * wt_nh : ld;               // row stride of W / W_s
+  const int ldp = (m_b + 7) & ~7;                       // row stride of P0
   {
     // a re-allocation moves a buffer: graphs that captured the old pointer must go
     const double* before[6] = {V.p, W.p, partials.p, murs.p, Z.p, tpart.p};
     V.ensure((size_t)h * ld);
-    W.ensure((size_t)std::max<i64>(n, 1) * ld);
+    W.ensure((size_t)std::max<i64>(n, 1) * ldw);
     B.ensure((size_t)MAXB * MAXB);
     sc.ensure(SC_COUNT);
     tbuf.ensure((size_t)h);
@@ -2197,6 +2218,11 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
       gout.ensure(MAXB);
     }
     if (fusedt) tpart.ensure((size_t)c->sm_count * hp);
+    if (lazy) {
+      ws.P0.ensure((size_t)MAXB * MAXB);
+      ws.P0t.ensure((size_t)MAXB * MAXB);
+      ws.Pmat.ensure((size_t)MAXB * MAXB);
+    }
     const double* after[6] = {V.p, W.p, partials.p, murs.p, Z.p, tpart.p};
     for (int q = 0; q < 6; ++q)
       if (before[q] != after[q]) ws.clear_graphs();
@@ -2206,7 +2232,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   // spmv_dots (wide): 512-thread CTAs, two per SM, four rows per warp
   const unsigned gb_sd = (unsigned)std::max<i64>(1, std::min<i64>((n + 63) / 64, 2 * (i64)c->sm_count));
   CUDA_CHECK(cudaMemsetAsync(V.p, 0, sizeof(double) * (size_t)h * ld, st));
-  CUDA_CHECK(cudaMemsetAsync(W.p, 0, sizeof(double) * (size_t)std::max<i64>(n, 1) * ld, st));
+  CUDA_CHECK(cudaMemsetAsync(W.p, 0, sizeof(double) * (size_t)std::max<i64>(n, 1) * ldw, st));
   CUDA_CHECK(cudaMemsetAsync(B.p, 0, sizeof(double) * m_b * m_b, st));
   CUDA_CHECK(cudaMemsetAsync(sc.p, 0, sizeof(double) * SC_COUNT, st));
   CUDA_CHECK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned) * 2, st));
@@ -2231,7 +2257,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   // cluster still holds VS_CLUSTER SMs: a CTA that had to wait for one of those would run its whole prologue after
   // everybody else's -- leave them out of the grid
   auto w3_fn = m_b + 1 <= 96 ? w_step3<VT, 6> : w_step3<VT, 8>;
-  auto wt_fn = m_b + 1 <= 96 ? w_step_t<VT, 6> : w_step_t<VT, 8>;
+  auto wt_fn = wt_nh_used == 6 ? w_step_t<VT, 6> : (wt_nh_used == 7 ? w_step_t<VT, 7> : w_step_t<VT, 8>);
   const size_t wt_smem = sizeof(double) * (size_t)(1 + WT_WARPS) * hp;
   if (zpath && !fusedt) CUDA_CHECK(cudaFuncSetAttribute(w3_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * h)));
   if (fusedt) CUDA_CHECK(cudaFuncSetAttribute(wt_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wt_smem));
@@ -2248,40 +2274,78 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     }
   }
   const int* hp_halt = nullptr;  // halt flag handed to the kernels of an outer iteration (run-ahead), else none
-  // V[:, :kc] (or outv) = V Sv[:, :kc]  and  W[:, :kc] (or outw) = W Su[:, :kc]: one launch for the tall-skinny GEMMs
-  // (and Z = A^T W, which follows W at a restart)
-  auto rotate2 = [&](int kc, double* outv, double* outw, int ldo, const double* scale_w, bool st_ready) {
+  // The tall-skinny GEMMs Q[:, :kc] (or out) = Q[:, :inner] S[:, :kc] of a restart / of the final vectors: up to three
+  // jobs in one launch (rows = 0: no CTAs), the SMs split between them in proportion to their 64-row tiles.
+  auto rotate_launch = [&](RotJob jv, RotJob jz, RotJob jw, int ldq, int inner, int kc) {
+    const int kcp = (kc + 7) & ~7;
+    const i64 sms = c->sm_count;
+    const i64 tv = (jv.rows + RB_ROWS - 1) / RB_ROWS, tz = (jz.rows + RB_ROWS - 1) / RB_ROWS, tw = (jw.rows + RB_ROWS - 1) / RB_ROWS;
+    const i64 tall = std::max<i64>(1, tv + tz + tw);
+    i64 bv = tv ? std::max<i64>(1, std::min<i64>((tv * sms + tall / 2) / tall, tv)) : 0;
+    i64 bz = tz ? std::max<i64>(1, std::min<i64>((tz * sms + tall / 2) / tall, tz)) : 0;
+    i64 bw = tw ? std::max<i64>(1, std::min<i64>(tw, sms - bv - bz)) : 0;
+    if (bv + bz + bw == 0) return;
+    const unsigned nbv = (unsigned)bv, nbz = (unsigned)bz, nbw = (unsigned)bw;
+    WORK(c, 8.0 * (jv.rows + jz.rows + jw.rows) * (inner + kc));
+    // few tiles per SM: rotate_rows (row range per CTA, loads pipelined along the inner dimension);
+    // long shards: rotate_basis (64-row tiles streamed through a double buffer)
+    i64 per = 1;  // rows per CTA
+    if (bv) per = std::max<i64>(per, (jv.rows + bv - 1) / bv);
+    if (bz) per = std::max<i64>(per, (jz.rows + bz - 1) / bz);
+    if (bw) per = std::max<i64>(per, (jw.rows + bw - 1) / bw);
+    const size_t s_bytes = sizeof(double) * (size_t)inner * kcp;
+    const int r_fit = (int)std::min<i64>(5, (((i64)(225 * 1024 - s_bytes) / (8 * inner)) - 1) / 32);
+    if (!hook(HK_ROTATE_STREAMED) && r_fit >= 1 && per <= 2 * 32 * r_fit) {
+      const i64 ntile = (per + 32 * r_fit - 1) / (32 * r_fit);
+      const int Rr = (int)std::min<i64>(r_fit, ((per + ntile - 1) / ntile + 31) / 32);
+      const size_t smem = s_bytes + sizeof(double) * (size_t)inner * (32 * Rr + 1);
+      rotate_rows_fn fn = rotate_rows_for(Rr);
+      CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      LAUNCH(c, "rotate_basis", (fn<<<nbv + nbz + nbw, 32 * (kcp / 8), smem, st>>>(jv, jz, jw, (int)nbv, (int)nbz, ldq, inner, kc, hp_halt)));
+    } else {
+      const size_t q_bytes = sizeof(double) * (size_t)inner * RB_QP;
+      const int nbuf = (s_bytes + 2 * q_bytes <= 225 * 1024) ? 2 : 1;
+      const size_t smem = s_bytes + nbuf * q_bytes;
+      REQUIRE(smem <= 227 * 1024, ADOBO_ERR_LIMIT, "rotate_basis: %d x %d rotation does not fit shared memory", inner, kcp);
+      CUDA_CHECK(cudaFuncSetAttribute(rotate_basis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      LAUNCH(c, "rotate_basis", (rotate_basis<<<nbv + nbz + nbw, 32 * (kcp / 8), smem, st>>>(jv, jz, jw, (int)nbv, (int)nbz, ldq, inner,
+                                                                                       kc, nbuf, hp_halt)));
+    }
+  };
+  const RotJob no_job{nullptr, 0, nullptr, nullptr, 0, nullptr};
+  // V[:, :kc] (or outv) = V Sv[:, :kc]  and  W[:, :kc] (or outw) = W Su[:, :kc]  (and Z = A^T W, which follows W at a
+  // restart); with_w = false: V and Z only (lazy rotation of W)
+  auto rotate2 = [&](int kc, double* outv, double* outw, int ldo, const double* scale_w, bool st_ready, bool with_w) {
     const int kcp = (kc + 7) & ~7;
     if (!st_ready)  // restarts: conv_check has laid the two matrices out already
       LAUNCH(c, "transpose_s", (transpose_s<<<(2 * m_b * kcp + 255) / 256, 256, 0, st>>>(Sv.p, Su.p, m_b, kc, kcp, St.p)));
     const bool with_z = zpath && outv == nullptr;  // restart rotation: Z = A^T W follows W
     RotJob jv{V.p, (i64)h, St.p, outv, ldo, nullptr};
-    RotJob jz{with_z ? Z.p : nullptr, with_z ? (i64)h : 0, St.p + (size_t)m_b * kcp, nullptr, 0, nullptr};
-    RotJob jw{W.p, n, St.p + (size_t)m_b * kcp, outw, ldo, scale_w};
-    // one wave: split the SMs between the jobs in proportion to their 64-row tiles
-    const i64 tv = (h + RB_ROWS - 1) / RB_ROWS, tz = with_z ? tv : 0, tw = (n + RB_ROWS - 1) / RB_ROWS, sms = c->sm_count;
-    const i64 tall = tv + tz + tw;
-    i64 bv = std::max<i64>(1, std::min<i64>((tv * sms + tall / 2) / tall, tv));
-    i64 bz = with_z ? bv : 0;
-    const i64 bw = std::max<i64>(1, std::min<i64>(tw, sms - bv - bz));
-    const unsigned nbv = (unsigned)bv, nbz = (unsigned)bz, nbw = (unsigned)bw;
-    WORK(c, 8.0 * (n + h + (with_z ? h : 0)) * (m_b + kc));
-    // few tiles per SM: rotate_rows (row range per CTA, loads pipelined along the inner dimension);
-    // long shards: rotate_basis (64-row tiles streamed through a double buffer)
-    const i64 per = std::max<i64>(((i64)h + bv - 1) / bv, (n + bw - 1) / bw);  // rows per CTA
-    const size_t s_bytes = sizeof(double) * (size_t)m_b * kcp;
-    const int r_fit = (int)std::min<i64>(5, (((i64)(225 * 1024 - s_bytes) / (8 * m_b)) - 1) / 32);
-    if (!hook(HK_ROTATE_STREAMED) && r_fit >= 1 && per <= 2 * 32 * r_fit) {
-      const i64 ntile = (per + 32 * r_fit - 1) / (32 * r_fit);
-      const int Rr = (int)std::min<i64>(r_fit, ((per + ntile - 1) / ntile + 31) / 32);
-      const size_t smem = s_bytes + sizeof(double) * (size_t)m_b * (32 * Rr + 1);
-      rotate_rows_fn fn = rotate_rows_for(Rr);
-      CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      LAUNCH(c, "rotate_basis", (fn<<<nbv + nbz + nbw, 32 * (kcp / 8), smem, st>>>(jv, jz, jw, (int)nbv, (int)nbz, ld, m_b, kc, hp_halt)));
-    } else {
-      LAUNCH(c, "rotate_basis", (rotate_basis<<<nbv + nbz + nbw, 32 * (kcp / 8), rot_smem, st>>>(jv, jz, jw, (int)nbv, (int)nbz,
-                                                                                           ld, m_b, kc, rot_nbuf, hp_halt)));
-    }
+    RotJob jz = with_z ? RotJob{Z.p, (i64)h, St.p + (size_t)m_b * kcp, nullptr, 0, nullptr} : no_job;
+    RotJob jw = with_w ? RotJob{W.p, n, St.p + (size_t)m_b * kcp, outw, ldo, scale_w} : no_job;
+    rotate_launch(jv, jz, jw, ld, m_b, kc);
+  };
+  // ---- lazy rotation of W: state of the stored columns (see irlb_step.cuh) ----
+  struct LState {
+    int U0 = 0, kp = 0, S = 0;  // S: stored columns once the iteration's steps are done
+  };
+  auto lazy_next = [&](const LState& a, int k, bool* materialise) {  // state of the iteration that restarts with k
+    LState b;
+    const bool mat = a.S + (m_b - k) > Ms;
+    if (materialise) *materialise = mat;
+    if (mat) b.U0 = 0, b.kp = 0, b.S = m_b;
+    else b.U0 = a.S, b.kp = k, b.S = a.S + (m_b - k);
+    return b;
+  };
+  auto lazy_args = [&](const LState& a) {
+    LazyArgs lz;
+    if (lazy) lz.P0 = ws.P0.p, lz.P0t = ws.P0t.p, lz.ldp = ldp, lz.U0 = a.U0, lz.kp = a.kp;
+    return lz;
+  };
+  // W_s[:, :kc] (or out) = W_s[:, :S] Pmat, the real rotation (Pmat: S x kcp from lazy_p0)
+  auto rotate_w_stored = [&](int S, int kc, double* out, int ldo, const double* scale_w) {
+    RotJob jw{W.p, n, ws.Pmat.p, out, ldo, scale_w};
+    rotate_launch(no_job, no_job, jw, ldw, S, kc);
   };
   const bool use_arrow = !hook(HK_SVD_JACOBI);
   const bool force_fallback = hook(HK_SVD_FALLBACK);
@@ -2365,13 +2429,26 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
       LAUNCH(c, "w_finish", (w_finish<<<fin_n, 256, 0, st>>>(ybuf_n.p, sc.p + SC_NRM2, sc.p, W.p, ld, jn, n, wcur.p, B.p, m_b, nullptr,
                                                              nullptr, 0, nullptr)));
   };
-  // restart update (irlb.py:238-246): Ritz vectors into the leading k columns, V[:,k] = F, new B
-  auto restart_update = [&](int k) {
-    rotate2(k, nullptr, nullptr, 0, nullptr, true);
-    LAUNCH(c, "set_restart", (set_restart<<<(std::max(h, m_b * m_b) + 255) / 256, 256, 0, st>>>(V.p, ld, h, fbuf.p, B.p,
-                                                                                            m_b, k, svd_s.p, R.p,
-                                                                                            zpath ? cvec.p : nullptr, sumW.p,
-                                                                                            ws.crot.p, hp_halt)));
+  // restart update (irlb.py:238-246): Ritz vectors into the leading k columns, V[:,k] = F, new B.
+  // `prev`: lazy-rotation state of the iteration that just ended (ignored without the lazy rotation)
+  auto restart_update = [&](int k, const LState& prev) {
+    const unsigned sr_grid = (unsigned)((std::max(h, m_b * m_b) + 255) / 256);
+    if (!lazy) {
+      rotate2(k, nullptr, nullptr, 0, nullptr, true, true);
+      LAUNCH(c, "set_restart", (set_restart<<<sr_grid, 256, 0, st>>>(V.p, ld, h, fbuf.p, B.p, m_b, k, svd_s.p, R.p,
+                                                                  zpath ? cvec.p : nullptr, sumW.p, ws.crot.p, hp_halt,
+                                                                  LazyArgs(), 0)));
+      return;
+    }
+    bool mat = false;
+    const LState next = lazy_next(prev, k, &mat);
+    const int kcp = (k + 7) & ~7;
+    rotate2(k, nullptr, nullptr, 0, nullptr, true, false);  // V and Z
+    LAUNCH(c, "lazy_p0", (lazy_p0<<<prev.S, 128, 0, st>>>(ws.P0.p, ws.P0t.p, ldp, prev.U0, prev.kp, Su.p, m_b, k,
+                                                         mat ? ws.Pmat.p : nullptr, kcp, hp_halt)));
+    if (mat) rotate_w_stored(prev.S, k, nullptr, 0, nullptr);  // W_s[:, :k] = the Ritz vectors themselves again
+    LAUNCH(c, "set_restart", (set_restart<<<sr_grid, 256, 0, st>>>(V.p, ld, h, fbuf.p, B.p, m_b, k, svd_s.p, R.p, cvec.p, sumW.p,
+                                                                ws.crot.p, hp_halt, lazy_args(next), next.U0 + (k - next.kp))));
   };
   const bool use_graphs = !c->profiling && !hook(HK_NO_GRAPH);
   // SVD of B (irlb.py:224): restarts have the diag + spike + bidiagonal-tail structure (svd_arrow), the first
@@ -2402,31 +2479,35 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     return za;
   };
   // ---- one outer iteration (irlb.py:155-231) up to the convergence read-back: two-kernel steps ----
-  auto enqueue_steps_fused = [&](bool first, int k) {
-    auto w_launch = [&](int jprev, int nd) {
-      WORK(c, w_bytes(nd, jprev));
+  auto enqueue_steps_fused = [&](bool first, int k, const LState& ls) {
+    const LazyArgs lz = lazy_args(ls);
+    auto slot = [&](int col) { return ls.U0 + (col - ls.kp); };  // where column col of W is stored
+    auto w_launch = [&](int jprev, int nd) {                     // effective indices in, stored indices to the kernel
+      const int nds = slot(nd), jps = jprev >= 0 ? nds - 1 : -1;
+      WORK(c, w_bytes(nds, jps));
       LAUNCH(c, "w_step_t", CUDA_CHECK(launch_k(wt_fn, dim3(gb_w2), dim3(W2_THREADS), wt_smem, st, pdl && jprev >= 0, 1, A.rptr.p,
-                                                A.cidx.p, A.rval.p, xs.p, sc.p, W.p, ld, jprev, nd, (int)n, cvec.p, ybuf_n.p,
+                                                A.cidx.p, A.rval.p, xs.p, sc.p, W.p, ldw, jps, nds, (int)n, cvec.p, ybuf_n.p,
                                                 partials.p, tpart.p, hp_halt, h, hp)));
     };
     int j = first ? 0 : k;
     w_launch(-1, j);
     while (j < m_b) {
       const bool last = j == m_b - 1;
+      const int sj = slot(j);
       if (last) {
         // W[:, m_b-1] and B[m_b-1, m_b-1] now: B is complete and its SVD runs beside the last V step
         if (c->world > 1)
-          LAUNCH(c, "w_norm_exchange", (w_norm_exchange<<<1, 256, 0, st>>>(partials.p, (int)gb_w2, j, gout.p + j, hp_halt, pcw)));
-        LAUNCH(c, "w_finish", (w_finish<<<fin_n, 256, 0, st>>>(ybuf_n.p, gout.p + j, sc.p, W.p, ld, j, n, wcur.p, B.p, m_b, hp_halt,
-                                                               c->world > 1 ? nullptr : partials.p, (int)gb_w2, gout.p)));
+          LAUNCH(c, "w_norm_exchange", (w_norm_exchange<<<1, 256, 0, st>>>(partials.p, (int)gb_w2, sj, gout.p, hp_halt, pcw)));
+        LAUNCH(c, "w_finish", (w_finish_t<<<fin_n, 256, 0, st>>>(ybuf_n.p, gout.p, sc.p, W.p, ldw, sj, j, n, B.p, m_b, hp_halt,
+                                                                 c->world > 1 ? nullptr : partials.p, (int)gb_w2)));
         if (fork_svd) fork_svd_here(first, k);
       }
-      WORK(c, 8.0 * gb_w2 * (hp + j + 2.0) + 8.0 * h * (2.0 * (j + 1) + 8));
+      WORK(c, 8.0 * gb_w2 * (hp + sj + 2.0) + 8.0 * h * (2.0 * (j + 1) + 8));
       LAUNCH(c, "v_step_t", CUDA_CHECK(launch_k(m_b <= 96 ? v_step_t<3> : v_step_t<4>, dim3(VS_CLUSTER), dim3(VS_THREADS),
                                                 vs_one_smem, st, pdl && !last, VS_CLUSTER, (const double*)tpart.p, hp,
                                                 (const double*)partials.p, (int)gb_w2, mu, rs,
                                                 (const double*)(centered ? murs.p : nullptr), sc.p, V.p, ld, j, m_b, h,
-                                                ybuf_h.p, fbuf.p, xs.p, B.p, zargs(j), hp_halt, pcw)));
+                                                ybuf_h.p, fbuf.p, xs.p, B.p, zargs(j), hp_halt, pcw, lz)));
       if (!last) w_launch(j, j + 1);
       ++j;
     }
@@ -2481,11 +2562,12 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
       ++j;
     }
   };
-  auto enqueue_iteration = [&](bool first, int k) {
+  // `prev`: lazy-rotation state of the iteration before (the fresh state for the first iteration)
+  auto enqueue_iteration = [&](bool first, int k, const LState& prev) {
     hp_halt = runahead ? info.p + 4 : nullptr;
-    if (!first) restart_update(k);
+    if (!first) restart_update(k, prev);
     if (fusedt)
-      enqueue_steps_fused(first, k);
+      enqueue_steps_fused(first, k, (first || !lazy) ? prev : lazy_next(prev, k, nullptr));
     else
       enqueue_steps(first, k);
     const bool arrow = !first && use_arrow && svd_arrow_supported(m_b, k);
@@ -2509,19 +2591,19 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     CUDA_CHECK(cudaMemcpyAsync(h_info, info.p, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
   };
-  auto run_iteration = [&](bool first, int k) {
+  auto run_iteration = [&](bool first, int k, const LState& prev) {
     if (!use_graphs) {
-      enqueue_iteration(first, k);
+      enqueue_iteration(first, k, prev);
       return;
     }
-    const int key = k | (first ? (1 << 16) : 0);
+    const i64 key = (first ? 1 : 0) | ((i64)k << 1) | ((i64)prev.kp << 9) | ((i64)prev.U0 << 17);
     auto it = ws.graphs.find(key);
     if (it == ws.graphs.end()) {
       const i64 l0 = c->launches;
       cudaGraph_t graph = nullptr;
       CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       try {
-        enqueue_iteration(first, k);
+        enqueue_iteration(first, k, prev);
       } catch (...) {
         cudaStreamEndCapture(st, &graph);
         if (graph) cudaGraphDestroy(graph);
@@ -2549,7 +2631,10 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   // iteration.  It runs up to RUN_DEPTH iterations ahead; when an iteration converges (or its SVD is rejected)
   // conv_check raises the halt flag on the device and every kernel of the iterations already enqueued behind it
   // returns at once, leaving V, W, B and the SVD of the converged iteration untouched.
-  std::vector<int> ks;  // k of every enqueued iteration
+  std::vector<int> ks;       // k of every enqueued iteration
+  std::vector<LState> lst;   // and the lazy-rotation state its steps run in (fresh without the lazy rotation)
+  LState fresh;
+  fresh.S = m_b;
   int it = 0, k = nu, enq = 0;
   bool converged = false;
   if (runahead)
@@ -2557,9 +2642,11 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
       if (!e) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   while (it < maxit) {
     while (enq < maxit && (enq == it || (runahead && enq - it < RUN_DEPTH && it > 0 && k == m_b - 3))) {
-      run_iteration(enq == 0, k);
+      const LState prev = enq == 0 ? fresh : lst[enq - 1];
+      run_iteration(enq == 0, k, prev);
       if (runahead) CUDA_CHECK(cudaEventRecord(ws.ev[enq % RUN_DEPTH], st));
       ks.push_back(k);
+      lst.push_back((enq == 0 || !lazy) ? fresh : lazy_next(prev, k, nullptr));
       ++enq;
     }
     if (runahead)
@@ -2575,6 +2662,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
       k = ks[it];
       enq = it + 1;
       ks.resize(enq);
+      lst.resize(enq);
     }
     if (h_info[0] < 0 || (force_fallback && it > 0)) {  // structured SVD failed its self-check (kept for safety)
       svd_fallback(it == 0, k);
@@ -2591,12 +2679,57 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   int nmult = 0;  // 1 + sum over j of (1 + [j < m_b-1]) mat-vecs per outer iteration
   for (int i = 0; i < (int)ks.size() && i <= it; ++i) nmult += 2 * (m_b - (i == 0 ? 0 : ks[i]));
   // the reference applies the restart update before `it` reaches maxit (irlb.py:238-247)
-  if (!converged && it > 0) restart_update(k);  // St for this k was laid out by the last conv_check
+  const LState fin = lst.empty() ? fresh : lst[std::min<size_t>(it, lst.size() - 1)];  // state the vectors were left in
+  const bool exhausted = !converged && it > 0;  // the reference applies the restart update before `it` reaches maxit
   // ---- U = W Su[:, :nu] (x diag(s) when var_weigh), V = V Sv[:, :nu]  (irlb.py:249-250, dr.py:164-168) ----
   outU.ensure((size_t)std::max<i64>(n, 1) * nu);
   outV.ensure((size_t)h * nu);
   outS.ensure((size_t)nu);
-  rotate2(nu, outV.p, outU.p, nu, var_weigh ? svd_s.p : nullptr, false);
+  if (!lazy) {
+    if (exhausted) restart_update(k, fin);  // St for this k was laid out by the last conv_check
+    rotate2(nu, outV.p, outU.p, nu, var_weigh ? svd_s.p : nullptr, false, true);
+  } else if (!exhausted) {
+    // U = W_s [P0 0; 0 I] Su[:, :nu]: the small product first, then one real rotation of the stored columns
+    rotate2(nu, outV.p, nullptr, nu, nullptr, false, false);
+    LAUNCH(c, "lazy_p0", (lazy_p0<<<fin.S, 128, 0, st>>>(ws.P0.p, ws.P0t.p, ldp, fin.U0, fin.kp, Su.p, m_b, nu, ws.Pmat.p,
+                                                        (nu + 7) & ~7, nullptr)));
+    rotate_w_stored(fin.S, nu, outU.p, nu, var_weigh ? svd_s.p : nullptr);
+  } else {
+    // Not converged within maxit.  The reference then rotates the first k columns of V and W once more and multiplies
+    // the MIXED basis (new Ritz vectors | old columns k..m_b-1) by Su[:, :nu] (irlb.py:238-250).  V is rotated in
+    // place as always; for W the two products are folded into one S x nu matrix on the host (off the hot path).
+    rotate2(k, nullptr, nullptr, 0, nullptr, true, false);
+    LAUNCH(c, "set_restart", (set_restart<<<(unsigned)((std::max(h, m_b * m_b) + 255) / 256), 256, 0, st>>>(
+                                 V.p, ld, h, fbuf.p, B.p, m_b, k, svd_s.p, R.p, nullptr, sumW.p, ws.crot.p, nullptr, LazyArgs(), 0)));
+    rotate2(nu, outV.p, nullptr, nu, nullptr, false, false);
+    std::vector<double> hsu((size_t)m_b * m_b), hp0((size_t)MAXB * MAXB);
+    CUDA_CHECK(cudaMemcpyAsync(hsu.data(), Su.p, sizeof(double) * m_b * m_b, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(hp0.data(), ws.P0.p, sizeof(double) * (size_t)MAXB * MAXB, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    const int S = fin.S, kcp = (nu + 7) & ~7;
+    auto su = [&](int e, int col) { return hsu[(size_t)col * m_b + e]; };          // component e of left vector col
+    auto pfull = [&](int sidx, int e) {                                            // [P0 0; 0 I]
+      if (e < fin.kp) return sidx < fin.U0 ? hp0[(size_t)sidx * ldp + e] : 0.0;
+      return sidx == fin.U0 + (e - fin.kp) ? 1.0 : 0.0;
+    };
+    std::vector<double> ritz((size_t)S * k), comb((size_t)S * kcp, 0.0);
+    for (int sidx = 0; sidx < S; ++sidx)
+      for (int col = 0; col < k; ++col) {
+        double a = 0;
+        for (int e = 0; e < m_b; ++e) a += pfull(sidx, e) * su(e, col);
+        ritz[(size_t)sidx * k + col] = a;                                           // W_new[:, col] = W_s ritz[:, col]
+      }
+    for (int sidx = 0; sidx < S; ++sidx)
+      for (int col = 0; col < nu; ++col) {
+        double a = 0;
+        for (int e = 0; e < k; ++e) a += ritz[(size_t)sidx * k + e] * su(e, col);
+        for (int e = k; e < m_b; ++e) a += pfull(sidx, e) * su(e, col);
+        comb[(size_t)sidx * kcp + col] = a;
+      }
+    CUDA_CHECK(cudaMemcpyAsync(ws.Pmat.p, comb.data(), sizeof(double) * (size_t)S * kcp, cudaMemcpyHostToDevice, st));
+    rotate_w_stored(S, nu, outU.p, nu, var_weigh ? svd_s.p : nullptr);
+    CUDA_CHECK(cudaStreamSynchronize(st));  // comb goes out of scope
+  }
   CUDA_CHECK(cudaMemcpyAsync(outS.p, svd_s.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));
   CUDA_CHECK(cudaStreamSynchronize(st));
 #ifdef ADOBO_B200_TIMELINE

@@ -188,6 +188,21 @@ __global__ void __launch_bounds__(W2_THREADS, 1)
 // thread, in one batch -- and, with several GPUs, exchanges that slice with the same CTA of every peer over NVLink
 // (channel 1 + c of the mailbox, self-validating 16-byte words -- peer_allreduce_ll: eight exchanges in flight, ONE
 // NVLink crossing per Lanczos step where there were two round trips, each behind a serial last-CTA sum).  Every rank adds the slices in rank order: V, Z, B stay bit-identical.
+// Lazy rotation of W (the tall-skinny GEMM W <- W Su[:, :k] of every restart, irlb.py:246, was the largest kernel of
+// the pass: 130 us of 330 per restart at 68 k cells).  W is kept as STORED columns W_s and a small matrix instead:
+//     W[:, c] = W_s[:, :U0] P0[:, c]      for c <  kp   (the Ritz vectors of the last restart)
+//     W[:, c] = W_s[:, U0 + c - kp]       for c >= kp   (columns generated since, stored raw)
+// A restart only multiplies the small matrix (lazy_p0: P0 <- [P0 0; 0 I] Su[:, :k], S x m x k flops instead of
+// n x m x k) and appends the next columns; W_s is rotated for real only when its columns run out (every 6th restart
+// at m_b = 95) and for the final U.  The row kernel works in stored space unchanged -- it gets c_s = [P0 c; c_raw]
+// and returns g_s = W_s^T y -- and v_step_t maps g_s to W^T y and the next coefficients back (two S x k mat-vecs
+// in the cluster's first CTA).  V, Z = A^T W, B and every coefficient stay in the rotated basis as before.
+struct LazyArgs {
+  const double* P0 = nullptr;   // [U0][ldp] row-major, columns >= kp zero
+  const double* P0t = nullptr;  // [kp][MAXB] its transpose
+  int ldp = 0, U0 = 0, kp = 0;  // fresh / just rotated: U0 = kp = 0, every column raw at its own index
+};
+
 constexpr int VT_G0 = MAXB;                  // msg[0 .. 128): rows of t;  msg[128], msg[129]: ||y||^2, sum y;
 constexpr int VT_MSG = VT_G0 + 2 + 16;       // msg[130 .. 146): columns c, c + 8, ... of g
 static_assert(VT_MSG <= PEER_LL_MAX, "a cluster CTA's slice must fit its mailbox channel");
@@ -198,9 +213,10 @@ __global__ void __launch_bounds__(VS_THREADS, 1)
              const double* __restrict__ mu, const double* __restrict__ rs, const double* __restrict__ murs,
              double* __restrict__ sc, double* __restrict__ V, int ldv, int j, int m_b, int h, double* __restrict__ ybuf,
              double* __restrict__ fbuf, double* __restrict__ xs, double* __restrict__ B, const ZArgs z,
-             const int* __restrict__ halt, const PeerComm pc) {
+             const int* __restrict__ halt, const PeerComm pc, const LazyArgs lz) {
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
+  const int slotj = lz.U0 + (j - lz.kp);  // where column j of W is stored = the width of w_step_t's vector g_s
   extern __shared__ __align__(16) double vs_dyn[];
   double(*wacc)[MAXB] = reinterpret_cast<double(*)[MAXB]>(vs_dyn);                    // [VS_WARPS][MAXB]
   double(*psum)[MAXB] = reinterpret_cast<double(*)[MAXB]>(vs_dyn + VS_WARPS * MAXB);  // [8][MAXB]
@@ -211,7 +227,9 @@ __global__ void __launch_bounds__(VS_THREADS, 1)
   __shared__ double red2[VS_WARPS][2];
   __shared__ double nall[VS_CLUSTER][2];
   __shared__ double msg[VT_MSG + 14];
-  __shared__ double gall[MAXB];  // CTA 0: g = W^T y, every column
+  __shared__ double gall[MAXB];  // CTA 0: g_s = W_s^T y, every stored column
+  __shared__ double geff[MAXB];  // CTA 0: g = W^T y in the rotated basis
+  __shared__ double cce[MAXB];   // CTA 0: the next coefficients in the rotated basis
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nd = j + 1;
   const int per = (h + csize - 1) / csize;
@@ -254,11 +272,11 @@ __global__ void __launch_bounds__(VS_THREADS, 1)
     psum[part][col] = (col < nrow) ? sum_partials_part<10>(tpart + r0 + col, part, 8, nblk, hp) : 0.0;  // two batches
     if (warp == 0) {  // ||y||^2 and sum y: the summation order w_finish / w_norm_exchange use (same bits)
       double t0, t1;
-      sum_partials_two(wparts, nblk, j, t0, t1);
+      sum_partials_two(wparts, nblk, slotj, t0, t1);
       if (lane == 0) msg[VT_G0] = t0, msg[VT_G0 + 1] = t1;
     } else if (warp >= 2 && warp < 18) {  // warp 2 + q: column c + 8 q of g
       const int gcol = crank + VS_CLUSTER * (warp - 2);
-      const double v = gcol < j ? sum_partials_warp(wparts + gcol, nblk) : 0.0;
+      const double v = gcol < slotj ? sum_partials_warp(wparts + gcol, nblk) : 0.0;
       if (lane == 0) msg[VT_G0 + warp] = v;
     }
     __syncthreads();
@@ -317,7 +335,7 @@ __global__ void __launch_bounds__(VS_THREADS, 1)
   cluster.barrier_wait();  // every CTA of the cluster is running
   if (tid < 16) {          // this CTA's columns of g to CTA 0, which forms the coefficients of the next W column
     const int gc = crank + VS_CLUSTER * tid;
-    if (gc < j) cluster.map_shared_rank(&gall[0], 0)[gc] = msg[VT_G0 + 2 + tid];
+    if (gc < slotj) cluster.map_shared_rank(&gall[0], 0)[gc] = msg[VT_G0 + 2 + tid];
   }
   {
     const int col = tid & (MAXB - 1), part = tid >> 7;
@@ -434,17 +452,60 @@ __global__ void __launch_bounds__(VS_THREADS, 1)
       }
     }
   }
-  if (ccthread) {
-    // coefficients of the next W column; column j itself: g = 1, sumW[j] = (sum y) / ||y||
-    const int col = tid - 32;
-    double zsum = 0;
-    for (int q = 0; q < csize; ++q) zsum += call2[q][col];
-    const double sw = (col == j) ? su : sw_col;
-    if (col == j) z.sumW[j] = sw;
-    const double mvs = murs ? inv * tot1 : 0.0;
-    double cc = inv * zsum - mvs * sw;
-    if (z.prev) cc -= nrm * ((col == j) ? 1.0 : gall[col] * sinvw);
-    z.cvec[col] = cc;
+  if (z.Z && crank == 0) {
+    // ---- g = W^T y from g_s (lazy rotation: the kp Ritz columns are combinations of the first U0 stored ones) ----
+    {
+      const int col = tid & (MAXB - 1), part = tid >> 7;
+      double p = 0;
+      if (col < lz.kp)
+        for (int sidx = part; sidx < lz.U0; sidx += 8) p = fma(__ldg(lz.P0 + (size_t)sidx * lz.ldp + col), gall[sidx], p);
+      psum[part][col] = p;
+    }
+    __syncthreads();
+    if (tid < j) {
+      double g = 0;
+      if (tid < lz.kp) {
+#pragma unroll
+        for (int g8 = 0; g8 < 8; ++g8) g += psum[g8][tid];
+      } else {
+        g = gall[lz.U0 + tid - lz.kp];
+      }
+      geff[tid] = g;
+    }
+    __syncthreads();
+    if (ccthread) {
+      // coefficients of the next W column; column j itself: g = 1, sumW[j] = (sum y) / ||y||
+      const int col = tid - 32;
+      double zsum = 0;
+      for (int q = 0; q < csize; ++q) zsum += call2[q][col];
+      const double sw = (col == j) ? su : sw_col;
+      if (col == j) z.sumW[j] = sw;
+      const double mvs = murs ? inv * tot1 : 0.0;
+      double cc = inv * zsum - mvs * sw;
+      if (z.prev) cc -= nrm * ((col == j) ? 1.0 : geff[col] * sinvw);
+      cce[col] = cc;
+      if (!z.prev) z.cvec[col] = cc;  // last column of the iteration: conv_check takes them to the next basis
+    }
+    __syncthreads();
+    if (z.prev) {
+      // ---- the coefficients in stored space for w_step_t: c_s = [P0 c[:kp] ; c[kp:]] ----
+      const int sidx = tid & (MAXB - 1), part = tid >> 7;
+      double p = 0;
+      if (sidx < lz.U0)
+        for (int col = part; col < lz.kp; col += 8) p = fma(__ldg(lz.P0t + (size_t)col * MAXB + sidx), cce[col], p);
+      psum[part][sidx] = p;
+      __syncthreads();
+      if (tid <= slotj) {
+        double cs = 0;
+        if (tid < lz.U0) {
+#pragma unroll
+          for (int g8 = 0; g8 < 8; ++g8) cs += psum[g8][tid];
+        } else {
+          cs = cce[lz.kp + tid - lz.U0];
+        }
+        z.cvec[tid] = cs;
+      }
+    }
   }
   if (crank == 0 && tid == 0) {
     sc[SC_S] = s;              // ||w_j||: w_step_t normalises W[:, j] with it, B[j, j]  (irlb.py:196 / 221)
@@ -477,4 +538,60 @@ __global__ void __launch_bounds__(256) w_norm_exchange(const double* __restrict_
   __syncthreads();
   if (pc.world > 1) peer_allreduce_ll(pc, two, 2, 0);
   if (threadIdx.x < 2) out2[threadIdx.x] = two[threadIdx.x];
+}
+
+// ---- last column of an outer iteration: W_s[:, slot] = y / ||y||, B[jn, jn] = ||y|| ------------------------------------
+// (the columns before it were written by the w_step_t that followed them).  One GPU: the norm is summed from
+// w_step_t's partials here (columns slot, slot + 1); several GPUs: n2p holds the exchanged pair.
+__global__ void w_finish_t(const double* __restrict__ ybuf, const double* __restrict__ n2p, double* __restrict__ sc,
+                           double* __restrict__ W, int ldw, int slot, int jn, i64 n, double* __restrict__ B, int m_b,
+                           const int* __restrict__ halt, const double* __restrict__ parts, int nblk) {
+  if (halt && *halt) return;
+  __shared__ double s_n2[2];
+  if (parts) {
+    if (threadIdx.x < 32) {
+      double t0, t1;
+      sum_partials_two(parts, nblk, slot, t0, t1);
+      if (threadIdx.x == 0) s_n2[0] = t0, s_n2[1] = t1;
+    }
+    __syncthreads();
+  }
+  const double n2v = parts ? s_n2[0] : n2p[0], syv = parts ? s_n2[1] : n2p[1];
+  const double s = sqrt(n2v);
+  const double sinv = inv_or_zero(s);
+  const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) W[(size_t)r * ldw + slot] = sinv * ybuf[r];
+  if (r == 0) {
+    sc[SC_S] = s;
+    sc[SC_SU] = sinv * syv;
+    B[(size_t)jn * m_b + jn] = s;  // irlb.py:196 / 221
+  }
+}
+
+// ---- lazy_p0: the small matrix of the lazy rotation after a restart -------------------------------------------------
+// P0_new = [P0 0; 0 I] Su[:, :kn]   (S rows: the U0 stored columns behind the old Ritz vectors, then the m - kp raw ones).
+// One CTA per row s, in place (row s of the product needs row s of P0 only); outputs: P0 (row stride ldp, zero
+// padded), its transpose P0t, and -- for the launches that rotate W_s for real -- the same matrix with row stride
+// kcp = kn rounded up to 8, the layout rotate_basis / rotate_rows read their rotation matrix in.
+__global__ void __launch_bounds__(128) lazy_p0(double* __restrict__ P0, double* __restrict__ P0t, int ldp, int U0, int kp,
+                                               const double* __restrict__ Su, int m, int kn, double* __restrict__ Pmat,
+                                               int kcp, const int* __restrict__ halt) {
+  if (halt && *halt) return;
+  __shared__ double row[MAXB];
+  const int sidx = blockIdx.x, c = threadIdx.x;
+  if (sidx < U0)
+    for (int e = c; e < kp; e += 128) row[e] = P0[(size_t)sidx * ldp + e];
+  __syncthreads();
+  double v = 0.0;
+  if (c < kn) {
+    const double* su = Su + (size_t)c * m;  // left singular vector c (column-major)
+    if (sidx < U0) {
+      for (int e = 0; e < kp; ++e) v = fma(row[e], su[e], v);
+    } else {
+      v = su[kp + (sidx - U0)];
+    }
+  }
+  if (c < ldp) P0[(size_t)sidx * ldp + c] = v;
+  if (c < kn) P0t[(size_t)c * MAXB + sidx] = v;
+  if (Pmat && c < kcp) Pmat[(size_t)sidx * kcp + c] = v;
 }

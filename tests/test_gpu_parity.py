@@ -224,7 +224,7 @@ def test_knn_blobs_30k_tensor_core_path(eng):
 
 @pytest.mark.parametrize('hook', ['svd_jacobi', 'svd_fallback', 'no_graph', 'no_fork', 'rotate_streamed', 'no_fusedt',
                                   'no_fusedt,no_vone', 'no_zpath', 'no_vstep', 'no_fusedt,no_wfold', 'no_fusedt,no_split',
-                                  'no_pdl', 'no_runahead', 'no_fusedt,no_pdl', 'SVD_CLUSTER'])
+                                  'no_pdl', 'no_runahead', 'no_fusedt,no_pdl', 'no_lazy', 'no_lazy,no_graph', 'SVD_CLUSTER'])
 def test_irlb_alternative_paths(eng, hook, monkeypatch):
     """Every fallback of the Lanczos driver (ADOBO_B200_IRLB hooks, csrc/irlb.cu: the kernels for sizes the two-kernel
     step does not cover, the generic Jacobi SVD of B, the synchronous forms of the asynchronous mechanisms) must give
@@ -303,7 +303,7 @@ def test_snn_counts_are_the_reference_matrix_entries(eng):
         V = O.snn_counts(case['nn_idx'])
         ref = np.asarray(V[edges[:, 0], edges[:, 1]]).ravel()
         appended = (edges[:, 0] == edges[:, 1]) & (v == 0)            # nodes without any kept edge (clustering.py:114-118)
-        assert np.array_equal(v[~appended], ref[~appended]) and v[~appended].min() >= 1 and v.max() <= case['k']
+        assert np.array_equal(v[~appended], ref[~appended]) and v[~appended].min() >= 1   # duplicates in nn_idx add up
 
 
 def test_impute_subpopulations_front_half(eng):
