@@ -1946,13 +1946,8 @@ __global__ void set_restart(double* __restrict__ V, int ldv, int h, const double
     if (t < k) sumW[t] = crot[MAXB + t];
     if (lz.P0 == nullptr) {
       if (t < k) cvec[t] = crot[t];
-    } else if (t < nds) {  // lazy rotation: the coefficients in stored space, c_s = [P0 c[:kp] ; c[kp:]]
-      double v = 0.0;
-      if (t < lz.U0)
-        for (int cc = 0; cc < lz.kp; ++cc) v = fma(lz.P0[(size_t)t * lz.ldp + cc], crot[cc], v);
-      else
-        v = crot[lz.kp + t - lz.U0];
-      cvec[t] = v;
+    } else if (t >= lz.U0 && t < nds) {  // lazy rotation: c_s = [P0 c[:kp] ; c[kp:]] -- lazy_p0 has left the first part
+      cvec[t] = crot[lz.kp + t - lz.U0];
     }
   }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2445,7 +2440,8 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     const int kcp = (k + 7) & ~7;
     rotate2(k, nullptr, nullptr, 0, nullptr, true, false);  // V and Z
     LAUNCH(c, "lazy_p0", (lazy_p0<<<prev.S, 128, 0, st>>>(ws.P0.p, ws.P0t.p, ldp, prev.U0, prev.kp, Su.p, m_b, k,
-                                                         mat ? ws.Pmat.p : nullptr, kcp, hp_halt)));
+                                                         mat ? ws.Pmat.p : nullptr, kcp, hp_halt,
+                                                         mat ? nullptr : (const double*)ws.crot.p, cvec.p)));
     if (mat) rotate_w_stored(prev.S, k, nullptr, 0, nullptr);  // W_s[:, :k] = the Ritz vectors themselves again
     LAUNCH(c, "set_restart", (set_restart<<<sr_grid, 256, 0, st>>>(V.p, ld, h, fbuf.p, B.p, m_b, k, svd_s.p, R.p, cvec.p, sumW.p,
                                                                 ws.crot.p, hp_halt, lazy_args(next), next.U0 + (k - next.kp))));
@@ -2692,7 +2688,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     // U = W_s [P0 0; 0 I] Su[:, :nu]: the small product first, then one real rotation of the stored columns
     rotate2(nu, outV.p, nullptr, nu, nullptr, false, false);
     LAUNCH(c, "lazy_p0", (lazy_p0<<<fin.S, 128, 0, st>>>(ws.P0.p, ws.P0t.p, ldp, fin.U0, fin.kp, Su.p, m_b, nu, ws.Pmat.p,
-                                                        (nu + 7) & ~7, nullptr)));
+                                                        (nu + 7) & ~7, nullptr, nullptr, nullptr)));
     rotate_w_stored(fin.S, nu, outU.p, nu, var_weigh ? svd_s.p : nullptr);
   } else {
     // Not converged within maxit.  The reference then rotates the first k columns of V and W once more and multiplies

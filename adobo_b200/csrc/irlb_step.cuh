@@ -31,18 +31,16 @@ struct WTRow {
   double wv[NH], yp;
   int b, len;
 };
+// (b, e1): the row's pointers -- loaded one pair EARLIER than the entries they delimit, so that the chain
+// row pointers -> entries -> gather never stalls a prefetch on two dependent round trips (ncu: the first use of the
+// prefetched entries and of the row length were the two hottest stall sites of the kernel)
 template <typename VT, int NH>
-__device__ __forceinline__ void wt_load(WTRow<VT, NH>& R, bool ok, const i64* __restrict__ rptr, int row,
+__device__ __forceinline__ void wt_load(WTRow<VT, NH>& R, bool ok, int b, int e1, int row,
                                         const int* __restrict__ cl, const VT* __restrict__ vl,
                                         const double* __restrict__ wr, const double* __restrict__ ybuf, bool lazy,
                                         const bool (&cm)[NH], int hl) {
-  int b = 0, e1 = 0;
-  if (ok) {
-    b = (int)__ldg(rptr + row);
-    e1 = (int)__ldg(rptr + row + 1);
-  }
   R.b = b;
-  R.len = e1 - b;
+  R.len = ok ? e1 - b : 0;
 #pragma unroll
   for (int q = 0; q < W3_EPF; ++q) {
     const bool in = hl + 16 * q < R.len;
@@ -85,7 +83,10 @@ __global__ void __launch_bounds__(W2_THREADS, 1)
   const VT* vl = rval + hl;
   const double* wr = W + (size_t)r * ldw + hl;
   WTRow<VT, NH> RA, RB;
-  wt_load<VT, NH>(RA, r < rend, rptr, r, cl, vl, wr, ybuf, lazy, cm, hl);
+  int pb = 0, pe = 0, qb = 0, qe = 0;  // pointers of this half-warp's rows r and r + 2
+  if (r < rend) pb = (int)__ldg(rptr + r), pe = (int)__ldg(rptr + r + 1);
+  if (r + 2 < rend) qb = (int)__ldg(rptr + r + 2), qe = (int)__ldg(rptr + r + 3);
+  wt_load<VT, NH>(RA, r < rend, pb, pe, r, cl, vl, wr, ybuf, lazy, cm, hl);
   pdl_sync();
   if (halt && *halt) return;
   TL_SYNC(nd);
@@ -103,7 +104,9 @@ __global__ void __launch_bounds__(W2_THREADS, 1)
   // one pair of rows: issue the loads of the next pair (into NX), then reduce and scatter the current one (CU)
   auto step = [&](WTRow<VT, NH>& CU, WTRow<VT, NH>& NX) {
     wr += 2 * (size_t)ldw;
-    wt_load<VT, NH>(NX, r + 2 < rend, rptr, r + 2, cl, vl, wr, ybuf, lazy, cm, hl);
+    wt_load<VT, NH>(NX, r + 2 < rend, qb, qe, r + 2, cl, vl, wr, ybuf, lazy, cm, hl);
+    qb = qe = 0;
+    if (r + 4 < rend) qb = (int)__ldg(rptr + r + 4), qe = (int)__ldg(rptr + r + 5);  // two pairs ahead
     const bool ok = r < rend;
     const double wp = sinvp * CU.yp;  // W[r, jprev]
     if (mine) {
@@ -573,11 +576,15 @@ __global__ void w_finish_t(const double* __restrict__ ybuf, const double* __rest
 // One CTA per row s, in place (row s of the product needs row s of P0 only); outputs: P0 (row stride ldp, zero
 // padded), its transpose P0t, and -- for the launches that rotate W_s for real -- the same matrix with row stride
 // kcp = kn rounded up to 8, the layout rotate_basis / rotate_rows read their rotation matrix in.
+// With crot != nullptr the CTA also leaves c_s[s] = P0_new[s, :] . crot, the coefficients of the restart's first new
+// column in stored space (crot: conv_check's coefficients in the new rotated basis).
 __global__ void __launch_bounds__(128) lazy_p0(double* __restrict__ P0, double* __restrict__ P0t, int ldp, int U0, int kp,
                                                const double* __restrict__ Su, int m, int kn, double* __restrict__ Pmat,
-                                               int kcp, const int* __restrict__ halt) {
+                                               int kcp, const int* __restrict__ halt, const double* __restrict__ crot,
+                                               double* __restrict__ cvec_s) {
   if (halt && *halt) return;
   __shared__ double row[MAXB];
+  __shared__ double red[4];
   const int sidx = blockIdx.x, c = threadIdx.x;
   if (sidx < U0)
     for (int e = c; e < kp; e += 128) row[e] = P0[(size_t)sidx * ldp + e];
@@ -594,4 +601,10 @@ __global__ void __launch_bounds__(128) lazy_p0(double* __restrict__ P0, double* 
   if (c < ldp) P0[(size_t)sidx * ldp + c] = v;
   if (c < kn) P0t[(size_t)c * MAXB + sidx] = v;
   if (Pmat && c < kcp) Pmat[(size_t)sidx * kcp + c] = v;
+  if (crot) {
+    double p = warp_sum(c < kn ? v * crot[c] : 0.0);
+    if ((c & 31) == 0) red[c >> 5] = p;
+    __syncthreads();
+    if (c == 0) cvec_s[sidx] = (red[0] + red[1]) + (red[2] + red[3]);
+  }
 }

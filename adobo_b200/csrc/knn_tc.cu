@@ -6,9 +6,13 @@
 //        s(q, r) = q . r - 1/2 ||r||^2          (largest s  <=>  smallest ||q - r||^2)
 //
 // with fp32 accuracy out of TF32 MMAs: every centred fp32 coordinate is split into two TF32
-// numbers x = hi + lo and the operands are laid out as K' = 3 Kp columns
-//        A' = [ q_hi | q_hi | q_lo ],   B' = [ r_hi | r_lo | r_hi ]     (A' B'^T = hi.hi + hi.lo + lo.hi)
-// and two spare columns of the first segment carry the norm:  A' = 1, 1 ;  B' = -rn_hi/2, -rn_lo/2.
+// numbers x = hi + lo, the operands are stored as 2 Kp columns each,
+//        A' = [ q_hi | q_lo ],   B' = [ r_hi | r_lo ],
+// and three products are accumulated per k-block: q_hi.r_hi and q_lo.r_hi against ONE staged block of r_hi, then
+// q_hi.r_lo (hi.hi + lo.hi + hi.lo).  The reference side is what streams through L2 -- every CTA reads all of B' for
+// its 128 queries, 6.5 TB/s at 1 M points when r_hi was staged twice -- so a block of B' is loaded once per use
+// pair: two thirds of the traffic for the same MMAs.
+// Two spare columns of the hi segments carry the norm:  A' = 1, 1 ;  B' = -rn_hi/2, -rn_lo/2.
 // The epilogue therefore does NO arithmetic: a score is a candidate iff it exceeds the thread's
 // current 32nd/64th best, one compare per element.
 //
@@ -108,13 +112,13 @@ __device__ __forceinline__ float tf32_round(float x) {
 }
 
 // ---- operand preparation ------------------------------------------------------------------------
-// x: n x p fp64; writes A' and B' (npad x Kt fp32, Kt = 3 Kp), fp32 norms of the centred points
+// x: n x p fp64; writes A' = [q_hi | q_lo] and B' = [r_hi | r_lo] (npad x 2 Kp fp32), fp32 norms of the centred points
 __global__ void knn_tc_prep(const double* __restrict__ x, i64 n, i64 npad, int p, int Kp, const double* __restrict__ ctr,
                             float* __restrict__ Aop, float* __restrict__ Bop, float* __restrict__ norms,
                             unsigned* __restrict__ maxnorm_bits) {
   const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npad) return;
-  const int Kt = 3 * Kp;
+  const int Kt = 2 * Kp;
   float* a = Aop + (size_t)i * Kt;
   float* b = Bop + (size_t)i * Kt;
   for (int d = 0; d < Kt; ++d) {
@@ -128,11 +132,9 @@ __global__ void knn_tc_prep(const double* __restrict__ x, i64 n, i64 npad, int p
       nrm = fmaf(v, v, nrm);
       const float hi = tf32_round(v), lo = tf32_round(v - hi);
       a[d] = hi;
-      a[Kp + d] = hi;
-      a[2 * Kp + d] = lo;
+      a[Kp + d] = lo;
       b[d] = hi;
       b[Kp + d] = lo;
-      b[2 * Kp + d] = hi;
     }
     norms[i] = nrm;
     atomicMax(maxnorm_bits, __float_as_uint(nrm));
@@ -153,16 +155,16 @@ constexpr int TC_POOL = 16;  // pool slots per query row = columns per tcgen05.l
 
 template <int E>  // shortlist length KP = 32 E
 __global__ void __launch_bounds__(TC_THREADS, 1)
-    knn_scores_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int KB /* k-blocks */,
-                  int nstages, int lists_in_smem, i64 ntiles, i64 qtile0, i64 q_begin, i64 q_end,
+    knn_scores_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                  int KB /* k-blocks per segment: A' and B' hold 2 KB each */, int nstages, int lists_in_smem, i64 ntiles, i64 qtile0, i64 q_begin, i64 q_end,
                   float* __restrict__ out_key, int* __restrict__ out_idx, float* __restrict__ gl_key,
                   int* __restrict__ gl_idx) {
   constexpr int KP = 32 * E;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024-byte aligned operand blocks first, then shortlists / pools / barriers
   unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned char* sA = base;                                   // KB blocks
-  unsigned char* sB = base + (size_t)KB * TC_BLOCK_BYTES;     // nstages blocks
+  unsigned char* sA = base;                                   // 2 KB blocks: q_hi, then q_lo
+  unsigned char* sB = base + (size_t)2 * KB * TC_BLOCK_BYTES; // nstages blocks
   unsigned char* after = sB + (size_t)nstages * TC_BLOCK_BYTES;
   float* pool_key = reinterpret_cast<float*>(after);          // [128][TC_POOL]
   int* pool_idx = reinterpret_cast<int*>(pool_key + TC_M * TC_POOL);
@@ -202,13 +204,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   if (warp == 0) {
     if (lane == 0) {
       // ---- TMA producer ----
-      mbar_expect_tx(a_full, (uint32_t)KB * TC_BLOCK_BYTES);
-      for (int kb = 0; kb < KB; ++kb)
+      mbar_expect_tx(a_full, (uint32_t)(2 * KB) * TC_BLOCK_BYTES);
+      for (int kb = 0; kb < 2 * KB; ++kb)
         tma_load_2d(sA + (size_t)kb * TC_BLOCK_BYTES, &mapA, a_full, kb * TC_KB, (int)(qtile * TC_M));
       int s = 0;
       uint32_t ph = 0;
       for (i64 t = 0; t < ntiles; ++t)
-        for (int kb = 0; kb < KB; ++kb) {
+        for (int kb = 0; kb < 2 * KB; ++kb) {  // r_hi blocks, then r_lo blocks
           mbar_wait(empty + s, ph ^ 1);
           mbar_expect_tx(full + s, TC_BLOCK_BYTES);
           tma_load_2d(sB + (size_t)s * TC_BLOCK_BYTES, &mapB, full + s, kb * TC_KB, (int)(t * TC_N));
@@ -231,16 +233,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         mbar_wait(tmem_empty + acc, accph ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * TC_N;
-        for (int kb = 0; kb < KB; ++kb) {
+        for (int kb = 0; kb < 2 * KB; ++kb) {
           mbar_wait(full + s, ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + (size_t)kb * TC_BLOCK_BYTES);
+          const bool hi = kb < KB;                   // staged block: r_hi[kb] or r_lo[kb - KB]
+          const int ka = hi ? kb : kb - KB;
+          const uint32_t ah_addr = smem_u32(sA + (size_t)ka * TC_BLOCK_BYTES);         // q_hi
+          const uint32_t al_addr = smem_u32(sA + (size_t)(KB + ka) * TC_BLOCK_BYTES);  // q_lo
           const uint32_t b_addr = smem_u32(sB + (size_t)s * TC_BLOCK_BYTES);
 #pragma unroll
           for (int k = 0; k < TC_KB / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes along the swizzled row
-            const uint64_t da = umma_desc_sw128(a_addr + k * 32);
             const uint64_t db = umma_desc_sw128(b_addr + k * 32);
-            umma_tf32(tmem_d, da, db, TC_IDESC, (kb | k) ? 1u : 0u);
+            umma_tf32(tmem_d, umma_desc_sw128(ah_addr + k * 32), db, TC_IDESC, (kb | k) ? 1u : 0u);  // q_hi.r_hi / q_hi.r_lo
+            if (hi) umma_tf32(tmem_d, umma_desc_sw128(al_addr + k * 32), db, TC_IDESC, 1u);         // q_lo.r_hi
           }
           umma_commit(empty + s);  // frees the B block when these MMAs have read it
           if (++s == nstages) {
@@ -382,8 +387,8 @@ static CUtensorMap make_map(float* ptr, i64 rows, int Kt) {
 // Can the tensor-core shortlist take this problem?  A' must stay resident next to >= 2 B' stages.
 bool knn_tc_supported(int p) {
   const int Kp = (p + 2 + TC_KB - 1) / TC_KB * TC_KB;
-  const int KB = 3 * Kp / TC_KB;
-  return (size_t)(KB + 2) * TC_BLOCK_BYTES + 1024 + (size_t)TC_M * TC_POOL * 8 + 256 <= 227 * 1024;
+  const int KB = Kp / TC_KB;
+  return (size_t)(2 * KB + 2) * TC_BLOCK_BYTES + 1024 + (size_t)TC_M * TC_POOL * 8 + 256 <= 227 * 1024;
 }
 
 // x: all points (n x p fp64, device).  Fills skey/sidx ((q_end-q_begin) x KP) for queries [q_begin, q_end),
@@ -392,7 +397,7 @@ void run_knn_shortlist_tc(adobo_ctx* c, const double* x, i64 n, int p, const dou
                           float* skey, int* sidx, DevBuf<float>& norms, unsigned* maxnorm) {
   cudaStream_t st = c->stream;
   const int Kp = (p + 2 + TC_KB - 1) / TC_KB * TC_KB;
-  const int Kt = 3 * Kp, KB = Kt / TC_KB;
+  const int Kt = 2 * Kp, KB = Kp / TC_KB;
   const i64 npad = (n + TC_N - 1) / TC_N * TC_N;
   DevBuf<float> Aop, Bop;
   Aop.ensure((size_t)npad * Kt);
@@ -407,7 +412,7 @@ void run_knn_shortlist_tc(adobo_ctx* c, const double* x, i64 n, int p, const dou
   // shared memory: A' resident + B' ring + pools + barriers (+ shortlists when they still leave >= 2 stages)
   const size_t cap = 227 * 1024, fixed = 1024 /*align*/ + (size_t)TC_M * TC_POOL * 8 + 256;
   const size_t lists = (size_t)TC_M * KP * 8;
-  const size_t a_bytes = (size_t)KB * TC_BLOCK_BYTES;
+  const size_t a_bytes = (size_t)2 * KB * TC_BLOCK_BYTES;
   const int lists_in_smem = (a_bytes + 2 * (size_t)TC_BLOCK_BYTES + fixed + lists <= cap) ? 1 : 0;
   int nstages = (int)((cap - a_bytes - fixed - (lists_in_smem ? lists : 0)) / TC_BLOCK_BYTES);
   if (nstages > 6) nstages = 6;
@@ -419,7 +424,7 @@ void run_knn_shortlist_tc(adobo_ctx* c, const double* x, i64 n, int p, const dou
     glk.ensure((size_t)(qt1 - qt0) * TC_M * KP);
     gli.ensure((size_t)(qt1 - qt0) * TC_M * KP);
   }
-  WORK(c, 2.0 * (double)(qt1 - qt0) * TC_M * (double)npad * Kt);  // tf32 flops actually issued
+  WORK(c, 2.0 * (double)(qt1 - qt0) * TC_M * (double)npad * 3.0 * Kp);  // tf32 flops actually issued (three products)
   if (E == 1) {
     CUDA_CHECK(cudaFuncSetAttribute(knn_scores_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LAUNCH(c, "knn_scores_tc", (knn_scores_tc<1><<<(unsigned)(qt1 - qt0), TC_THREADS, smem, st>>>(
