@@ -280,17 +280,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const uint32_t accph = (uint32_t)((t >> 1) & 1);
       mbar_wait(tmem_full + acc, accph);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < TC_N / TC_POOL; ++c) {
-        uint32_t v[16];
+      // the TMEM loads are pipelined one chunk deep: chunk c + 1 is in flight while chunk c is compared
+      uint32_t v[16], w[16];
+      auto tmem_ld16 = [&](uint32_t (&d)[16], int c) {
         const uint32_t taddr = tmem_base + ((uint32_t)(slab * 32) << 16) + (uint32_t)(acc * TC_N + c * TC_POOL);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]),
+              "=r"(d[8]), "=r"(d[9]), "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15])
             : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      };
+      tmem_ld16(w, 0);
+#pragma unroll 1
+      for (int c = 0; c < TC_N / TC_POOL; ++c) {
+        // the loaded registers are operands of the wait: nothing that reads them may be scheduled above it
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]),
+                       "+r"(w[8]), "+r"(w[9]), "+r"(w[10]), "+r"(w[11]), "+r"(w[12]), "+r"(w[13]), "+r"(w[14]), "+r"(w[15])
+                     :
+                     : "memory");
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = w[j];
+        if (c + 1 < TC_N / TC_POOL) tmem_ld16(w, c + 1);
         int cnt = 0;
         const int ref0 = (int)(t * TC_N + c * TC_POOL);
 #pragma unroll
@@ -415,7 +427,7 @@ void run_knn_shortlist_tc(adobo_ctx* c, const double* x, i64 n, int p, const dou
   const size_t a_bytes = (size_t)2 * KB * TC_BLOCK_BYTES;
   const int lists_in_smem = (a_bytes + 2 * (size_t)TC_BLOCK_BYTES + fixed + lists <= cap) ? 1 : 0;
   int nstages = (int)((cap - a_bytes - fixed - (lists_in_smem ? lists : 0)) / TC_BLOCK_BYTES);
-  if (nstages > 6) nstages = 6;
+  if (nstages > 8) nstages = 8;  // the barrier block holds 8 full / empty pairs
   REQUIRE(nstages >= 2, ADOBO_ERR_LIMIT, "knn: embedding too wide for the tensor-core shortlist");
   const size_t smem = a_bytes + (size_t)nstages * TC_BLOCK_BYTES + fixed + (lists_in_smem ? lists : 0);
   DevBuf<float> glk;

@@ -68,6 +68,7 @@ def parse_args():
     ap.add_argument('--parity', default='fast', choices=['off', 'fast', 'full'],
                     help='c3/c4: fast = stage-wise exact / property checks; full = also the whole oracle on the full matrix')
     ap.add_argument('--profile-steps', type=int, default=2)
+    ap.add_argument('--ks', default='', help='c5: comma-separated k values (default 10,20,30)')
     return ap.parse_args()
 
 
@@ -525,7 +526,7 @@ def run_c5(args, eng, dist, rank, world, local_rank, barrier, max_over_ranks):
     sweep = []
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches = 0
-    for k in C5['ks']:
+    for k in ([int(x) for x in args.ks.split(',')] if args.ks else C5['ks']):
         for _ in range(args.warmup):
             eng.knn(None, k, fetch=False)
             eng.snn(None, k, 0.067, fetch=False)

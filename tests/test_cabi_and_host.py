@@ -134,3 +134,33 @@ def test_csr_backed_dataset_matches_frame_backed():
     fa = ca
     kf = ResidentKey(fa)
     assert kf.matches(fa) and not kf.matches(fa.copy())
+
+
+def test_partitioner_hand_off_builds_the_reference_graph(monkeypatch):
+    """f2: `_igraph_from_edges` (arrays straight into igraph) executed against a recording stand-in for igraph --
+    the package is absent here -- and compared with what the reference's construction hands over
+    (clustering.py:154-162: vertex count from the first column, 1-based names, edges as tuples from itertuples)."""
+    import types
+    from adobo_b200 import clustering
+
+    class Graph:
+        def __init__(self):
+            self.n = 0
+            self.vs = {}
+            self.edges = None
+
+        def add_vertices(self, n):
+            self.n += n
+
+        def add_edges(self, e):
+            self.edges = [tuple(int(v) for v in row) for row in e]
+
+    monkeypatch.setitem(__import__('sys').modules, 'igraph', types.SimpleNamespace(Graph=Graph))
+    rng = np.random.default_rng(0)
+    src = np.sort(rng.integers(0, 50, 400))
+    snn_graph = pd.DataFrame({'source_node': src, 'target_node': rng.integers(0, 50, 400)})
+    g = clustering._igraph_from_edges(snn_graph)
+    # the reference: nodes = unique(first column); names 1..n; edges = [(row[0], row[1]) for row in itertuples]
+    nodes = np.unique(snn_graph[snn_graph.columns[0]])
+    ref_edges = [(int(r[0]), int(r[1])) for r in snn_graph.itertuples(index=False)]
+    assert g.n == len(nodes) and g.vs['name'] == list(range(1, len(nodes) + 1)) and g.edges == ref_edges
