@@ -290,6 +290,7 @@ static void upload_pattern(adobo_ctx* c, i64 n, int g, const i64* indptr, const 
   CUDA_CHECK(cudaMemcpyAsync(c->indptr.p, indptr, sizeof(i64) * (n + 1), cudaMemcpyHostToDevice, c->stream));
   if (nnz) CUDA_CHECK(cudaMemcpyAsync(c->indices.p, indices, sizeof(int) * nnz, cudaMemcpyHostToDevice, c->stream));
   c->have_counts = c->have_norm = c->have_moments = c->have_pca = c->have_knn = false;
+  c->have_suboffs = false;
   refresh_partition(c);
 }
 
@@ -551,6 +552,7 @@ int adobo_synth_counts(adobo_ctx* c, int64_t n_rows, int32_t n_genes, int64_t ro
   run_synth_counts(c, n_rows, n_genes, row_begin, seed, lam_table, n_clusters, &nnz);
   c->have_counts = true;
   c->have_norm = c->have_moments = c->have_pca = c->have_knn = false;
+  c->have_suboffs = false;
   refresh_partition(c);
   if (out_nnz) *out_nnz = nnz;
   API_END

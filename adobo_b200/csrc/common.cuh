@@ -145,6 +145,9 @@ struct adobo_ctx {
   double val_bound = 0;             // max |normalized value| when known analytically (0: measure it)
   double zero_level = 0;            // value of the implicit zeros of the normalized matrix: vals hold y - zero_level
   bool have_moments = false;
+  adobo::DevBuf<int> suboffs;       // gene moments: per row, where each column sub-range starts (moments.cu)
+  bool have_suboffs = false;
+  int suboffs_gw = 0;
   std::vector<double> h_mean, h_var;
   std::vector<int> hvg_order;  // reference output order
   // ---- PCA ----

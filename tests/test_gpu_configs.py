@@ -32,7 +32,7 @@ def test_normalize_at_config_shape(eng, cfg):
     assert abs(vals.data.sum() - float(cfg['norm_sum'])) <= 1e-12 * float(cfg['norm_sum'])
 
 
-def test_moments_and_hvg_at_config_shape(eng, cfg):
+def test_moments_and_hvg_at_config_shape(eng, cfg, monkeypatch):
     from oracle import adobo_oracle as O
     eng.upload_counts(cfg['counts_csr'])
     eng.normalize(10000, 1, 1.0, want_values=False)
@@ -47,6 +47,12 @@ def test_moments_and_hvg_at_config_shape(eng, cfg):
     eng.normalize(10000, 1, 1.0, want_values=False)
     mean2, var2 = eng.gene_moments()
     assert np.array_equal(mean, mean2) and np.array_equal(var, var2, equal_nan=True)
+    # the tiled kernel (private accumulators in shared memory, no atomics) and the atomic one (small matrices) add the
+    # same integers: same bits
+    monkeypatch.setenv('ADOBO_B200_MOMENTS_ATOMIC', '1')
+    eng.normalize(10000, 1, 1.0, want_values=False)
+    mean3, var3 = eng.gene_moments()
+    assert np.array_equal(mean, mean3) and np.array_equal(var, var3, equal_nan=True)
 
 
 def test_irlb_at_config_shape(eng, cfg, capsys):
