@@ -53,7 +53,10 @@ __global__ void __launch_bounds__(256) csr_gene_moments(const i64* __restrict__ 
 // once per uploaded matrix from the column ids, 4 bytes per non-zero of extra reading).  CTA (row block, tile)
 // writes its GT sums to a scratch slab and moments_combine adds the slabs per gene.  Fixed-point integers throughout:
 // any order, any launch shape, any sharding gives the same bits.
-constexpr int GM_WARPS = 16, GM_THREADS = GM_WARPS * 32, GM_MAX_GT = 12288;
+#ifndef ADOBO_GM_WARPS
+#define ADOBO_GM_WARPS 16
+#endif
+constexpr int GM_WARPS = ADOBO_GM_WARPS, GM_THREADS = GM_WARPS * 32, GM_MAX_GT = 12288;
 
 // offs[q][row] = number of entries of the row whose column id lies below sub-range q (q = 0 .. NS), one warp per row
 __global__ void __launch_bounds__(256) sub_offsets(const i64* __restrict__ indptr, const int* __restrict__ indices, i64 n,
