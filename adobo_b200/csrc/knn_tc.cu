@@ -21,10 +21,12 @@
 //              ring of B' blocks, cp.async.bulk.tensor.2d -> mbarrier complete_tx
 //   warp 1     MMA issuer: tcgen05.mma.cta_group::1.kind::tf32, M=128, N=128, K=8 per instruction,
 //              accumulators in TMEM (2 x 128 columns, double buffered), tcgen05.commit -> mbarriers
-//   warps 2-5  epilogue: tcgen05.ld 32x32b.x16 (thread = query row), one compare per score against the
-//              row's threshold; the rare survivors go to a 16-slot pool per row in shared memory and
-//              the warp then merges the pools of its 32 rows cooperatively into the sorted shortlists
-//              (lanes hold the list, shuffle insertion -- no divergent per-thread insertion)
+//   warps 2-5  epilogue: tcgen05.ld 32x32b.x16 (thread = query row).  A chunk of 16 scores whose maximum does not
+//              exceed the row's threshold costs a max tree and one compare; survivors are appended to a 32-slot pool
+//              per row in shared memory.  A pool is merged into the row's sorted shortlist only when the next chunk
+//              could overflow it: the warp sorts the pool across its lanes (bitonic network) and merges it with the
+//              list by one reversed min step + a bitonic merge -- ~20 batched merges per row at 68 k points where
+//              an insertion per survivor took 250 (and was what the kernel spent its time on: tensor pipe 21 % busy)
 // The shortlist is re-ranked in fp64 and certified by knn_rerank (knn.cu), exactly as before.
 #include <cuda.h>
 
@@ -64,6 +66,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// The producer and the MMA issuer are single threads that share a scheduler with an epilogue warp: a bare try_wait
+// loop re-issues every ~9 cycles (ncu: 3.7e8 try_waits in an 11 ms launch, the XU pipe 87 % busy with them), so
+// they back off between polls
+#ifndef ADOBO_KNN_SPIN_NS
+#define ADOBO_KNN_SPIN_NS 32
+#endif
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  for (;;) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (ADOBO_KNN_SPIN_NS > 0) __nanosleep(ADOBO_KNN_SPIN_NS);
+  }
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -84,6 +108,30 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// one lane of a converged warp (CUTLASS elect_one_sync)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync _|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// A from tensor memory (lane = row of A, one 32-bit column per k), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -151,31 +199,51 @@ __global__ void knn_tc_prep(const double* __restrict__ x, i64 n, i64 npad, int p
 }
 
 // ---- the tensor-core kernel ------------------------------------------------------------------------
-constexpr int TC_POOL = 16;  // pool slots per query row = columns per tcgen05.ld step
+constexpr int TC_ACC = 3;                            // most accumulators in TMEM (3 x 128 columns when A' leaves room, else 2):
+                                                     // the epilogue's time per tile varies (pool merges)
+constexpr int TC_CHUNK = 16;                         // columns per append / flush-check step
+constexpr int TC_POOL = 32;                          // pool slots per query row; flushed when a chunk might not fit
+constexpr int TC_POOL_STRIDE = TC_M * 8 + 8;         // bytes between slots: [slot][row] of {score, ref}, padded so that
+                                                     // both the appends (same slot, 32 rows) and the flush (32 slots,
+                                                     // one row) are free of bank conflicts
+constexpr int TC_POOL_BYTES = TC_POOL * TC_POOL_STRIDE;
 
-template <int E>  // shortlist length KP = 32 E
+__device__ __forceinline__ bool better(float ka, int ia, float kb, int ib) { return ka > kb || (ka == kb && ia < ib); }
+// compare-exchange with the lane at distance d: this lane keeps the better candidate iff keep_better
+__device__ __forceinline__ void cmpx_lane(float& k, int& i, int d, bool keep_better) {
+  const float ok = __shfl_xor_sync(0xffffffffu, k, d);
+  const int oi = __shfl_xor_sync(0xffffffffu, i, d);
+  if (better(k, i, ok, oi) != keep_better) {
+    k = ok;
+    i = oi;
+  }
+}
+
+// E: shortlist length KP = 32 E.  KS = ceil(p / 8): the k-slices of 8 columns that hold q_lo / r_lo data; the hi
+// segments (p + 2 columns) have ks_hi = KS or KS + 1.  KS is a template parameter so that the MMA schedule of a tile
+// is straight-line code (see the MMA issuer below).
+template <int E, int KS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-    knn_scores_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                  int KB /* k-blocks per segment: A' and B' hold 2 KB each */, int nstages, int lists_in_smem, i64 ntiles, i64 qtile0, i64 q_begin, i64 q_end,
+    knn_scores_tc(const float* __restrict__ Aop, const __grid_constant__ CUtensorMap mapB,
+                  int KB /* k-blocks per segment: A' and B' hold 2 KB each */, int ks_hi, int nstages, int lists_in_smem, int dbg, i64 ntiles, i64 qtile0, i64 q_begin, i64 q_end,
                   float* __restrict__ out_key, int* __restrict__ out_idx, float* __restrict__ gl_key,
                   int* __restrict__ gl_idx) {
   constexpr int KP = 32 * E;
+  constexpr int ks_lo = KS;
+  constexpr int NB_LO = (KS + 3) / 4;            // 32-column blocks of a lo segment that hold data
+  const int nb_hi = (ks_hi + 3) / 4;             // ... of a hi segment (NB_LO or NB_LO + 1)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024-byte aligned operand blocks first, then shortlists / pools / barriers
   unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned char* sA = base;                                   // 2 KB blocks: q_hi, then q_lo
-  unsigned char* sB = base + (size_t)2 * KB * TC_BLOCK_BYTES; // nstages blocks
-  unsigned char* after = sB + (size_t)nstages * TC_BLOCK_BYTES;
-  float* pool_key = reinterpret_cast<float*>(after);          // [128][TC_POOL]
-  int* pool_idx = reinterpret_cast<int*>(pool_key + TC_M * TC_POOL);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(pool_idx + TC_M * TC_POOL);
+  unsigned char* sB = base;                                   // nstages blocks of B'
+  unsigned char* pool = sB + (size_t)nstages * TC_BLOCK_BYTES;          // [TC_POOL][128] {score, ref}, padded stride
+  uint64_t* bars = reinterpret_cast<uint64_t*>(pool + TC_POOL_BYTES);
   uint64_t* full = bars;                 // [nstages]
   uint64_t* empty = bars + 8;            // [nstages]
-  uint64_t* a_full = bars + 16;
-  uint64_t* tmem_full = bars + 17;       // [2]
-  uint64_t* tmem_empty = bars + 19;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
-  float* sm_lkey = reinterpret_cast<float*>(bars + 24);       // [128][KP] when lists_in_smem
+  uint64_t* tmem_full = bars + 17;       // [TC_ACC]
+  uint64_t* tmem_empty = bars + 21;      // [TC_ACC]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+  float* sm_lkey = reinterpret_cast<float*>(bars + 28);       // [128][KP] when lists_in_smem
   int* sm_lidx = reinterpret_cast<int*>(sm_lkey + TC_M * KP);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const i64 qtile = qtile0 + blockIdx.x;
@@ -185,35 +253,61 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_init(full + s, 1);
       mbar_init(empty + s, 1);
     }
-    mbar_init(a_full, 1);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < TC_ACC; ++b) {
       mbar_init(tmem_full + b, 1);
       mbar_init(tmem_empty + b, 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM: 2 accumulators x 128 columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)));
+  if (warp == 1) {  // TMEM: all 512 columns (one CTA per SM): nacc accumulators of 128, then A'
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // A' = [q_hi | q_lo] lives in TENSOR MEMORY (lane = query row, one tf32 per column), not in shared memory: with
+  // both operands in shared memory an M = N = 128, K = 8 MMA reads 8 KB for 64 cycles of math and the operand fetch
+  // (~57 B/clk measured) paces the tensor pipe at 143 cycles per MMA.  Only the k-slices that hold data are stored:
+  // ks_hi slices of q_hi (p + 2 columns), then ks_lo slices of q_lo.
+  const int a_cols = (ks_hi + ks_lo) * 8;
+  const int nacc = (512 - a_cols) / TC_N >= 3 ? 3 : 2;
+  const uint32_t tmem_a = tmem_base + (uint32_t)nacc * TC_N;
+  if (warp >= 2) {
+    const int slab = warp & 3;
+    const float* arow = Aop + (size_t)(qtile * TC_M + slab * 32 + lane) * (size_t)(2 * KB * TC_KB);
+    for (int sl = 0; sl < ks_hi + ks_lo; ++sl) {
+      const float* src = sl < ks_hi ? arow + sl * 8 : arow + KB * TC_KB + (sl - ks_hi) * 8;
+      const float4 x0 = *reinterpret_cast<const float4*>(src), x1 = *reinterpret_cast<const float4*>(src + 4);
+      const uint32_t taddr = tmem_a + ((uint32_t)(slab * 32) << 16) + (uint32_t)sl * 8;
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                   "r"(__float_as_uint(x0.x)), "r"(__float_as_uint(x0.y)), "r"(__float_as_uint(x0.z)),
+                   "r"(__float_as_uint(x0.w)), "r"(__float_as_uint(x1.x)), "r"(__float_as_uint(x1.y)),
+                   "r"(__float_as_uint(x1.z)), "r"(__float_as_uint(x1.w))
+                   : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp == 0) {
     if (lane == 0) {
       // ---- TMA producer ----
-      mbar_expect_tx(a_full, (uint32_t)(2 * KB) * TC_BLOCK_BYTES);
-      for (int kb = 0; kb < 2 * KB; ++kb)
-        tma_load_2d(sA + (size_t)kb * TC_BLOCK_BYTES, &mapA, a_full, kb * TC_KB, (int)(qtile * TC_M));
       int s = 0;
       uint32_t ph = 0;
       for (i64 t = 0; t < ntiles; ++t)
-        for (int kb = 0; kb < 2 * KB; ++kb) {  // r_hi blocks, then r_lo blocks
-          mbar_wait(empty + s, ph ^ 1);
-          mbar_expect_tx(full + s, TC_BLOCK_BYTES);
-          tma_load_2d(sB + (size_t)s * TC_BLOCK_BYTES, &mapB, full + s, kb * TC_KB, (int)(t * TC_N));
+        for (int kb = 0; kb < nb_hi + NB_LO; ++kb) {  // the r_hi blocks that hold data, then the r_lo blocks
+          const int col = kb < nb_hi ? kb * TC_KB : (KB + kb - nb_hi) * TC_KB;
+          mbar_wait_backoff(empty + s, ph ^ 1);
+          if (dbg & 4) {
+            mbar_arrive(full + s);
+          } else {
+            mbar_expect_tx(full + s, TC_BLOCK_BYTES);
+            tma_load_2d(sB + (size_t)s * TC_BLOCK_BYTES, &mapB, full + s, col, (int)(t * TC_N));
+          }
           if (++s == nstages) {
             s = 0;
             ph ^= 1;
@@ -221,39 +315,74 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---- MMA issuer ----
-      mbar_wait(a_full, 0);
+    // ---- MMA issuer ----
+    // The issue rate of this one warp is what the tensor pipe sees.  Two things made it the bottleneck of the kernel
+    // (measured with the producer and the epilogue switched off: 178, then 122 cycles per MMA where the pipe needs
+    // 64): (1) inside `if (lane == 0)` the compiler cannot prove that the operands of tcgen05.mma are warp-uniform
+    // and wrapped every MMA in an elect / broadcast / branch waterfall -- so the whole warp walks the loop and ONE
+    // elected lane issues; (2) with run-time slice counts a k-block cost ~150 dependent scalar instructions (predicates,
+    // 64-bit descriptor arithmetic, vector -> uniform moves) -- so the schedule of a tile is unrolled at compile time
+    // (KS): a barrier wait, then up to 8 MMAs whose operands differ by immediates.
+    const uint64_t descB = umma_desc_sw128(smem_u32(sB));   // + byte offset >> 4 selects block / k-slice
+    const bool extra = ks_hi > KS;                          // the hi segments hold one slice more than the lo ones
+    const uint32_t tal0 = tmem_a + (uint32_t)ks_hi * 8;     // q_lo slices follow the q_hi slices
+    int s = 0, acc = 0;
+    uint32_t ph = 0, accph = 0;
+    for (i64 t = 0; t < ntiles; ++t) {
+      mbar_wait_backoff(tmem_empty + acc, accph ^ 1);
       tc_fence_after();
-      int s = 0;
-      uint32_t ph = 0;
-      for (i64 t = 0; t < ntiles; ++t) {
-        const int acc = (int)(t & 1);
-        const uint32_t accph = (uint32_t)((t >> 1) & 1);
-        mbar_wait(tmem_empty + acc, accph ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)acc * TC_N;
-        for (int kb = 0; kb < 2 * KB; ++kb) {
-          mbar_wait(full + s, ph);
-          tc_fence_after();
-          const bool hi = kb < KB;                   // staged block: r_hi[kb] or r_lo[kb - KB]
-          const int ka = hi ? kb : kb - KB;
-          const uint32_t ah_addr = smem_u32(sA + (size_t)ka * TC_BLOCK_BYTES);         // q_hi
-          const uint32_t al_addr = smem_u32(sA + (size_t)(KB + ka) * TC_BLOCK_BYTES);  // q_lo
-          const uint32_t b_addr = smem_u32(sB + (size_t)s * TC_BLOCK_BYTES);
+      const uint32_t tmem_d = tmem_base + (uint32_t)acc * TC_N;
 #pragma unroll
-          for (int k = 0; k < TC_KB / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes along the swizzled row
-            const uint64_t db = umma_desc_sw128(b_addr + k * 32);
-            umma_tf32(tmem_d, umma_desc_sw128(ah_addr + k * 32), db, TC_IDESC, (kb | k) ? 1u : 0u);  // q_hi.r_hi / q_hi.r_lo
-            if (hi) umma_tf32(tmem_d, umma_desc_sw128(al_addr + k * 32), db, TC_IDESC, 1u);         // q_lo.r_hi
+      for (int b = 0; b < NB_LO + 1; ++b) {        // r_hi blocks: q_hi . r_hi and q_lo . r_hi
+        if (b < NB_LO || (b * 4 == KS && extra)) { // (the last one exists only when slice KS starts a new block)
+          mbar_wait_backoff(full + s, ph);
+          tc_fence_after();
+          const uint64_t db = descB + (uint64_t)((s * TC_BLOCK_BYTES) >> 4);
+          if (elect_one()) {
+            if (!(dbg & 2)) {
+#pragma unroll
+              for (int k = 0; k < TC_KB / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes along the swizzled row
+                const int sl = b * 4 + k;
+                if (sl < KS) {
+                  umma_tf32_ts(tmem_d, tmem_a + 8 * sl, db + 2 * k, TC_IDESC, sl ? 1u : 0u);
+                  umma_tf32_ts(tmem_d, tal0 + 8 * sl, db + 2 * k, TC_IDESC, 1u);
+                } else if (sl == KS) {
+                  if (extra) umma_tf32_ts(tmem_d, tmem_a + 8 * sl, db + 2 * k, TC_IDESC, 1u);
+                }
+              }
+            }
+            umma_commit(empty + s);                // frees the B block when these MMAs have read it
           }
-          umma_commit(empty + s);  // frees the B block when these MMAs have read it
+          __syncwarp();
           if (++s == nstages) {
             s = 0;
             ph ^= 1;
           }
         }
-        umma_commit(tmem_full + acc);  // accumulator complete
+      }
+#pragma unroll
+      for (int b = 0; b < NB_LO; ++b) {            // r_lo blocks: q_hi . r_lo
+        mbar_wait_backoff(full + s, ph);
+        tc_fence_after();
+        const uint64_t db = descB + (uint64_t)((s * TC_BLOCK_BYTES) >> 4);
+        if (elect_one()) {
+          if (!(dbg & 2)) {
+#pragma unroll
+            for (int k = 0; k < TC_KB / 8; ++k)
+              if (b * 4 + k < KS) umma_tf32_ts(tmem_d, tmem_a + 8 * (b * 4 + k), db + 2 * k, TC_IDESC, 1u);
+          }
+          umma_commit(empty + s);
+          if (b == NB_LO - 1) umma_commit(tmem_full + acc);   // accumulator complete
+        }
+        __syncwarp();
+        if (++s == nstages) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+      if (++acc == nacc) {
+        acc = 0;
+        accph ^= 1;
       }
     }
   } else {
@@ -262,99 +391,184 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int row = slab * 32 + lane;
     const i64 q = qtile * TC_M + row;
     const bool mine = (q >= q_begin && q < q_end);
-    // shortlists of this CTA's 128 rows: shared memory when they fit, else a global scratch
+    // shortlists of this CTA's 128 rows, best first, entry i of a row at [row][i] with i = 32 e + lane: shared memory
+    // when they fit, else a global scratch
     float* lkey = lists_in_smem ? sm_lkey : gl_key + (size_t)blockIdx.x * TC_M * KP;
     int* lidx = lists_in_smem ? sm_lidx : gl_idx + (size_t)blockIdx.x * TC_M * KP;
-    for (int r = 0; r < 32; ++r)                     // keys are -score: ascending = best first
+    for (int r = 0; r < 32; ++r)
 #pragma unroll
       for (int e = 0; e < E; ++e) {
-        lkey[(size_t)(slab * 32 + r) * KP + lane * E + e] = INFINITY;
-        lidx[(size_t)(slab * 32 + r) * KP + lane * E + e] = INT_MAX;
+        lkey[(size_t)(slab * 32 + r) * KP + e * 32 + lane] = -INFINITY;
+        lidx[(size_t)(slab * 32 + r) * KP + e * 32 + lane] = INT_MAX;
       }
     __syncwarp();
     float thr = mine ? -INFINITY : INFINITY;         // rows outside this rank's range never pass
-    float* my_pk = pool_key + row * TC_POOL;
-    int* my_pi = pool_idx + row * TC_POOL;
-    for (i64 t = 0; t < ntiles; ++t) {
-      const int acc = (int)(t & 1);
-      const uint32_t accph = (uint32_t)((t >> 1) & 1);
-      mbar_wait(tmem_full + acc, accph);
-      tc_fence_after();
-      // the TMEM loads are pipelined one chunk deep: chunk c + 1 is in flight while chunk c is compared
-      uint32_t v[16], w[16];
-      auto tmem_ld16 = [&](uint32_t (&d)[16], int c) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(slab * 32) << 16) + (uint32_t)(acc * TC_N + c * TC_POOL);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]),
-              "=r"(d[8]), "=r"(d[9]), "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15])
-            : "r"(taddr));
-      };
-      tmem_ld16(w, 0);
-#pragma unroll 1
-      for (int c = 0; c < TC_N / TC_POOL; ++c) {
-        // the loaded registers are operands of the wait: nothing that reads them may be scheduled above it
-        asm volatile("tcgen05.wait::ld.sync.aligned;"
-                     : "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]),
-                       "+r"(w[8]), "+r"(w[9]), "+r"(w[10]), "+r"(w[11]), "+r"(w[12]), "+r"(w[13]), "+r"(w[14]), "+r"(w[15])
-                     :
-                     : "memory");
+    const uint32_t pool_row = smem_u32(pool) + (uint32_t)row * 8;   // slot 0 of this thread's row
+    const uint32_t pool_slab = smem_u32(pool) + (uint32_t)(slab * 32) * 8;
+    uint32_t pw = pool_row;                           // where the next survivor goes
+    // merges the pool of row r (warp-uniform) into its shortlist; n_new entries
+    auto flush_row = [&](int r) {
+      const int n_new = (int)((__shfl_sync(0xffffffffu, pw, r) - (pool_slab + (uint32_t)r * 8)) / TC_POOL_STRIDE);
+      float pk = -INFINITY;
+      int pi = INT_MAX;
+      if (lane < n_new) {
+        const uint32_t a = pool_slab + (uint32_t)r * 8 + (uint32_t)lane * TC_POOL_STRIDE;
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=f"(pk), "=r"(pi) : "r"(a));
+      }
+      // bitonic sort of the pool across the lanes, best first
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = w[j];
-        if (c + 1 < TC_N / TC_POOL) tmem_ld16(w, c + 1);
-        int cnt = 0;
-        const int ref0 = (int)(t * TC_N + c * TC_POOL);
+      for (int k2 = 2; k2 <= 32; k2 <<= 1)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float sc = __uint_as_float(v[j]);
-          if (sc > thr) {
-            my_pk[cnt] = -sc;
-            my_pi[cnt] = ref0 + j;
-            ++cnt;
-          }
+        for (int j = k2 >> 1; j > 0; j >>= 1) cmpx_lane(pk, pi, j, ((lane & j) == 0) == ((lane & k2) == 0));
+      // reversed pool against the LAST 32 entries of the list: the better of each pair; with the entries before
+      // them this is a bitonic sequence holding the best KP of list + pool
+      const float rk = __shfl_sync(0xffffffffu, pk, 31 - lane);
+      const int ri = __shfl_sync(0xffffffffu, pi, 31 - lane);
+      const size_t lo = (size_t)(slab * 32 + r) * KP + lane;
+      float key[E];
+      int idx[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        key[e] = lkey[lo + e * 32];
+        idx[e] = lidx[lo + e * 32];
+      }
+      if (better(rk, ri, key[E - 1], idx[E - 1])) {
+        key[E - 1] = rk;
+        idx[E - 1] = ri;
+      }
+      if (E == 2) {                                   // half-cleaner at distance 32 lives in registers
+        if (better(key[E - 1], idx[E - 1], key[0], idx[0])) {
+          const float tk = key[0];
+          const int ti = idx[0];
+          key[0] = key[E - 1];
+          idx[0] = idx[E - 1];
+          key[E - 1] = tk;
+          idx[E - 1] = ti;
         }
-        unsigned pending = __ballot_sync(0xffffffffu, cnt > 0);
-        if (pending) __syncwarp();                   // pool writes visible to the whole warp
-        while (pending) {                            // warp-uniform: merge one row's pool at a time
+      }
+#pragma unroll
+      for (int j = 16; j > 0; j >>= 1)
+#pragma unroll
+        for (int e = 0; e < E; ++e) cmpx_lane(key[e], idx[e], j, (lane & j) == 0);
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        lkey[lo + e * 32] = key[e];
+        lidx[lo + e * 32] = idx[e];
+      }
+      const float worst = __shfl_sync(0xffffffffu, key[E - 1], 31);
+      if (lane == r) {
+        thr = worst;
+        pw = pool_row;
+      }
+    };
+    // appends the survivors of 16 scores (registers x[o .. o + 15], references ref0 ..) to the thread's pool
+    auto append16 = [&](const uint32_t (&x)[32], int o, int ref0) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (__uint_as_float(x[o + j]) > thr) {
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(pw), "r"(x[o + j]), "r"(ref0 + j) : "memory");
+          pw += TC_POOL_STRIDE;
+        }
+    };
+    // a pool that the next 16 scores could overflow is merged now (warp-uniform loop over the rows that need it)
+    auto flush_check = [&]() {
+      unsigned pending = __ballot_sync(0xffffffffu, pw > pool_row + (TC_POOL - TC_CHUNK) * TC_POOL_STRIDE);
+      if (pending) {
+        __syncwarp();                                 // pool writes visible to the whole warp
+        while (pending) {
           const int r = __ffs(pending) - 1;
           pending &= pending - 1;
-          const int n_new = __shfl_sync(0xffffffffu, cnt, r);
-          const size_t lo = (size_t)(slab * 32 + r) * KP + lane * E;
-          float key[E];
-          int idx[E];
-#pragma unroll
-          for (int e = 0; e < E; ++e) {
-            key[e] = lkey[lo + e];
-            idx[e] = lidx[lo + e];
-          }
-          const float* pk = pool_key + (slab * 32 + r) * TC_POOL;
-          const int* pi = pool_idx + (slab * 32 + r) * TC_POOL;
-          for (int s2 = 0; s2 < n_new; ++s2) list_insert<float, E>(key, idx, pk[s2], pi[s2], lane);
-#pragma unroll
-          for (int e = 0; e < E; ++e) {
-            lkey[lo + e] = key[e];
-            lidx[lo + e] = idx[e];
-          }
-          const float worst = __shfl_sync(0xffffffffu, key[E - 1], 31);
-          if (lane == r) thr = -worst;
+          flush_row(r);
         }
         __syncwarp();
+      }
+    };
+    auto max16 = [](const uint32_t (&x)[32], int o) {
+      const float a = fmaxf(fmaxf(__uint_as_float(x[o + 0]), __uint_as_float(x[o + 1])), __uint_as_float(x[o + 2]));
+      const float b = fmaxf(fmaxf(__uint_as_float(x[o + 3]), __uint_as_float(x[o + 4])), __uint_as_float(x[o + 5]));
+      const float c = fmaxf(fmaxf(__uint_as_float(x[o + 6]), __uint_as_float(x[o + 7])), __uint_as_float(x[o + 8]));
+      const float d = fmaxf(fmaxf(__uint_as_float(x[o + 9]), __uint_as_float(x[o + 10])), __uint_as_float(x[o + 11]));
+      const float e = fmaxf(fmaxf(__uint_as_float(x[o + 12]), __uint_as_float(x[o + 13])), __uint_as_float(x[o + 14]));
+      return fmaxf(fmaxf(fmaxf(a, b), c), fmaxf(fmaxf(d, e), __uint_as_float(x[o + 15])));
+    };
+    // 32 scores of the row: a max tree and ONE vote when no row of the warp has a survivor (the common case at
+    // large n); otherwise the halves are appended by the lanes that have one
+    auto process32 = [&](const uint32_t (&x)[32], int ref0) {
+      const float m0 = max16(x, 0), m1 = max16(x, 16);
+      if (__any_sync(0xffffffffu, fmaxf(m0, m1) > thr)) {
+        if (m0 > thr) append16(x, 0, ref0);
+        flush_check();
+        if (m1 > thr) append16(x, 16, ref0 + 16);
+        flush_check();
+      }
+    };
+    auto tmem_ld32 = [&](uint32_t (&d)[32], uint32_t taddr) {
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]),
+            "=r"(d[8]), "=r"(d[9]), "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15]),
+            "=r"(d[16]), "=r"(d[17]), "=r"(d[18]), "=r"(d[19]), "=r"(d[20]), "=r"(d[21]), "=r"(d[22]), "=r"(d[23]),
+            "=r"(d[24]), "=r"(d[25]), "=r"(d[26]), "=r"(d[27]), "=r"(d[28]), "=r"(d[29]), "=r"(d[30]), "=r"(d[31])
+          : "r"(taddr));
+    };
+    // the loaded registers are operands of the wait: nothing that reads them may be scheduled above it
+    auto tmem_wait = [&](uint32_t (&d)[32]) {
+      asm volatile("tcgen05.wait::ld.sync.aligned;"
+                   : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]), "+r"(d[4]), "+r"(d[5]), "+r"(d[6]), "+r"(d[7]),
+                     "+r"(d[8]), "+r"(d[9]), "+r"(d[10]), "+r"(d[11]), "+r"(d[12]), "+r"(d[13]), "+r"(d[14]), "+r"(d[15]),
+                     "+r"(d[16]), "+r"(d[17]), "+r"(d[18]), "+r"(d[19]), "+r"(d[20]), "+r"(d[21]), "+r"(d[22]), "+r"(d[23]),
+                     "+r"(d[24]), "+r"(d[25]), "+r"(d[26]), "+r"(d[27]), "+r"(d[28]), "+r"(d[29]), "+r"(d[30]), "+r"(d[31])
+                   :
+                   : "memory");
+    };
+    int acc = 0;
+    uint32_t accph = 0;
+    for (i64 t = 0; t < ntiles; ++t) {
+      mbar_wait(tmem_full + acc, accph);
+      tc_fence_after();
+      // two register sets, loads one step ahead: set B is in flight while set A is compared and vice versa
+      uint32_t va[32], vb[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(slab * 32) << 16) + (uint32_t)(acc * TC_N);
+      const int ref0 = (int)(t * TC_N);
+      if (!(dbg & 1)) tmem_ld32(va, taddr);
+#pragma unroll 1
+      for (int c = 0; c < ((dbg & 1) ? 0 : TC_N / 64); ++c) {
+        tmem_wait(va);
+        tmem_ld32(vb, taddr + c * 64 + 32);
+        process32(va, ref0 + c * 64);
+        tmem_wait(vb);
+        if (c + 1 < TC_N / 64) tmem_ld32(va, taddr + c * 64 + 64);
+        process32(vb, ref0 + c * 64 + 32);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty + acc);
+      if (++acc == nacc) {
+        acc = 0;
+        accph ^= 1;
+      }
     }
-    // hand the shortlists to knn_rerank in its convention: key = ||r||^2 - 2 q.r = -2 s, ascending
+    {  // what is still in the pools
+      unsigned pending = __ballot_sync(0xffffffffu, pw != pool_row);
+      __syncwarp();
+      while (pending) {
+        const int r = __ffs(pending) - 1;
+        pending &= pending - 1;
+        flush_row(r);
+      }
+    }
+    // hand the shortlists to knn_rerank in its convention: key = ||r||^2 - 2 q.r = -2 s, ascending, worst last
     __syncwarp();
     for (int r = 0; r < 32; ++r) {
       const i64 qq = qtile * TC_M + slab * 32 + r;
       if (qq >= q_begin && qq < q_end) {
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-          const size_t src = (size_t)(slab * 32 + r) * KP + lane * E + e;
-          out_key[(size_t)(qq - q_begin) * KP + lane * E + e] = 2.0f * lkey[src];
-          out_idx[(size_t)(qq - q_begin) * KP + lane * E + e] = lidx[src];
+          const size_t src = (size_t)(slab * 32 + r) * KP + e * 32 + lane;
+          out_key[(size_t)(qq - q_begin) * KP + e * 32 + lane] = -2.0f * lkey[src];
+          out_idx[(size_t)(qq - q_begin) * KP + e * 32 + lane] = lidx[src];
         }
       }
     }
@@ -362,7 +576,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
   }
 }
 
@@ -396,11 +610,39 @@ static CUtensorMap make_map(float* ptr, i64 rows, int Kt) {
   return m;
 }
 
-// Can the tensor-core shortlist take this problem?  A' must stay resident next to >= 2 B' stages.
+struct TcLaunch {
+  const float* Aop;
+  CUtensorMap mapB;
+  int KB, ks_hi, nstages, lists_in_smem, dbg;
+  i64 ntiles, qt0, q_begin, q_end;
+  float* skey;
+  int* sidx;
+  float* glk;
+  int* gli;
+  unsigned grid;
+  size_t smem;
+  cudaStream_t st;
+};
+// one instantiation per KS = ceil(p / 8) = 1 .. 16 (p <= 126)
+template <int E, int KS>
+static bool tc_dispatch(adobo_ctx* c, const TcLaunch& L, int ks) {
+  if constexpr (KS >= 1) {
+    if (ks == KS) {
+      CUDA_CHECK(cudaFuncSetAttribute(knn_scores_tc<E, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+      LAUNCH(c, "knn_scores_tc", (knn_scores_tc<E, KS><<<L.grid, TC_THREADS, L.smem, L.st>>>(
+                                     L.Aop, L.mapB, L.KB, L.ks_hi, L.nstages, L.lists_in_smem, L.dbg, L.ntiles, L.qt0, L.q_begin,
+                                     L.q_end, L.skey, L.sidx, L.glk, L.gli)));
+      return true;
+    }
+    return tc_dispatch<E, KS - 1>(c, L, ks);
+  } else {
+    return false;
+  }
+}
+
+// Can the tensor-core shortlist take this problem?
 bool knn_tc_supported(int p) {
-  const int Kp = (p + 2 + TC_KB - 1) / TC_KB * TC_KB;
-  const int KB = Kp / TC_KB;
-  return (size_t)(2 * KB + 2) * TC_BLOCK_BYTES + 1024 + (size_t)TC_M * TC_POOL * 8 + 256 <= 227 * 1024;
+  return 8 * ((p + 2 + 7) / 8 + (p + 7) / 8) + 2 * TC_N <= 512;   // A' and two accumulators in tensor memory
 }
 
 // x: all points (n x p fp64, device).  Fills skey/sidx ((q_end-q_begin) x KP) for queries [q_begin, q_end),
@@ -417,17 +659,19 @@ void run_knn_shortlist_tc(adobo_ctx* c, const double* x, i64 n, int p, const dou
   norms.ensure((size_t)npad);
   LAUNCH(c, "knn_tc_prep", (knn_tc_prep<<<(unsigned)((npad + 127) / 128), 128, 0, st>>>(x, n, npad, p, Kp, ctr, Aop.p, Bop.p,
                                                                                       norms.p, maxnorm)));
-  const CUtensorMap mapA = make_map(Aop.p, npad, Kt), mapB = make_map(Bop.p, npad, Kt);
+  const CUtensorMap mapB = make_map(Bop.p, npad, Kt);
   const int KP = 32 * E;
   const i64 qt0 = q_begin / TC_M, qt1 = (q_end + TC_M - 1) / TC_M;
   const i64 ntiles = npad / TC_N;
   // shared memory: A' resident + B' ring + pools + barriers (+ shortlists when they still leave >= 2 stages)
-  const size_t cap = 227 * 1024, fixed = 1024 /*align*/ + (size_t)TC_M * TC_POOL * 8 + 256;
+  const size_t cap = 227 * 1024, fixed = 1024 /*align*/ + (size_t)TC_POOL_BYTES + 256;
   const size_t lists = (size_t)TC_M * KP * 8;
-  const size_t a_bytes = (size_t)2 * KB * TC_BLOCK_BYTES;
+  const size_t a_bytes = 0;   // A' is kept in tensor memory
   const int lists_in_smem = (a_bytes + 2 * (size_t)TC_BLOCK_BYTES + fixed + lists <= cap) ? 1 : 0;
   int nstages = (int)((cap - a_bytes - fixed - (lists_in_smem ? lists : 0)) / TC_BLOCK_BYTES);
   if (nstages > 8) nstages = 8;  // the barrier block holds 8 full / empty pairs
+  const int dbg = getenv("ADOBO_B200_KNN_DBG") ? atoi(getenv("ADOBO_B200_KNN_DBG")) : 0;
+  if (getenv("ADOBO_B200_KNN_STAGES")) nstages = std::min(nstages, atoi(getenv("ADOBO_B200_KNN_STAGES")));
   REQUIRE(nstages >= 2, ADOBO_ERR_LIMIT, "knn: embedding too wide for the tensor-core shortlist");
   const size_t smem = a_bytes + (size_t)nstages * TC_BLOCK_BYTES + fixed + (lists_in_smem ? lists : 0);
   DevBuf<float> glk;
@@ -436,18 +680,12 @@ void run_knn_shortlist_tc(adobo_ctx* c, const double* x, i64 n, int p, const dou
     glk.ensure((size_t)(qt1 - qt0) * TC_M * KP);
     gli.ensure((size_t)(qt1 - qt0) * TC_M * KP);
   }
-  WORK(c, 2.0 * (double)(qt1 - qt0) * TC_M * (double)npad * 3.0 * Kp);  // tf32 flops actually issued (three products)
-  if (E == 1) {
-    CUDA_CHECK(cudaFuncSetAttribute(knn_scores_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LAUNCH(c, "knn_scores_tc", (knn_scores_tc<1><<<(unsigned)(qt1 - qt0), TC_THREADS, smem, st>>>(
-                                   mapA, mapB, KB, nstages, lists_in_smem, ntiles, qt0, q_begin, q_end, skey, sidx, glk.p,
-                                   gli.p)));
-  } else {
-    CUDA_CHECK(cudaFuncSetAttribute(knn_scores_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LAUNCH(c, "knn_scores_tc", (knn_scores_tc<2><<<(unsigned)(qt1 - qt0), TC_THREADS, smem, st>>>(
-                                   mapA, mapB, KB, nstages, lists_in_smem, ntiles, qt0, q_begin, q_end, skey, sidx, glk.p,
-                                   gli.p)));
-  }
+  WORK(c, 2.0 * (double)(qt1 - qt0) * TC_M * (double)npad * 8.0 * ((p + 2 + 7) / 8 + 2 * ((p + 7) / 8)));  // tf32 flops actually issued (three products, k-slices of 8)
+  TcLaunch L{Aop.p, mapB, KB, (p + 2 + 7) / 8, nstages, lists_in_smem, dbg, ntiles, qt0, q_begin, q_end, skey, sidx, glk.p, gli.p,
+             (unsigned)(qt1 - qt0), smem, st};
+  const int KS = (p + 7) / 8;
+  bool done = (E == 1) ? tc_dispatch<1, 16>(c, L, KS) : tc_dispatch<2, 16>(c, L, KS);
+  REQUIRE(done, ADOBO_ERR_LIMIT, "knn: embedding too wide for the tensor-core shortlist");
   CUDA_CHECK(cudaStreamSynchronize(st));  // Aop / Bop die here
 }
 
