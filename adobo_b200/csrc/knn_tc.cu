@@ -670,8 +670,9 @@ void run_knn_shortlist_tc(adobo_ctx* c, const double* x, i64 n, int p, const dou
   const int lists_in_smem = (a_bytes + 2 * (size_t)TC_BLOCK_BYTES + fixed + lists <= cap) ? 1 : 0;
   int nstages = (int)((cap - a_bytes - fixed - (lists_in_smem ? lists : 0)) / TC_BLOCK_BYTES);
   if (nstages > 8) nstages = 8;  // the barrier block holds 8 full / empty pairs
+  // diagnostic: switch pipeline roles off (1 = epilogue, 2 = MMAs, 4 = TMA loads) to time the others alone -- how the
+  // issue-bound MMA loop was found (profiles/r02_knn_stages.md); results are meaningless with any bit set
   const int dbg = getenv("ADOBO_B200_KNN_DBG") ? atoi(getenv("ADOBO_B200_KNN_DBG")) : 0;
-  if (getenv("ADOBO_B200_KNN_STAGES")) nstages = std::min(nstages, atoi(getenv("ADOBO_B200_KNN_STAGES")));
   REQUIRE(nstages >= 2, ADOBO_ERR_LIMIT, "knn: embedding too wide for the tensor-core shortlist");
   const size_t smem = a_bytes + (size_t)nstages * TC_BLOCK_BYTES + fixed + (lists_in_smem ? lists : 0);
   DevBuf<float> glk;
