@@ -287,17 +287,24 @@ class Engine:
         check(self.lib.adobo_result_sizes(self.h, out))
         return dict(zip(('n', 'ncomp', 'h', 'k', 'knn_n', 'n_edges', 'nnz', 'g'), (int(v) for v in out)))
 
-    def fetch_pca(self, h=None, ncomp=None):
+    def fetch_pca(self, h=None, ncomp=None, out=None):
+        """PCA results to the host.  out: dict(comp, contr, s, genes) of caller-owned arrays (e.g. page-locked with
+        pin(), reused from pass to pass) -- the C-ABI's caller-allocated outputs; default: fresh arrays."""
         sz = self.result_sizes()
         if (h is not None and h != sz['h']) or (ncomp is not None and ncomp != sz['ncomp']):
             raise Exception('fetch_pca: the device holds %d genes x %d components, not %s x %s' % (sz['h'], sz['ncomp'], h, ncomp))
         h, ncomp = sz['h'], sz['ncomp']
-        comp = np.empty((sz['n'], ncomp))
-        contr = np.empty((h, ncomp))
-        s = np.empty(ncomp)
-        genes = np.empty(h, dtype=np.int32)
+        if out is not None:
+            comp, contr, s, genes = out['comp'], out['contr'], out['s'], out['genes']
+            if comp.shape != (sz['n'], ncomp) or contr.shape != (h, ncomp) or s.shape != (ncomp,) or genes.shape != (h,):
+                raise Exception('fetch_pca: out arrays do not have the shapes of the results on the device')
+        else:
+            comp = np.empty((sz['n'], ncomp))
+            contr = np.empty((h, ncomp))
+            s = np.empty(ncomp)
+            genes = np.empty(h, dtype=np.int32)
         check(self.lib.adobo_fetch_pca(self.h, comp, s, contr, genes))
-        return dict(comp=comp, contr=contr, s=s, genes=genes.astype(np.int64))
+        return dict(comp=comp, contr=contr, s=s, genes=genes if out is not None else genes.astype(np.int64))
 
     def fetch_knn(self, k=None):
         sz = self.result_sizes()
@@ -307,12 +314,19 @@ class Engine:
         check(self.lib.adobo_fetch_knn(self.h, out))
         return out
 
-    def fetch_edges(self, ne=None, counts=False):
-        """Edge list of the last SNN (E x 2 int32); with counts=True also V_ij per edge."""
+    def fetch_edges(self, ne=None, counts=False, out=None):
+        """Edge list of the last SNN (E x 2 int32); with counts=True also V_ij per edge.  out: (src, dst) caller-owned
+        int32 arrays of at least E entries (returned as they are, no stacking)."""
         have = self.result_sizes()['n_edges']
         if ne is not None and ne != have:
             raise Exception('fetch_edges: the device holds %d edges, not %d' % (have, ne))
         ne = have
+        if out is not None:
+            src, dst = out
+            if src.size < ne or dst.size < ne:
+                raise Exception('fetch_edges: out arrays hold fewer than %d entries' % ne)
+            check(self.lib.adobo_snn_fetch(self.h, src, dst))
+            return src[:ne], dst[:ne]
         if counts:
             v = np.empty(max(ne, 1), dtype=np.int32)
             check(self.lib.adobo_snn_fetch_counts(self.h, v))
