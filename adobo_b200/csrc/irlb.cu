@@ -2252,7 +2252,14 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   // cluster still holds VS_CLUSTER SMs: a CTA that had to wait for one of those would run its whole prologue after
   // everybody else's -- leave them out of the grid
   auto w3_fn = m_b + 1 <= 96 ? w_step3<VT, 6> : w_step3<VT, 8>;
-  auto wt_fn = wt_nh_used == 6 ? w_step_t<VT, 6> : (wt_nh_used == 7 ? w_step_t<VT, 7> : w_step_t<VT, 8>);
+  // entry slots per lane of w_step_t: enough for a typical row (1.5 x the mean length), the rest of a long row loops
+  const double mean_len = (double)A.nnz / (double)std::max<i64>(n, 1);
+  const int wt_epf = mean_len * 1.5 <= 32 ? 2 : (mean_len * 1.5 <= 64 ? 4 : 6);
+  auto wt_pick = [&](auto nh) {
+    constexpr int NHc = decltype(nh)::value;
+    return wt_epf == 2 ? w_step_t<VT, NHc, 2> : (wt_epf == 4 ? w_step_t<VT, NHc, 4> : w_step_t<VT, NHc, 6>);
+  };
+  auto wt_fn = wt_nh_used == 6 ? wt_pick(std::integral_constant<int, 6>()) : (wt_nh_used == 7 ? wt_pick(std::integral_constant<int, 7>()) : wt_pick(std::integral_constant<int, 8>()));
   const size_t wt_smem = sizeof(double) * (size_t)(1 + WT_WARPS) * hp;
   if (zpath && !fusedt) CUDA_CHECK(cudaFuncSetAttribute(w3_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * h)));
   if (fusedt) CUDA_CHECK(cudaFuncSetAttribute(wt_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wt_smem));

@@ -24,35 +24,42 @@
 constexpr int WT_WARPS = W2_THREADS / 32;
 constexpr int WT_HMAX = 1024;  // (1 + WT_WARPS) copies of h doubles in shared memory
 
-template <typename VT, int NH>
+// EPF: entry slots per lane held in registers (16 EPF entries of a row; longer rows finish in a loop).  Every slot
+// costs its loads, its fma and its scatter whether the row fills it or not, so the host picks EPF from the mean row
+// length of the subset (15 entries at 68 k x 1000 HVGs: EPF = 2; six slots were 355 instructions per pair of rows).
+template <typename VT, int NH, int EPF>
 struct WTRow {
-  int ci[W3_EPF];
-  VT va[W3_EPF];
+  int ci[EPF];
+  VT va[EPF];
   double wv[NH], yp;
   int b, len;
 };
 // (b, e1): the row's pointers -- loaded one pair EARLIER than the entries they delimit, so that the chain
 // row pointers -> entries -> gather never stalls a prefetch on two dependent round trips (ncu: the first use of the
 // prefetched entries and of the row length were the two hottest stall sites of the kernel)
-template <typename VT, int NH>
-__device__ __forceinline__ void wt_load(WTRow<VT, NH>& R, bool ok, int b, int e1, int row,
+// The basis slice of a row is loaded WITHOUT per-lane predicates: every column of W_s holds a finite number (the
+// buffer is zeroed when the decomposition starts and only ever written with finite values), the coefficient of a
+// column that is not in use is zero, and what such a column adds to g_s is never read -- so only whole groups of 16
+// columns beyond nd are skipped (a warp-uniform test).  A row past the end reads row n - 1 (its y is forced to 0).
+template <typename VT, int NH, int EPF>
+__device__ __forceinline__ void wt_load(WTRow<VT, NH, EPF>& R, bool ok, int b, int e1, int rowc,
                                         const int* __restrict__ cl, const VT* __restrict__ vl,
                                         const double* __restrict__ wr, const double* __restrict__ ybuf, bool lazy,
-                                        const bool (&cm)[NH], int hl) {
+                                        int nd, int hl) {
   R.b = b;
   R.len = ok ? e1 - b : 0;
 #pragma unroll
-  for (int q = 0; q < W3_EPF; ++q) {
+  for (int q = 0; q < EPF; ++q) {
     const bool in = hl + 16 * q < R.len;
     R.ci[q] = in ? __ldg(cl + b + 16 * q) : 0;
     R.va[q] = in ? __ldg(vl + b + 16 * q) : VT(0);
   }
 #pragma unroll
-  for (int q = 0; q < NH; ++q) R.wv[q] = (ok && cm[q]) ? __ldcg(wr + 16 * q) : 0.0;
-  R.yp = (ok && lazy) ? __ldcg(ybuf + row) : 0.0;
+  for (int q = 0; q < NH; ++q) R.wv[q] = (16 * q < nd) ? __ldcg(wr + 16 * q) : 0.0;
+  R.yp = lazy ? __ldcg(ybuf + rowc) : 0.0;
 }
 
-template <typename VT, int NH>
+template <typename VT, int NH, int EPF>
 __global__ void __launch_bounds__(W2_THREADS, 1)
     w_step_t(const i64* __restrict__ rptr, const int* __restrict__ cidx, const VT* __restrict__ rval,
              const double* __restrict__ xs, const double* __restrict__ sc, double* __restrict__ W, int ldw, int jprev,
@@ -76,17 +83,14 @@ __global__ void __launch_bounds__(W2_THREADS, 1)
   const bool lazy = jprev >= 0;
   const int jq = lazy ? (jprev >> 4) : -1;
   const bool mine = lazy && hl == (jprev & 15);   // the lane that holds column jprev of the basis slice
-  bool cm[NH];
-#pragma unroll
-  for (int q = 0; q < NH; ++q) cm[q] = (hl + 16 * q < nd) && (hl + 16 * q != jprev);  // column jprev is not stored yet
   const int* cl = cidx + hl;
   const VT* vl = rval + hl;
-  const double* wr = W + (size_t)r * ldw + hl;
-  WTRow<VT, NH> RA, RB;
+  const int rlast = max(n - 1, 0);
+  WTRow<VT, NH, EPF> RA, RB;
   int pb = 0, pe = 0, qb = 0, qe = 0;  // pointers of this half-warp's rows r and r + 2
   if (r < rend) pb = (int)__ldg(rptr + r), pe = (int)__ldg(rptr + r + 1);
   if (r + 2 < rend) qb = (int)__ldg(rptr + r + 2), qe = (int)__ldg(rptr + r + 3);
-  wt_load<VT, NH>(RA, r < rend, pb, pe, r, cl, vl, wr, ybuf, lazy, cm, hl);
+  wt_load<VT, NH, EPF>(RA, r < rend, pb, pe, min(r, rlast), cl, vl, W + (size_t)min(r, rlast) * ldw + hl, ybuf, lazy, nd, hl);
   pdl_sync();
   if (halt && *halt) return;
   TL_SYNC(nd);
@@ -102,13 +106,15 @@ __global__ void __launch_bounds__(W2_THREADS, 1)
   double n2 = 0, ax = 0;
   __syncthreads();
   // one pair of rows: issue the loads of the next pair (into NX), then reduce and scatter the current one (CU)
-  auto step = [&](WTRow<VT, NH>& CU, WTRow<VT, NH>& NX) {
-    wr += 2 * (size_t)ldw;
-    wt_load<VT, NH>(NX, r + 2 < rend, qb, qe, r + 2, cl, vl, wr, ybuf, lazy, cm, hl);
+  auto step = [&](WTRow<VT, NH, EPF>& CU, WTRow<VT, NH, EPF>& NX) {
+    {
+      const int rn = min(r + 2, rlast);
+      wt_load<VT, NH, EPF>(NX, r + 2 < rend, qb, qe, rn, cl, vl, W + (size_t)rn * ldw + hl, ybuf, lazy, nd, hl);
+    }
     qb = qe = 0;
     if (r + 4 < rend) qb = (int)__ldg(rptr + r + 4), qe = (int)__ldg(rptr + r + 5);  // two pairs ahead
     const bool ok = r < rend;
-    const double wp = sinvp * CU.yp;  // W[r, jprev]
+    const double wp = sinvp * CU.yp;  // W[r, jprev]: not stored yet (the loaded value is stale)
     if (mine) {
 #pragma unroll
       for (int q = 0; q < NH; ++q)
@@ -117,9 +123,9 @@ __global__ void __launch_bounds__(W2_THREADS, 1)
     }
     double a = 0;
 #pragma unroll
-    for (int q = 0; q < W3_EPF; ++q)
+    for (int q = 0; q < EPF; ++q)
       if (hl + 16 * q < CU.len) a += (double)CU.va[q] * xsm[CU.ci[q]];
-    for (int e = 16 * W3_EPF + hl; e < CU.len; e += 16) a += (double)__ldg(vl + CU.b + e - hl) * xsm[__ldg(cl + CU.b + e - hl)];
+    for (int e = 16 * EPF + hl; e < CU.len; e += 16) a += (double)__ldg(vl + CU.b + e - hl) * xsm[__ldg(cl + CU.b + e - hl)];
 #pragma unroll
     for (int q = 0; q < NH; ++q) a -= CU.wv[q] * creg[q];
 #pragma unroll
@@ -135,9 +141,9 @@ __global__ void __launch_bounds__(W2_THREADS, 1)
     for (int ph = 0; ph < 2; ++ph) {
       if (hf == ph) {
 #pragma unroll
-        for (int q = 0; q < W3_EPF; ++q)
+        for (int q = 0; q < EPF; ++q)
           if (hl + 16 * q < CU.len) tp[CU.ci[q]] = fma((double)CU.va[q], w, tp[CU.ci[q]]);
-        for (int e = 16 * W3_EPF + hl; e < CU.len; e += 16) {
+        for (int e = 16 * EPF + hl; e < CU.len; e += 16) {
           const int cc = __ldg(cl + CU.b + e - hl);
           tp[cc] = fma((double)__ldg(vl + CU.b + e - hl), w, tp[cc]);
         }
