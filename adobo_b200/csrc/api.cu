@@ -1,3 +1,4 @@
+#include <chrono>
 // C-ABI of adobo_b200 (include/adobo_b200.h): context, NCCL plumbing, stopwatch, and the entry
 // points that mirror the reference's functions.  Everything computes on the GPU; there is no
 // host fallback -- adobo_ctx_create fails when no CUDA device is usable.
@@ -791,16 +792,34 @@ int adobo_embed_path(adobo_ctx* c, double scaling_factor, int32_t ngenes, int32_
                      double prune_snn, int32_t* out_steps, int32_t* out_nmult, int64_t* out_n_edges) {
   API_BEGIN
   CUDA_CHECK(cudaSetDevice(c->device));
+  // ADOBO_B200_DEBUG: wall-clock of the stages (each synchronised at its end) on stderr
+  const bool dbg = getenv("ADOBO_B200_DEBUG") != nullptr;
+  double t[7];
+  auto stamp = [&](int i) {
+    if (!dbg) return;
+    cudaStreamSynchronize(c->stream);
+    t[i] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  };
+  stamp(0);
   run_normalize(c, scaling_factor, ADOBO_LOG_2, 1.0, nullptr, nullptr);
+  stamp(1);
   run_moments(c);
+  stamp(2);
   std::vector<double> z;
   run_seurat_host(c, ngenes, 20, c->hvg_order, z);
   const int h = std::min<int>(ngenes, (int)c->hvg_order.size());
   std::vector<int> genes(c->hvg_order.begin(), c->hvg_order.begin() + h);
+  stamp(3);
   do_pca(c, genes, ncomp, 0.0001, 1000, v0, true, true, out_steps, out_nmult);
+  stamp(4);
   run_knn(c, c->comp.p, c->n, c->p, k);
+  stamp(5);
   i64 ne = 0, pr = 0, tot = 0;
   do_snn(c, c->nn.p, c->knn_n, k, prune_snn, &ne, &pr, &tot);
+  stamp(6);
+  if (dbg)
+    fprintf(stderr, "[adobo_b200] embed_path ms: normalize %.3f  moments %.3f  seurat(host) %.3f  pca %.3f  knn %.3f  snn %.3f\n",
+            t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[6] - t[5]);
   if (out_n_edges) *out_n_edges = ne;
   API_END
 }

@@ -46,7 +46,7 @@ __device__ __forceinline__ unsigned long long tl_gt() {
   return t;
 }
 __device__ unsigned long long tl_cta[8][256];  // per-CTA stamps of the last w_step launch
-__device__ unsigned long long tl_ctak[2][8][256];  // ... of the last spmvT_csc_sm (0) and v_step_one (1) launches
+__device__ unsigned long long tl_ctak[2][10][256];  // ... of the last spmvT_csc_sm (0) and v_step_one (1) launches
 #define TL_CTA(i) do { if (threadIdx.x == 0 && blockIdx.x < 256) tl_cta[i][blockIdx.x] = tl_gt(); } while (0)
 #define TL_CTAK(k, i) do { if (threadIdx.x == 0 && blockIdx.x < 256 && tl_on) tl_ctak[k][i][blockIdx.x] = tl_gt(); } while (0)
 #define TL_ENTRY(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) { tl_buf[0][slot] = tl_gt(); tl_buf[3][slot] = clock64(); } } while (0)
@@ -2030,6 +2030,24 @@ static void dump_timeline() {
   std::sort(evs.begin(), evs.end(), [](const Ev& a, const Ev& b) { return a.t0 < b.t0; });
   const size_t from = evs.size() > 24 ? evs.size() - 24 : 0;
   const unsigned long long base = evs.empty() ? 0 : evs[from].t0;
+  {
+    static unsigned long long ck[2][10][256];
+    cudaMemcpyFromSymbol(ck, tl_ctak, sizeof(ck));
+    static const char* nm[10] = {"sync", "phase A done", "Z landed", "c pushed", "cluster sync 1", "phase B pushed", "cluster sync 2",
+                                 "exit", "slice summed", "exchange done"};
+    static const int order[10] = {0, 8, 9, 1, 2, 3, 4, 5, 6, 7};
+    fprintf(stderr, "last v_step_t, stamps of the cluster's 8 CTAs relative to the earliest sync return (us): min / max\n");
+    unsigned long long b0 = ~0ull;
+    for (int cta = 0; cta < 8; ++cta)
+      if (ck[1][0][cta]) b0 = std::min(b0, ck[1][0][cta]);
+    for (int oi = 0; oi < 10; ++oi) {
+      const int i = order[oi];
+      double lo = 1e30, hi = -1e30;
+      for (int cta = 0; cta < 8; ++cta)
+        if (ck[1][i][cta]) lo = std::min(lo, (ck[1][i][cta] - b0) * 1e-3), hi = std::max(hi, (ck[1][i][cta] - b0) * 1e-3);
+      if (hi > -1e29) fprintf(stderr, "  %-16s %8.2f %8.2f\n", nm[i], lo, hi);
+    }
+  }
   fprintf(stderr, "timeline of the last kernels (us from the first, %%globaltimer)\n");
   for (size_t q = from; q < evs.size(); ++q)
     fprintf(stderr, "%-16s entry %8.2f sync %8.2f exit %8.2f\n", evs[q].name, (evs[q].t0 - base) * 1e-3,

@@ -296,7 +296,9 @@ __global__ void __launch_bounds__(VS_THREADS, 1)
       msg[tid] = s;
     }
     __syncthreads();
+    TL_CTAK(1, 8);
     if (pc.world > 1) peer_allreduce_ll(pc, msg, VT_MSG, 1 + crank);  // ends with a CTA barrier
+    TL_CTAK(1, 9);
   }
   // the W column this step consumes was left unnormalised: s = ||y||, u = y / s  (irlb.py:176-178, 217-219)
   const double n2w = msg[VT_G0], syw = msg[VT_G0 + 1];

@@ -347,14 +347,33 @@ void run_seurat_host(adobo_ctx* c, int ngenes, int num_bins, std::vector<int>& o
       concat.push_back(mem[t]);
     }
   }
-  // sort_values(ascending=False): NaN last; ties keep concat order (the reference's own tie
-  // order is arbitrary -- numpy quicksort)
-  std::vector<int> good, bad;
-  for (int id : concat) (std::isnan(z[id]) ? bad : good).push_back(id);
-  std::stable_sort(good.begin(), good.end(), [&](int a, int b) { return z[a] > z[b]; });
-  order = good;
-  order.insert(order.end(), bad.begin(), bad.end());
-  (void)ngenes;
+  // sort_values(ascending=False): NaN last; ties keep concat order (the reference's own tie order is arbitrary --
+  // numpy quicksort).  Only the first `ngenes` of the list are ever handed out (hvg.py:70), so they are SELECTED
+  // (nth_element on contiguous (z, position) keys, then a sort of the selection) instead of sorting all g genes
+  // through an indirect comparator -- 2.8 ms of a 41 ms pass at 33,000 genes.
+  struct Key {
+    double z;
+    int pos, id;
+  };
+  std::vector<Key> good;
+  std::vector<int> bad;
+  good.reserve(concat.size());
+  for (size_t p = 0; p < concat.size(); ++p) {
+    const int id = concat[p];
+    if (std::isnan(z[id])) bad.push_back(id);
+    else good.push_back(Key{z[id], (int)p, id});
+  }
+  auto before = [](const Key& a, const Key& b) { return a.z > b.z || (a.z == b.z && a.pos < b.pos); };
+  const size_t want = (size_t)std::max(ngenes, 0);
+  if (want < good.size()) {
+    std::nth_element(good.begin(), good.begin() + want, good.end(), before);
+    good.resize(want);
+  }
+  std::sort(good.begin(), good.end(), before);
+  order.clear();
+  order.reserve(good.size() + bad.size());
+  for (const Key& k : good) order.push_back(k.id);
+  if (order.size() < want) order.insert(order.end(), bad.begin(), bad.end());
 }
 
 }  // namespace adobo

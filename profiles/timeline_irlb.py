@@ -9,7 +9,7 @@ from adobo_b200.synth import synth_counts
 
 cells = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 eng = Engine(0)
-counts = synth_counts(cells, 3000, 0.10, 77)
+counts = synth_counts(cells, 3000, 0.05, 77)
 eng.upload_counts(counts)
 np.random.seed(42)
 v0 = np.random.randn(1000)
