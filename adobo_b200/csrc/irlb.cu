@@ -1921,6 +1921,125 @@ __global__ void __launch_bounds__(RS == 1 ? 512 : 768) rotate_rows(const RotJob 
   }
   TL_EXIT(384);
 }
+// ---- rotate_mma: the same product on the fp64 tensor-core path (mma.sync m8n8k4) -------------------------------------
+// The SIMT kernels above feed 16 DFMA from 6 shared-memory loads per inner step and keep the fp64 pipe ~29 % busy
+// (rotate_basis, ncu) -- the shared-memory pipe and instruction issue are what they wait for, and a tile of 64 rows is
+// the least a CTA can take (14 us for the 1000-row V and Z of every restart: 32 CTAs on 148 SMs).  DMMA has the same
+// peak as DFMA on this part (64 FMA/clk/SM, profiles/micro) but does 256 FMAs per instruction from two operand
+// registers: a warp tile of WM x WN 8 x 8 blocks needs WM + WN loads for 256 WM WN FMAs, and the tile height is a
+// free multiple of 8 rows.  Q arrives ROW-MAJOR through 16-byte cp.async (no transposing 8-byte copies); both operand
+// tiles have a row stride = 4 (mod 16) doubles, so the 8 x 4 / 4 x 8 fragment loads are free of bank conflicts.
+//   <MB, WM, WN> = <8, 4, 2>: 64-row tiles streamed through a double buffer (long shards: W)
+//   <MB, WM, WN> = <2, 2, 1>: 16-row tiles, one per CTA (V and Z of a restart on all SMs)
+__device__ __forceinline__ void dmma_884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+template <int MB, int WM, int WN>
+__global__ void __launch_bounds__(512) rotate_mma(const RotJob ja, const RotJob jb, const RotJob jc, int nba, int nbb,
+                                                  int ld, int m, int kc, int nbuf, const int* __restrict__ halt) {
+  if (halt && *halt) return;
+  TL_ENTRY(384);
+  constexpr int TR = 8 * MB, NWM = MB / WM;
+  const int which = ((int)blockIdx.x >= nba) + ((int)blockIdx.x >= nba + nbb);
+  const RotJob& job = which == 0 ? ja : (which == 1 ? jb : jc);
+  double* __restrict__ Q = job.Q;
+  const i64 rows = job.rows;
+  const double* __restrict__ St = job.St;
+  double* __restrict__ out = job.out;
+  const int ldo = job.ldo;
+  const double* __restrict__ colscale = job.colscale;
+  const unsigned bid = which == 0 ? blockIdx.x : (which == 1 ? blockIdx.x - nba : blockIdx.x - nba - nbb);
+  const unsigned nblk = which == 0 ? nba : (which == 1 ? nbb : gridDim.x - nba - nbb);
+  extern __shared__ __align__(16) double sm[];
+  const int kcp = (kc + 7) & ~7, m4 = (m + 3) & ~3;
+  const int ldp = kcp + 4, ldq = ((m + 7) & ~7) + 4;
+  double* Ssm = sm;                       // [m4][ldp], rows >= m zero
+  double* Qs = sm + (size_t)m4 * ldp;     // [nbuf][TR][ldq]
+  const size_t qstride = (size_t)TR * ldq;
+  const int nthr = (int)blockDim.x;
+  for (int idx = threadIdx.x; idx < m4 * (kcp >> 1); idx += nthr) {
+    const int i = idx / (kcp >> 1), c2 = idx - i * (kcp >> 1);
+    double2 v = make_double2(0.0, 0.0);
+    if (i < m) v = *reinterpret_cast<const double2*>(St + (size_t)i * kcp + 2 * c2);
+    *reinterpret_cast<double2*>(Ssm + (size_t)i * ldp + 2 * c2) = v;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp % NWM, wn = warp / NWM;
+  const i64 ntiles = (rows + TR - 1) / TR;
+  // the columns m .. m4 - 1 of a tile are whatever the buffer holds there (finite: every basis is zero-filled when the
+  // decomposition starts): they meet the zero rows of Ssm
+  auto fetch = [&](i64 t, int buf) {
+    const i64 row0 = t * TR;
+    double* dst = Qs + buf * qstride;
+    const int nch = m4 >> 1;
+    for (int idx = threadIdx.x; idx < TR * nch; idx += nthr) {
+      const int r = idx / nch, c2 = idx - r * nch;
+      double* d = dst + (size_t)r * ldq + 2 * c2;
+      if (row0 + r < rows) cp_async16(d, Q + (size_t)(row0 + r) * ld + 2 * c2);
+      else *reinterpret_cast<double2*>(d) = make_double2(0.0, 0.0);
+    }
+    cp_async_commit();
+  };
+  int buf = 0;
+  if ((i64)bid < ntiles) fetch(bid, 0);
+  const int ar = lane >> 2, ak = lane & 3;   // fragment coordinates: A[row ar][k ak], B[k ak][col ar], C[row ar][cols 2 ak, 2 ak + 1]
+  for (i64 t = bid; t < ntiles; t += nblk) {
+    cp_async_wait_all();
+    __syncthreads();  // tile t landed (and Ssm written); everybody is done with the other buffer
+    const i64 tn = t + nblk;
+    if (nbuf == 2 && tn < ntiles) fetch(tn, buf ^ 1);
+    const double* qa = Qs + buf * qstride + (size_t)(8 * wm * WM + ar) * ldq + ak;
+    const double* sb = Ssm + (size_t)ak * ldp + 8 * wn * WN + ar;
+    double acc[WM][WN][2];
+#pragma unroll
+    for (int i = 0; i < WM; ++i)
+#pragma unroll
+      for (int j = 0; j < WN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    bool nbok[WN];
+#pragma unroll
+    for (int j = 0; j < WN; ++j) nbok[j] = 8 * (wn * WN + j) < kcp;
+#pragma unroll 2
+    for (int k0 = 0; k0 < m4; k0 += 4) {
+      double a[WM], b[WN];
+#pragma unroll
+      for (int i = 0; i < WM; ++i) a[i] = qa[(size_t)(8 * i) * ldq + k0];
+#pragma unroll
+      for (int j = 0; j < WN; ++j) b[j] = nbok[j] ? sb[(size_t)k0 * ldp + 8 * j] : 0.0;
+#pragma unroll
+      for (int i = 0; i < WM; ++i)
+#pragma unroll
+        for (int j = 0; j < WN; ++j) dmma_884(acc[i][j], a[i], b[j]);
+    }
+    if (nbuf == 1) {
+      __syncthreads();  // single buffer: everybody is done reading before it is refilled
+      if (tn < ntiles) fetch(tn, 0);
+    }
+    const i64 row0 = t * TR;
+#pragma unroll
+    for (int i = 0; i < WM; ++i) {
+      const i64 r = row0 + 8 * (wm * WM + i) + ar;
+      if (r < rows) {
+        double* dst = out ? out + (size_t)r * ldo : Q + (size_t)r * ld;
+#pragma unroll
+        for (int j = 0; j < WN; ++j) {
+          const int col = 8 * (wn * WN + j) + 2 * ak;
+          double v0 = acc[i][j][0], v1 = acc[i][j][1];
+          if (colscale) {
+            if (col < kc) v0 *= colscale[col];
+            if (col + 1 < kc) v1 *= colscale[col + 1];
+          }
+          if (col + 1 < kc) *reinterpret_cast<double2*>(dst + col) = make_double2(v0, v1);
+          else if (col < kc) dst[col] = v0;
+        }
+      }
+    }
+    if (nbuf == 2) buf ^= 1;
+  }
+  cp_async_wait_all();
+}
+
 using rotate_rows_fn = void (*)(const RotJob, const RotJob, const RotJob, int, int, int, int, int, const int*);
 static rotate_rows_fn rotate_rows_for(int R, int RS = 1) {
   if (RS == 2) return R <= 2 ? rotate_rows<2, 2> : rotate_rows<3, 2>;
@@ -2074,6 +2193,7 @@ enum : unsigned {
   HK_NO_RUNAHEAD = 1u << 12,     // wait for every convergence read-back
   HK_TRACE = 1u << 13,           // one line per outer iteration on stderr
   HK_NO_LAZY = 1u << 14,         // rotate W at every restart (two-kernel step without the lazy rotation)
+  HK_ROTATE_SIMT = 1u << 15,     // DFMA rotation kernels (rotate_rows / rotate_basis) instead of the tensor-core one
 };
 static unsigned irlb_hooks() {
   static const struct { const char* name; unsigned bit; } names[] = {
@@ -2081,7 +2201,7 @@ static unsigned irlb_hooks() {
       {"no_fork", HK_NO_FORK}, {"rotate_streamed", HK_ROTATE_STREAMED}, {"no_fusedt", HK_NO_FUSEDT},
       {"no_vone", HK_NO_VONE}, {"no_zpath", HK_NO_ZPATH}, {"no_vstep", HK_NO_VSTEP}, {"no_wfold", HK_NO_WFOLD},
       {"no_split", HK_NO_SPLIT}, {"no_pdl", HK_NO_PDL}, {"no_runahead", HK_NO_RUNAHEAD}, {"trace", HK_TRACE},
-      {"no_lazy", HK_NO_LAZY}};
+      {"no_lazy", HK_NO_LAZY}, {"rotate_simt", HK_ROTATE_SIMT}};
   const char* e = getenv("ADOBO_B200_IRLB");
   unsigned bits = 0;
   if (!e) return 0;
@@ -2296,6 +2416,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   const int* hp_halt = nullptr;  // halt flag handed to the kernels of an outer iteration (run-ahead), else none
   // The tall-skinny GEMMs Q[:, :kc] (or out) = Q[:, :inner] S[:, :kc] of a restart / of the final vectors: up to three
   // jobs in one launch (rows = 0: no CTAs), the SMs split between them in proportion to their 64-row tiles.
+  auto ldo_even = [&](const RotJob& j) { return j.rows == 0 || j.out == nullptr || (j.ldo % 2 == 0 && ((uintptr_t)j.out & 15) == 0); };
   auto rotate_launch = [&](RotJob jv, RotJob jz, RotJob jw, int ldq, int inner, int kc) {
     const int kcp = (kc + 7) & ~7;
     const i64 sms = c->sm_count;
@@ -2307,6 +2428,34 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     if (bv + bz + bw == 0) return;
     const unsigned nbv = (unsigned)bv, nbz = (unsigned)bz, nbw = (unsigned)bw;
     WORK(c, 8.0 * (jv.rows + jz.rows + jw.rows) * (inner + kc));
+    // tensor-core path (rotate_mma): 16-row tiles when every SM gets at most a few of them, else 64-row tiles
+    // streamed through a double buffer.  The SIMT kernels stay behind the rotate_simt / rotate_streamed hooks.
+    if (!hook(HK_ROTATE_SIMT) && !hook(HK_ROTATE_STREAMED) && (ldo_even(jv) && ldo_even(jz) && ldo_even(jw))) {
+      const int m4 = (inner + 3) & ~3, ldp = kcp + 4, ldqs = ((inner + 7) & ~7) + 4;
+      const i64 rows_all = jv.rows + jz.rows + jw.rows;
+      const bool small = rows_all <= 16 * 3 * sms;
+      const int TR = small ? 16 : 64;
+      const i64 uv = (jv.rows + TR - 1) / TR, uz = (jz.rows + TR - 1) / TR, uw = (jw.rows + TR - 1) / TR;
+      const i64 uall = std::max<i64>(1, uv + uz + uw);
+      const i64 cap = small ? uall : sms;   // small: one tile per CTA (several CTAs per SM); long: persistent CTAs
+      i64 cv = uv ? std::max<i64>(1, std::min<i64>((uv * cap + uall / 2) / uall, uv)) : 0;
+      i64 cz = uz ? std::max<i64>(1, std::min<i64>((uz * cap + uall / 2) / uall, uz)) : 0;
+      i64 cw = uw ? std::max<i64>(1, std::min<i64>(uw, std::max<i64>(1, cap - cv - cz))) : 0;
+      const size_t s_b = sizeof(double) * (size_t)m4 * ldp, q_b = sizeof(double) * (size_t)TR * ldqs;
+      const int nbuf = (!small && s_b + 2 * q_b <= 225 * 1024) ? 2 : 1;
+      const size_t smem = s_b + nbuf * q_b;
+      REQUIRE(smem <= 227 * 1024, ADOBO_ERR_LIMIT, "rotate_mma: %d x %d rotation does not fit shared memory", inner, kcp);
+      if (small) {
+        CUDA_CHECK(cudaFuncSetAttribute(rotate_mma<2, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LAUNCH(c, "rotate_basis", (rotate_mma<2, 2, 1><<<(unsigned)(cv + cz + cw), 32 * (kcp / 8), smem, st>>>(
+                                     jv, jz, jw, (int)cv, (int)cz, ldq, inner, kc, nbuf, hp_halt)));
+      } else {
+        CUDA_CHECK(cudaFuncSetAttribute(rotate_mma<8, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LAUNCH(c, "rotate_basis", (rotate_mma<8, 4, 2><<<(unsigned)(cv + cz + cw), 32 * 2 * ((kcp / 8 + 1) / 2), smem, st>>>(
+                                     jv, jz, jw, (int)cv, (int)cz, ldq, inner, kc, nbuf, hp_halt)));
+      }
+      return;
+    }
     // few tiles per SM: rotate_rows (row range per CTA, loads pipelined along the inner dimension);
     // long shards: rotate_basis (64-row tiles streamed through a double buffer)
     i64 per = 1;  // rows per CTA
