@@ -1800,12 +1800,6 @@ __global__ void __launch_bounds__(512) rotate_basis(const RotJob ja, const RotJo
   cp_async_wait_all();
 }
 
-// ---- rotate_rows<R>: the same product for shards of up to a few hundred rows per SM ---------------
-// At the C2 size a CTA owns ~140 rows: rotate_basis would run three 64-row tiles behind a serial prologue
-// (S, then the first tile).  Here a CTA takes its whole row range as tiles of 32 R rows (R rows per lane,
-// 8 R accumulators), and the loads of a tile are pipelined along the INNER dimension instead: S and Q are
-// fetched in four cp.async groups by ranges of i, and the FMA loop over the first range starts when that
-// group has landed while the other three are still in flight.  8 R DFMA per R + 4 shared loads.
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
@@ -1814,113 +1808,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
-constexpr int RR_CHUNKS = 4;
 
-// RS = row splits: the tile's rows are divided between RS groups of (kcp / 8) warps, which doubles the resident warps
-// (ncu on rotate_rows<5>: 12 warps per SM keep the fp64 pipe 42 % busy; the rest is dependency and LDS waits).
-template <int R, int RS>
-__global__ void __launch_bounds__(RS == 1 ? 512 : 768) rotate_rows(const RotJob ja, const RotJob jb, const RotJob jc, int nba, int nbb,
-                                                   int ld, int m, int kc, const int* __restrict__ halt) {
-  if (halt && *halt) return;
-  TL_ENTRY(384);
-  const int which = ((int)blockIdx.x >= nba) + ((int)blockIdx.x >= nba + nbb);
-  const RotJob& job = which == 0 ? ja : (which == 1 ? jb : jc);
-  double* __restrict__ Q = job.Q;
-  const double* __restrict__ St = job.St;
-  double* __restrict__ out = job.out;
-  const int ldo = job.ldo;
-  const double* __restrict__ colscale = job.colscale;
-  const i64 bid = which == 0 ? blockIdx.x : (which == 1 ? blockIdx.x - nba : blockIdx.x - nba - nbb);
-  const i64 nblk = which == 0 ? nba : (which == 1 ? nbb : gridDim.x - nba - nbb);
-  const i64 per = (job.rows + nblk - 1) / nblk;
-  const i64 lo = bid * per, hi = min(job.rows, lo + per);
-  constexpr int TR = 32 * R * RS, RP = TR + 1;
-  extern __shared__ __align__(16) double sm[];
-  const int kcp = (kc + 7) & ~7;
-  double* Ssm = sm;                   // [m][kcp]
-  double* Qs = sm + (size_t)m * kcp;  // [m][RP], transposed tile
-  const int lane = threadIdx.x & 31, nthr = blockDim.x;
-  const int wcols = (int)(blockDim.x >> 5) / RS;                      // warps along the columns
-  const int warp = (int)(threadIdx.x >> 5) % wcols;                   // column group: columns 8 warp .. 8 warp + 7
-  const int rbase = ((int)(threadIdx.x >> 5) / wcols) * 32 * R;       // first row of this warp's share of the tile
-  bool s_loaded = false;
-  for (i64 row0 = lo; row0 < hi; row0 += TR) {
-    const int nrow = (int)min((i64)TR, hi - row0);
-    if (row0 != lo) __syncthreads();  // everybody is done with the previous tile
-#pragma unroll
-    for (int ch = 0; ch < RR_CHUNKS; ++ch) {
-      const int i0 = (m * ch) / RR_CHUNKS, w = (m * (ch + 1)) / RR_CHUNKS - i0;
-      if (!s_loaded)
-        for (int idx = threadIdx.x; idx < w * kcp / 2; idx += nthr)
-          cp_async16(Ssm + (size_t)i0 * kcp + 2 * idx, St + (size_t)i0 * kcp + 2 * idx);
-      for (int idx = threadIdx.x; idx < nrow * w; idx += nthr) {
-        const int r = idx / w, i = i0 + (idx - r * w);
-        cp_async8(Qs + (size_t)i * RP + r, Q + (size_t)(row0 + r) * ld + i);
-      }
-      cp_async_commit();
-    }
-    s_loaded = true;
-    double acc[R][8];
-#pragma unroll
-    for (int q = 0; q < R; ++q)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) acc[q][c] = 0.0;
-    const double* qp = Qs + rbase + lane;
-    const double* sp = Ssm + warp * 8;
-#pragma unroll
-    for (int ch = 0; ch < RR_CHUNKS; ++ch) {
-      if (ch == 0) cp_async_wait<3>();
-      if (ch == 1) cp_async_wait<2>();
-      if (ch == 2) cp_async_wait<1>();
-      if (ch == 3) cp_async_wait<0>();
-      __syncthreads();
-      const int i0 = (m * ch) / RR_CHUNKS, i1 = (m * (ch + 1)) / RR_CHUNKS;
-#pragma unroll 2
-      for (int i = i0; i < i1; ++i) {
-        double x[R];
-#pragma unroll
-        for (int q = 0; q < R; ++q) x[q] = qp[(size_t)i * RP + 32 * q];
-        const double2 s0 = *reinterpret_cast<const double2*>(sp + (size_t)i * kcp);
-        const double2 s1 = *reinterpret_cast<const double2*>(sp + (size_t)i * kcp + 2);
-        const double2 s2 = *reinterpret_cast<const double2*>(sp + (size_t)i * kcp + 4);
-        const double2 s3 = *reinterpret_cast<const double2*>(sp + (size_t)i * kcp + 6);
-#pragma unroll
-        for (int q = 0; q < R; ++q) {
-          acc[q][0] = fma(x[q], s0.x, acc[q][0]);
-          acc[q][1] = fma(x[q], s0.y, acc[q][1]);
-          acc[q][2] = fma(x[q], s1.x, acc[q][2]);
-          acc[q][3] = fma(x[q], s1.y, acc[q][3]);
-          acc[q][4] = fma(x[q], s2.x, acc[q][4]);
-          acc[q][5] = fma(x[q], s2.y, acc[q][5]);
-          acc[q][6] = fma(x[q], s3.x, acc[q][6]);
-          acc[q][7] = fma(x[q], s3.y, acc[q][7]);
-        }
-      }
-    }
-    const bool vec = out == nullptr && warp * 8 + 8 <= kc;  // in place, full column group: 128-bit stores
-#pragma unroll
-    for (int q = 0; q < R; ++q) {
-      const int r = rbase + lane + 32 * q;
-      if (r < nrow) {
-        if (vec) {
-          double2* dst = reinterpret_cast<double2*>(Q + (size_t)(row0 + r) * ld + warp * 8);
-          dst[0] = make_double2(acc[q][0], acc[q][1]);
-          dst[1] = make_double2(acc[q][2], acc[q][3]);
-          dst[2] = make_double2(acc[q][4], acc[q][5]);
-          dst[3] = make_double2(acc[q][6], acc[q][7]);
-        } else {
-          double* dst = out ? out + (size_t)(row0 + r) * ldo : Q + (size_t)(row0 + r) * ld;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const int col = warp * 8 + c;
-            if (col < kc) dst[col] = colscale ? acc[q][c] * colscale[col] : acc[q][c];
-          }
-        }
-      }
-    }
-  }
-  TL_EXIT(384);
-}
 // ---- rotate_mma: the same product on the fp64 tensor-core path (mma.sync m8n8k4) -------------------------------------
 // The SIMT kernels above feed 16 DFMA from 6 shared-memory loads per inner step and keep the fp64 pipe ~29 % busy
 // (rotate_basis, ncu) -- the shared-memory pipe and instruction issue are what they wait for, and a tile of 64 rows is
@@ -2038,18 +1926,6 @@ __global__ void __launch_bounds__(512) rotate_mma(const RotJob ja, const RotJob 
     if (nbuf == 2) buf ^= 1;
   }
   cp_async_wait_all();
-}
-
-using rotate_rows_fn = void (*)(const RotJob, const RotJob, const RotJob, int, int, int, int, int, const int*);
-static rotate_rows_fn rotate_rows_for(int R, int RS = 1) {
-  if (RS == 2) return R <= 2 ? rotate_rows<2, 2> : rotate_rows<3, 2>;
-  switch (R) {
-    case 1: return rotate_rows<1, 1>;
-    case 2: return rotate_rows<2, 1>;
-    case 3: return rotate_rows<3, 1>;
-    case 4: return rotate_rows<4, 1>;
-    default: return rotate_rows<5, 1>;
-  }
 }
 
 // ---- V[:,k] = F ; B = diag(sv[:k]) + R[:k] in column k  (irlb.py:239-244) ------------------------
@@ -2182,7 +2058,6 @@ enum : unsigned {
   HK_SVD_FALLBACK = 1u << 1,     // exercise the fallback that runs when svd_arrow rejects its own result
   HK_NO_GRAPH = 1u << 2,         // launch kernel by kernel instead of replaying CUDA graphs
   HK_NO_FORK = 1u << 3,          // SVD of B in the main stream instead of beside the last step
-  HK_ROTATE_STREAMED = 1u << 4,  // rotate_basis (long shards) whatever the shard length
   HK_NO_FUSEDT = 1u << 5,        // three-kernel step (w_step3 + spmvT_csc + v_step*): the path for h > 1024
   HK_NO_VONE = 1u << 6,          // v_step instead of v_step_one: the path for 1024 < h <= 8192
   HK_NO_ZPATH = 1u << 7,         // two-pass Gram-Schmidt kernels: the path for h > 8192 or m_b > 126
@@ -2193,15 +2068,15 @@ enum : unsigned {
   HK_NO_RUNAHEAD = 1u << 12,     // wait for every convergence read-back
   HK_TRACE = 1u << 13,           // one line per outer iteration on stderr
   HK_NO_LAZY = 1u << 14,         // rotate W at every restart (two-kernel step without the lazy rotation)
-  HK_ROTATE_SIMT = 1u << 15,     // DFMA rotation kernels (rotate_rows / rotate_basis) instead of the tensor-core one
+  HK_ROTATE_SIMT = 1u << 4,      // DFMA rotation kernel (rotate_basis) instead of the tensor-core one
 };
 static unsigned irlb_hooks() {
   static const struct { const char* name; unsigned bit; } names[] = {
       {"svd_jacobi", HK_SVD_JACOBI}, {"svd_fallback", HK_SVD_FALLBACK}, {"no_graph", HK_NO_GRAPH},
-      {"no_fork", HK_NO_FORK}, {"rotate_streamed", HK_ROTATE_STREAMED}, {"no_fusedt", HK_NO_FUSEDT},
+      {"no_fork", HK_NO_FORK}, {"rotate_simt", HK_ROTATE_SIMT}, {"no_fusedt", HK_NO_FUSEDT},
       {"no_vone", HK_NO_VONE}, {"no_zpath", HK_NO_ZPATH}, {"no_vstep", HK_NO_VSTEP}, {"no_wfold", HK_NO_WFOLD},
       {"no_split", HK_NO_SPLIT}, {"no_pdl", HK_NO_PDL}, {"no_runahead", HK_NO_RUNAHEAD}, {"trace", HK_TRACE},
-      {"no_lazy", HK_NO_LAZY}, {"rotate_simt", HK_ROTATE_SIMT}};
+      {"no_lazy", HK_NO_LAZY}};
   const char* e = getenv("ADOBO_B200_IRLB");
   unsigned bits = 0;
   if (!e) return 0;
@@ -2429,8 +2304,8 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     const unsigned nbv = (unsigned)bv, nbz = (unsigned)bz, nbw = (unsigned)bw;
     WORK(c, 8.0 * (jv.rows + jz.rows + jw.rows) * (inner + kc));
     // tensor-core path (rotate_mma): 16-row tiles when every SM gets at most a few of them, else 64-row tiles
-    // streamed through a double buffer.  The SIMT kernels stay behind the rotate_simt / rotate_streamed hooks.
-    if (!hook(HK_ROTATE_SIMT) && !hook(HK_ROTATE_STREAMED) && (ldo_even(jv) && ldo_even(jz) && ldo_even(jw))) {
+    // streamed through a double buffer
+    if (!hook(HK_ROTATE_SIMT) && ldo_even(jv) && ldo_even(jz) && ldo_even(jw)) {
       const int m4 = (inner + 3) & ~3, ldp = kcp + 4, ldqs = ((inner + 7) & ~7) + 4;
       const i64 rows_all = jv.rows + jz.rows + jw.rows;
       const bool small = rows_all <= 16 * 3 * sms;
@@ -2456,22 +2331,9 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
       }
       return;
     }
-    // few tiles per SM: rotate_rows (row range per CTA, loads pipelined along the inner dimension);
-    // long shards: rotate_basis (64-row tiles streamed through a double buffer)
-    i64 per = 1;  // rows per CTA
-    if (bv) per = std::max<i64>(per, (jv.rows + bv - 1) / bv);
-    if (bz) per = std::max<i64>(per, (jz.rows + bz - 1) / bz);
-    if (bw) per = std::max<i64>(per, (jw.rows + bw - 1) / bw);
+    // fallback (rotate_simt hook; an output whose rows are not 16-byte aligned): the DFMA kernel, 64-row tiles
     const size_t s_bytes = sizeof(double) * (size_t)inner * kcp;
-    const int r_fit = (int)std::min<i64>(5, (((i64)(225 * 1024 - s_bytes) / (8 * inner)) - 1) / 32);
-    if (!hook(HK_ROTATE_STREAMED) && r_fit >= 1 && per <= 2 * 32 * r_fit) {
-      const i64 ntile = (per + 32 * r_fit - 1) / (32 * r_fit);
-      const int Rr = (int)std::min<i64>(r_fit, ((per + ntile - 1) / ntile + 31) / 32);
-      const size_t smem = s_bytes + sizeof(double) * (size_t)inner * (32 * Rr + 1);
-      rotate_rows_fn fn = rotate_rows_for(Rr);
-      CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      LAUNCH(c, "rotate_basis", (fn<<<nbv + nbz + nbw, 32 * (kcp / 8), smem, st>>>(jv, jz, jw, (int)nbv, (int)nbz, ldq, inner, kc, hp_halt)));
-    } else {
+    {
       const size_t q_bytes = sizeof(double) * (size_t)inner * RB_QP;
       const int nbuf = (s_bytes + 2 * q_bytes <= 225 * 1024) ? 2 : 1;
       const size_t smem = s_bytes + nbuf * q_bytes;
@@ -2613,6 +2475,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     const LState next = lazy_next(prev, k, &mat);
     const int kcp = (k + 7) & ~7;
     rotate2(k, nullptr, nullptr, 0, nullptr, true, false);  // V and Z
+    // (lazy_p0 beside this rotation on the side stream was measured: the fork / join nodes cost what the overlap saves)
     LAUNCH(c, "lazy_p0", (lazy_p0<<<prev.S, 128, 0, st>>>(ws.P0.p, ws.P0t.p, ldp, prev.U0, prev.kp, Su.p, m_b, k,
                                                          mat ? ws.Pmat.p : nullptr, kcp, hp_halt,
                                                          mat ? nullptr : (const double*)ws.crot.p, cvec.p)));

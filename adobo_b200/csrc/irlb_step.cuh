@@ -583,7 +583,7 @@ __global__ void w_finish_t(const double* __restrict__ ybuf, const double* __rest
 // P0_new = [P0 0; 0 I] Su[:, :kn]   (S rows: the U0 stored columns behind the old Ritz vectors, then the m - kp raw ones).
 // One CTA per row s, in place (row s of the product needs row s of P0 only); outputs: P0 (row stride ldp, zero
 // padded), its transpose P0t, and -- for the launches that rotate W_s for real -- the same matrix with row stride
-// kcp = kn rounded up to 8, the layout rotate_basis / rotate_rows read their rotation matrix in.
+// kcp = kn rounded up to 8, the layout the rotation kernels read their matrix in.
 // With crot != nullptr the CTA also leaves c_s[s] = P0_new[s, :] . crot, the coefficients of the restart's first new
 // column in stored space (crot: conv_check's coefficients in the new rotated basis).
 __global__ void __launch_bounds__(128) lazy_p0(double* __restrict__ P0, double* __restrict__ P0t, int ldp, int U0, int kp,

@@ -222,7 +222,7 @@ def test_knn_blobs_30k_tensor_core_path(eng):
         assert np.array_equal(nn[:, 0], np.arange(1, 30001))
 
 
-@pytest.mark.parametrize('hook', ['svd_jacobi', 'svd_fallback', 'no_graph', 'no_fork', 'rotate_streamed', 'no_fusedt',
+@pytest.mark.parametrize('hook', ['svd_jacobi', 'svd_fallback', 'no_graph', 'no_fork', 'rotate_simt', 'no_fusedt',
                                   'no_fusedt,no_vone', 'no_zpath', 'no_vstep', 'no_fusedt,no_wfold', 'no_fusedt,no_split',
                                   'no_pdl', 'no_runahead', 'no_fusedt,no_pdl', 'no_lazy', 'no_lazy,no_graph', 'SVD_CLUSTER'])
 def test_irlb_alternative_paths(eng, hook, monkeypatch):
