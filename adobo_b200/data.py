@@ -70,6 +70,19 @@ class CsrFrame:
         return 'CsrFrame(%d genes x %d cells, %d non-zeros, %s)' % (self.shape + (self.csr.nnz, self.csr.dtype))
 
 
+def _row_sums(csr):
+    """Row sums of a CSR matrix in int64 / float64 without the dtype-converted copy of `data` that scipy's sum makes
+    (0.2 s at 70 M non-zeros): one reduceat over the row starts, empty rows set to zero afterwards."""
+    n = csr.shape[0]
+    out = np.zeros(n, dtype=np.int64 if np.issubdtype(csr.dtype, np.integer) else np.float64)
+    if csr.nnz == 0 or n == 0:
+        return out
+    lens = np.diff(csr.indptr)
+    rows = np.flatnonzero(lens > 0)
+    out[rows] = np.add.reduceat(csr.data, csr.indptr[rows], dtype=out.dtype)
+    return out
+
+
 class dataset:
     def __init__(self, raw_mat, desc='no desc set', output_file=None, input_file=None, sparse=True, verbose=False):
         self.sparse = sparse
@@ -87,11 +100,12 @@ class dataset:
         self._norm_data = {}
         csr = frame_to_csr(self.count_data)                                  # cells x genes
         self.meta_cells = pd.DataFrame(index=raw_mat.columns)                # data.py:75-78
-        self.meta_cells['total_reads'] = np.asarray(csr.sum(axis=1)).ravel()
+        self.meta_cells['total_reads'] = _row_sums(csr)
         self.meta_cells['status'] = ['OK'] * raw_mat.shape[1]
         self.meta_cells['detected_genes'] = np.diff(csr.indptr)
         self.meta_genes = pd.DataFrame(index=raw_mat.index)                  # data.py:80-89
-        expressed = np.bincount(csr.indices[csr.data > 0], minlength=raw_mat.shape[0])
+        pos = csr.data > 0
+        expressed = np.bincount(csr.indices if pos.all() else csr.indices[pos], minlength=raw_mat.shape[0])
         self.meta_genes['expressed'] = expressed
         self.meta_genes['expressed_perc'] = expressed / raw_mat.shape[1] * 100
         self.meta_genes['status'] = ['OK'] * raw_mat.shape[0]

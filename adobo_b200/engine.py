@@ -119,7 +119,7 @@ class Engine:
         indptr = np.ascontiguousarray(m.indptr, dtype=np.int64)
         indices = np.ascontiguousarray(m.indices, dtype=np.int32)
         data = np.ascontiguousarray(m.data)
-        if data.size and (data.min() < -2 ** 31 or data.max() >= 2 ** 31):
+        if data.dtype != np.int32 and data.size and (data.min() < -2 ** 31 or data.max() >= 2 ** 31):
             raise Exception('counts do not fit int32')
         data = data.astype(np.int32, copy=False)
         check(self.lib.adobo_upload_counts(self.h, m.shape[0], m.shape[1], indptr, indices, np.ascontiguousarray(data)))
@@ -168,7 +168,9 @@ class Engine:
             m = self.download_counts()
             self._pattern = (np.ascontiguousarray(m.indptr, dtype=np.int64), np.ascontiguousarray(m.indices, dtype=np.int32))
         indptr, indices = self._pattern
-        return sp.csr_matrix((vals, indices, indptr), shape=(self.n, self.g)), lib
+        out = sp.csr_matrix((vals, indices, indptr), shape=(self.n, self.g))
+        out.has_sorted_indices = True                    # the pattern that was uploaded (as_csr sorts): no re-check per use
+        return out, lib
 
     def gene_moments(self):
         mean = np.empty(self.g)
