@@ -371,12 +371,17 @@ __device__ __forceinline__ void peer_allreduce_block(const PeerComm& pc, double*
 // store is split on the way: the protocol of NCCL's LL).  The receiver polls the words themselves: one NVLink
 // crossing per exchange instead of data + system fence + flag.  vec: shared memory of the calling CTA, count <=
 // PEER_LL_MAX; parity double buffering as above.
-__device__ __forceinline__ void peer_allreduce_ll(const PeerComm& pc, double* vec, int count, int ch) {
+// seq_pre: this exchange's sequence number (pc.seq[ch] + 1) when the caller has read it already -- v_step_t does in its
+// prologue, off the critical path -- else 0.
+__device__ __forceinline__ void peer_allreduce_ll(const PeerComm& pc, double* vec, int count, int ch, unsigned seq_pre = 0) {
   __shared__ unsigned s_seq_ll;
   const int W = pc.world, me = pc.rank;
-  if (threadIdx.x == 0) s_seq_ll = pc.seq[ch] + 1u;
-  __syncthreads();
-  const unsigned seq = s_seq_ll;
+  unsigned seq = seq_pre;
+  if (seq_pre == 0) {
+    if (threadIdx.x == 0) s_seq_ll = pc.seq[ch] + 1u;
+    __syncthreads();
+    seq = s_seq_ll;
+  }
   const int par = (int)(seq & 1u);
   const int i = threadIdx.x;
   if (i < count) {
@@ -386,25 +391,38 @@ __device__ __forceinline__ void peer_allreduce_ll(const PeerComm& pc, double* ve
       uint4* dst = pc.ll[r] + ((size_t)(par * W + me) * PEER_CH + ch) * PEER_LL_MAX + i;
       asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(lo), "r"(seq), "r"(hi), "r"(seq) : "memory");
     }
-    double s = 0;
+    // every rank's word is polled in the SAME round (independent loads: one L2 round trip per round, not one per
+    // rank -- eight serial polls were 3 us of the exchange at N = 8); the sum is then taken in rank order
+    const uint4* src0 = pc.ll[me] + ((size_t)(par * W) * PEER_CH + ch) * PEER_LL_MAX + i;
+    unsigned wa[PEER_MAX], wc[PEER_MAX];
+    unsigned pending = (W >= 32) ? 0xffffffffu : ((1u << W) - 1u);
     unsigned long long t0 = 0;
-    for (int r = 0; r < W; ++r) {  // rank order: the same sum on every rank
-      const uint4* src = pc.ll[me] + ((size_t)(par * W + r) * PEER_CH + ch) * PEER_LL_MAX + i;
-      unsigned a, b, c, d, polls = 0;
-      for (;;) {
-        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(src) : "memory");
-        if (b == seq && d == seq) break;
-        if ((++polls & 1023u) == 0) {
-          const unsigned long long now = peer_now_ns();
-          if (t0 == 0) t0 = now;
-          if (now - t0 > PEER_TIMEOUT_NS) {
-            if (pc.err) atomicExch(pc.err, 1 + r);
-            break;
-          }
+    unsigned polls = 0;
+    while (pending) {
+      unsigned b[PEER_MAX], d[PEER_MAX];
+#pragma unroll
+      for (int r = 0; r < PEER_MAX; ++r)
+        if ((pending >> r) & 1u)
+          asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(wa[r]), "=r"(b[r]), "=r"(wc[r]), "=r"(d[r])
+                       : "l"(src0 + (size_t)r * PEER_CH * PEER_LL_MAX)
+                       : "memory");
+#pragma unroll
+      for (int r = 0; r < PEER_MAX; ++r)
+        if (((pending >> r) & 1u) && b[r] == seq && d[r] == seq) pending &= ~(1u << r);
+      if (pending && (++polls & 1023u) == 0) {
+        const unsigned long long now = peer_now_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > PEER_TIMEOUT_NS) {
+          if (pc.err) atomicExch(pc.err, 1 + (__ffs(pending) - 1));
+          break;
         }
       }
-      s += __longlong_as_double((long long)(((unsigned long long)c << 32) | a));
     }
+    double s = 0;
+#pragma unroll
+    for (int r = 0; r < PEER_MAX; ++r)   // rank order: the same sum on every rank
+      if (r < W) s += __longlong_as_double((long long)(((unsigned long long)wc[r] << 32) | wa[r]));
     vec[i] = s;
   }
   __syncthreads();

@@ -266,6 +266,8 @@ __global__ void __launch_bounds__(VS_THREADS, 1)
 #pragma unroll
     for (int q = 0; q < NQ; ++q) vq[i][q] = (ok && lane + 32 * q < nd) ? __ldcg(vr + lane + 32 * q) : 0.0;
   }
+  // the exchange's sequence number: last written by the v_step_t two kernels back, read here off the critical path
+  const unsigned seq_pre = pc.world > 1 ? pc.seq[1 + crank] + 1u : 0u;
   pdl_sync();
   if (halt && *halt) {  // uniform over the cluster
     cp_async_wait_all();
@@ -297,7 +299,7 @@ __global__ void __launch_bounds__(VS_THREADS, 1)
     }
     __syncthreads();
     TL_CTAK(1, 8);
-    if (pc.world > 1) peer_allreduce_ll(pc, msg, VT_MSG, 1 + crank);  // ends with a CTA barrier
+    if (pc.world > 1) peer_allreduce_ll(pc, msg, VT_MSG, 1 + crank, seq_pre);  // ends with a CTA barrier
     TL_CTAK(1, 9);
   }
   // the W column this step consumes was left unnormalised: s = ||y||, u = y / s  (irlb.py:176-178, 217-219)
