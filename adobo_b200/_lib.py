@@ -80,6 +80,7 @@ SIGNATURES = {
                                     C.c_double, C.c_int32, _arr(_f64), _OptArr(_f64, 2), _OptArr(_f64),
                                     _OptArr(_f64, 2), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     'adobo_knn': (C.c_int, [ctx_p, _OptArr(_f64, 2), C.c_int64, C.c_int32, C.c_int32, _OptArr(_i64, 2)]),
+    'adobo_knn_metric': (C.c_int, [ctx_p, _OptArr(_f64, 2), C.c_int64, C.c_int32, C.c_int32, C.c_int32, _OptArr(_i64, 2)]),
     'adobo_upload_embedding': (C.c_int, [ctx_p, _arr(_f64, 2), C.c_int64, C.c_int32]),
     'adobo_snn': (C.c_int, [ctx_p, _OptArr(_i64, 2), C.c_int64, C.c_int32, C.c_double, C.POINTER(C.c_int64),
                             C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

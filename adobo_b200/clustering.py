@@ -9,14 +9,23 @@ import pandas as pd
 from . import engine as _engine
 
 
+# clustering.py:47-48 hands `distance` to sklearn's ball tree; these are the ball-tree metrics that need no extra
+# parameter (seuclidean / mahalanobis need V / VI, which the reference cannot pass either; 'minkowski' runs with the
+# ball tree's default p = 2).  Codes: include/adobo_b200.h ADOBO_METRIC_*.
+METRICS = {'euclidean': 0, 'l2': 0, 'minkowski': 0, 'manhattan': 1, 'cityblock': 1, 'l1': 1, 'chebyshev': 2, 'infinity': 2,
+           'hamming': 3, 'canberra': 4, 'braycurtis': 5}
+
+
 def knn(comp, k=10, distance='euclidean', eng=None):
     """clustering.knn (clustering.py:25-52): exact k nearest neighbours of every cell in PCA
-    space; returns an (n, k) int64 array of 1-based indices, column 0 being the cell itself."""
-    if distance != 'euclidean':
-        raise Exception('adobo_b200.clustering.knn supports distance="euclidean" only.')
+    space; returns an (n, k) int64 array of 1-based indices, column 0 being the cell itself.
+    `distance`: the parameter-free ball-tree metrics in METRICS (Euclidean on the tensor cores, the
+    others by exact fp64 brute force)."""
+    if distance not in METRICS:
+        raise ValueError("Unrecognized metric '%s'; adobo_b200.clustering.knn supports %s" % (distance, ', '.join(METRICS)))
     eng = eng or _engine.default_engine()
     x = np.ascontiguousarray(np.asarray(comp), dtype=np.float64)
-    return eng.knn(x, k)
+    return eng.knn(x, k, metric=METRICS[distance])
 
 
 def snn(nn_idx, k=10, prune_snn=0.067, verbose=False, eng=None):

@@ -695,7 +695,7 @@ int adobo_lanczos_csr(adobo_ctx* c, int64_t rows, int32_t cols, const int64_t* i
   API_END
 }
 
-int adobo_knn(adobo_ctx* c, const double* comp, int64_t n, int32_t p, int32_t k, int64_t* out_idx) {
+int adobo_knn_metric(adobo_ctx* c, const double* comp, int64_t n, int32_t p, int32_t k, int32_t metric, int64_t* out_idx) {
   API_BEGIN
   CUDA_CHECK(cudaSetDevice(c->device));
   if (comp) {
@@ -703,13 +703,17 @@ int adobo_knn(adobo_ctx* c, const double* comp, int64_t n, int32_t p, int32_t k,
     DevBuf<double> x;
     x.ensure((size_t)n * p);
     CUDA_CHECK(cudaMemcpyAsync(x.p, comp, sizeof(double) * n * p, cudaMemcpyHostToDevice, c->stream));
-    run_knn(c, x.p, n, p, k);
+    run_knn(c, x.p, n, p, k, metric);
   } else {
     REQUIRE(c->have_pca, ADOBO_ERR_STATE, "Compute principal components first using adobo.dr.pca(...)");
-    run_knn(c, c->comp.p, c->n, c->p, k);
+    run_knn(c, c->comp.p, c->n, c->p, k, metric);
   }
   if (out_idx) nn_to_host(c, out_idx);
   API_END
+}
+
+int adobo_knn(adobo_ctx* c, const double* comp, int64_t n, int32_t p, int32_t k, int64_t* out_idx) {
+  return adobo_knn_metric(c, comp, n, p, k, ADOBO_METRIC_EUCLIDEAN, out_idx);
 }
 
 int adobo_upload_embedding(adobo_ctx* c, const double* comp, int64_t n, int32_t p) {

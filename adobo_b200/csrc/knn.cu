@@ -329,12 +329,133 @@ __global__ void __launch_bounds__(256) knn_exact_rows(const double* __restrict__
   }
 }
 
+
+// ---- 4. other ball-tree metrics (clustering.py:47-48 forwards `distance` to sklearn's ball tree) --------------------
+// Exact brute force in fp64 on the CUDA cores: 32 queries per CTA (four per warp), references streamed through a
+// transposed shared-memory tile (lane = reference, the query coordinate is a broadcast), coordinates accumulated in
+// index order like sklearn's DistanceMetric does, so the distances have the same bits.  Order: (distance, index),
+// the query itself first.  n^2 p fp64 operations: fine at 68 k cells (tens of ms), not the path for 1 M.
+constexpr int MQ = 32;   // queries per CTA
+constexpr int MQW = 4;   // queries per warp
+constexpr int MRT = 64;  // references per tile (two per lane)
+constexpr int MRS = MRT + 1;
+
+template <int METRIC>
+struct MetricAcc {
+  double a = 0, b = 0;
+  __device__ __forceinline__ void add(double x, double y) {
+    if (METRIC == ADOBO_METRIC_EUCLIDEAN) {
+      const double d = x - y;
+      a = fma(d, d, a);
+    } else if (METRIC == ADOBO_METRIC_MANHATTAN) {
+      a += fabs(x - y);
+    } else if (METRIC == ADOBO_METRIC_CHEBYSHEV) {
+      a = fmax(a, fabs(x - y));
+    } else if (METRIC == ADOBO_METRIC_HAMMING) {
+      a += (x != y) ? 1.0 : 0.0;
+    } else if (METRIC == ADOBO_METRIC_CANBERRA) {
+      const double den = fabs(x) + fabs(y);
+      if (den > 0) a += fabs(x - y) / den;
+    } else {  // Bray-Curtis as sklearn defines it: |x| + |y| in the denominator (scipy has |x + y|)
+      a += fabs(x - y);
+      b += fabs(x) + fabs(y);
+    }
+  }
+  __device__ __forceinline__ double value() const {
+    if (METRIC == ADOBO_METRIC_BRAYCURTIS) return b > 0 ? a / b : 0.0;
+    return a;  // squared (Euclidean) / un-normalised (Hamming): the order is the metric's
+  }
+};
+
+template <int METRIC>
+__global__ void __launch_bounds__(256) knn_metric_tile(const double* __restrict__ x, i64 n, int p, i64 q_begin,
+                                                       i64 n_local, int k, int* __restrict__ nn0) {
+  constexpr int E = 2;
+  extern __shared__ __align__(16) double km_dyn[];  // xq[MQ][p] | rt[p][MRS]
+  double* xq = km_dyn;
+  double* rt = km_dyn + (size_t)MQ * p;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const i64 ql0 = (i64)blockIdx.x * MQ;
+  for (int e = threadIdx.x; e < MQ * p; e += 256) {
+    const i64 ql = ql0 + e / p;
+    xq[e] = ql < n_local ? x[(q_begin + ql) * p + (e % p)] : 0.0;
+  }
+  double key[MQW][E];
+  int idx[MQW][E];
+#pragma unroll
+  for (int q = 0; q < MQW; ++q)
+#pragma unroll
+    for (int e = 0; e < E; ++e) key[q][e] = INFINITY, idx[q][e] = INT_MAX;
+  const double* myq = xq + (size_t)warp * MQW * p;
+  for (i64 base = 0; base < n; base += MRT) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < MRT * p; e += 256) {  // coalesced along the coordinates, transposed on the way in
+      const int i = e / p, t = e - i * p;
+      const i64 r = base + i;
+      rt[(size_t)t * MRS + i] = r < n ? x[r * p + t] : 0.0;
+    }
+    __syncthreads();
+    MetricAcc<METRIC> acc[MQW][2];
+    for (int t = 0; t < p; ++t) {
+      const double ra = rt[(size_t)t * MRS + lane], rb = rt[(size_t)t * MRS + lane + 32];
+#pragma unroll
+      for (int q = 0; q < MQW; ++q) {
+        const double qv = myq[(size_t)q * p + t];
+        acc[q][0].add(qv, ra);
+        acc[q][1].add(qv, rb);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < MQW; ++q) {
+      const i64 qg = q_begin + ql0 + warp * MQW + q;
+#pragma unroll
+      for (int hq = 0; hq < 2; ++hq) {
+        const i64 r = base + lane + 32 * hq;
+        double dd = r < n ? acc[q][hq].value() : INFINITY;
+        int ri = r < n ? (int)r : INT_MAX;
+        if (r == qg) ri = -1;  // the query itself wins a zero-distance tie
+        const double wk = __shfl_sync(0xffffffffu, key[q][E - 1], 31);
+        const int wi = __shfl_sync(0xffffffffu, idx[q][E - 1], 31);
+        unsigned m = __ballot_sync(0xffffffffu, cand_less(dd, ri, wk, wi));
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          const double nk = __shfl_sync(0xffffffffu, dd, src);
+          const int ni = __shfl_sync(0xffffffffu, ri, src);
+          list_insert<double, E>(key[q], idx[q], nk, ni, lane);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < MQW; ++q) {
+    const i64 ql = ql0 + warp * MQW + q;
+    if (ql >= n_local) continue;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int rank = lane * E + e;
+      if (rank < k) nn0[(size_t)ql * k + rank] = (idx[q][e] == -1) ? (int)(q_begin + ql) : idx[q][e];
+    }
+  }
+}
+
+template <int METRIC>
+static void launch_knn_metric(adobo_ctx* c, const double* x, i64 n, int p, i64 q_begin, i64 n_local, int k) {
+  const size_t smem = sizeof(double) * ((size_t)MQ * p + (size_t)p * MRS);
+  CUDA_CHECK(cudaFuncSetAttribute(knn_metric_tile<METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  WORK(c, (double)n_local * (double)n * p);
+  LAUNCH(c, "knn_metric_tile", (knn_metric_tile<METRIC><<<(unsigned)((n_local + MQ - 1) / MQ), 256, smem, c->stream>>>(
+                                   x, n, p, q_begin, n_local, k, c->nn.p)));
+}
+
 bool knn_tc_supported(int p);  // knn_tc.cu
 void run_knn_shortlist_tc(adobo_ctx* c, const double* x, i64 n, int p, const double* ctr, i64 q_begin, i64 q_end, int E,
                           float* skey, int* sidx, DevBuf<float>& norms, unsigned* maxnorm);
 
 // comp_local: this rank's rows (n_local x p, device, fp64).  Leaves c->nn (n_local x k, 0-based global ids).
-void run_knn(adobo_ctx* c, const double* comp_local, i64 n_local, int p, int k) {
+void run_knn(adobo_ctx* c, const double* comp_local, i64 n_local, int p, int k, int metric) {
+  REQUIRE(metric >= ADOBO_METRIC_EUCLIDEAN && metric <= ADOBO_METRIC_EUCLIDEAN_FP64, ADOBO_ERR_ARG, "knn: unknown metric %d",
+          metric);
   REQUIRE(p >= 1 && p <= MAXP, ADOBO_ERR_LIMIT, "knn: %d dimensions (supported: 1..%d)", p, MAXP);
   REQUIRE(k >= 1 && k <= 48, ADOBO_ERR_LIMIT, "knn: k=%d (supported: 1..48)", k);
   cudaStream_t st = c->stream;
@@ -357,6 +478,24 @@ void run_knn(adobo_ctx* c, const double* comp_local, i64 n_local, int p, int k) 
     for (int r = 0; r < c->world; ++r) bytes[r] = (size_t)all_n[r] * p * sizeof(double);
     allgatherv_bytes(c, comp_local, gathered.p, bytes);
     x = gathered.p;
+  }
+  if (metric != ADOBO_METRIC_EUCLIDEAN) {
+    c->nn.ensure((size_t)std::max<i64>(n_local, 1) * k);
+    c->k = k;
+    c->knn_n = n_local;
+    if (n_local > 0) {
+      switch (metric) {
+        case ADOBO_METRIC_MANHATTAN: launch_knn_metric<ADOBO_METRIC_MANHATTAN>(c, x, n, p, q_begin, n_local, k); break;
+        case ADOBO_METRIC_CHEBYSHEV: launch_knn_metric<ADOBO_METRIC_CHEBYSHEV>(c, x, n, p, q_begin, n_local, k); break;
+        case ADOBO_METRIC_HAMMING: launch_knn_metric<ADOBO_METRIC_HAMMING>(c, x, n, p, q_begin, n_local, k); break;
+        case ADOBO_METRIC_CANBERRA: launch_knn_metric<ADOBO_METRIC_CANBERRA>(c, x, n, p, q_begin, n_local, k); break;
+        case ADOBO_METRIC_BRAYCURTIS: launch_knn_metric<ADOBO_METRIC_BRAYCURTIS>(c, x, n, p, q_begin, n_local, k); break;
+        default: launch_knn_metric<ADOBO_METRIC_EUCLIDEAN>(c, x, n, p, q_begin, n_local, k); break;  // fp64 brute force
+      }
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    c->have_knn = true;
+    return;
   }
   const int P = (p + 3) & ~3;
   const i64 npad = (n + RT - 1) / RT * RT;

@@ -239,14 +239,14 @@ class Engine:
                                          v0, U, s, V, C.byref(steps), C.byref(nmult)))
         return LanczosResult(U=U, s=s, V=V, steps=steps.value, nmult=nmult.value)
 
-    def knn(self, comp=None, k=10, n_local=None, fetch=True):
+    def knn(self, comp=None, k=10, n_local=None, fetch=True, metric=0):
         if comp is not None:
             comp = np.ascontiguousarray(comp, dtype=np.float64)
             n, p = comp.shape
         else:
             n, p = (self.n if n_local is None else n_local), 0
         out = np.empty((n, k), dtype=np.int64) if fetch else None
-        check(self.lib.adobo_knn(self.h, comp, n, p, int(k), out))
+        check(self.lib.adobo_knn_metric(self.h, comp, n, p, int(k), int(metric), out))
         return out
 
     def upload_embedding(self, comp):

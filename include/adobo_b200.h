@@ -150,6 +150,21 @@ int64_t adobo_perm_row(int64_t n_cells, uint64_t perm_seed, int32_t col, int64_t
  * out_idx int64[n x k] (this rank's cells; indices are global). */
 int adobo_knn(adobo_ctx* ctx, const double* comp, int64_t n, int32_t p, int32_t k, int64_t* out_idx);
 
+/* The other metrics clustering.knn(distance=...) forwards to sklearn's ball tree (clustering.py:47-48): the same call
+ * with a metric code.  ADOBO_METRIC_EUCLIDEAN is adobo_knn itself (tensor-core shortlist + fp64 re-rank); the others
+ * are an exact fp64 brute force on the CUDA cores that accumulates the coordinates in index order like sklearn's
+ * DistanceMetric (same distances, bit for bit), ordered by (distance, index) with the query itself first.
+ * ADOBO_METRIC_EUCLIDEAN_FP64 is that brute force with squared differences (a cross-check of the tensor path). */
+#define ADOBO_METRIC_EUCLIDEAN 0      /* 'euclidean', 'l2', 'minkowski' (p = 2, the ball tree's default) */
+#define ADOBO_METRIC_MANHATTAN 1      /* 'manhattan', 'cityblock', 'l1' */
+#define ADOBO_METRIC_CHEBYSHEV 2      /* 'chebyshev', 'infinity' */
+#define ADOBO_METRIC_HAMMING 3        /* 'hamming' */
+#define ADOBO_METRIC_CANBERRA 4       /* 'canberra' */
+#define ADOBO_METRIC_BRAYCURTIS 5     /* 'braycurtis' */
+#define ADOBO_METRIC_EUCLIDEAN_FP64 6
+int adobo_knn_metric(adobo_ctx* ctx, const double* comp, int64_t n, int32_t p, int32_t k, int32_t metric,
+                     int64_t* out_idx);
+
 /* Leaves a caller-supplied embedding (this rank's cells, float64 [n x p] row-major) on the device as if adobo_irlb had
  * produced it: adobo_knn(ctx, NULL, ...) then runs on it (obj.norm_data[..]['dr']['pca']['comp'] of an earlier
  * session, clustering.py:337-341; the kNN / SNN sweep of bench.py). */

@@ -334,6 +334,67 @@ def knn(comp, k=10, block=256, return_dist=False):
     return idx + 1
 
 
+def knn_metric(comp, k=10, distance='manhattan'):
+    """clustering.knn with another ball-tree metric (clustering.py:47-48 forwards `distance` to
+    sklearn.neighbors.NearestNeighbors(algorithm='ball_tree', metric=distance)).  Restates the parameter-free metrics
+    of scikit-learn 1.9.0's DistanceMetric (sklearn/metrics/_dist_metrics.pyx.tp: ManhattanDistance sum |x - y|,
+    ChebyshevDistance max |x - y|, HammingDistance mean(x != y), CanberraDistance sum |x - y| / (|x| + |y|) skipping
+    0 / 0, BrayCurtisDistance sum |x - y| / sum (|x| + |y|) -- not scipy's |x + y|), coordinates accumulated in index order, every pair, ties
+    by index with the point itself first.  1-based like the reference.  Pinned against the ball tree itself by
+    tests/test_oracle_golden.py::test_knn_metric_is_the_ball_tree."""
+    x = np.ascontiguousarray(np.asarray(comp, dtype=np.float64))
+    n, p = x.shape
+    out = np.empty((n, k), dtype=np.int64)
+    ids = np.arange(n)
+    for i in range(n):
+        d = np.zeros(n)
+        den = np.zeros(n)
+        for t in range(p):                                   # index order: the same rounding as the metric's loop
+            a = np.abs(x[i, t] - x[:, t])
+            if distance in ('manhattan', 'cityblock', 'l1'):
+                d += a
+            elif distance in ('chebyshev', 'infinity'):
+                d = np.maximum(d, a)
+            elif distance == 'hamming':
+                d += (x[i, t] != x[:, t])
+            elif distance == 'canberra':
+                q = np.abs(x[i, t]) + np.abs(x[:, t])
+                d += np.divide(a, q, out=np.zeros(n), where=q > 0)
+            elif distance == 'braycurtis':
+                d += a
+                den += np.abs(x[i, t]) + np.abs(x[:, t])
+            elif distance in ('euclidean', 'l2', 'minkowski'):
+                d += a * a
+            else:
+                raise ValueError("Unrecognized metric '%s'" % distance)
+        if distance == 'braycurtis':
+            d = np.divide(d, den, out=np.zeros(n), where=den > 0)
+        key = ids.copy()
+        key[i] = -1
+        out[i] = ids[np.lexsort((key, d))[:k]]
+    return out + 1
+
+
+def metric_dist_rows(comp, rows, idx1, distance):
+    """Distances (same definitions as knn_metric, up to the monotone final step) of x[rows] to x[idx1 - 1]."""
+    x = np.asarray(comp, dtype=np.float64)
+    a = x[rows][:, None, :]
+    b = x[np.asarray(idx1) - 1]
+    if distance in ('manhattan', 'cityblock', 'l1'):
+        return np.abs(a - b).sum(axis=2)
+    if distance in ('chebyshev', 'infinity'):
+        return np.abs(a - b).max(axis=2)
+    if distance == 'hamming':
+        return (a != b).sum(axis=2).astype(np.float64)
+    if distance == 'canberra':
+        q = np.abs(a) + np.abs(b)
+        return np.divide(np.abs(a - b), q, out=np.zeros(q.shape), where=q > 0).sum(axis=2)
+    if distance == 'braycurtis':
+        den = (np.abs(a) + np.abs(b)).sum(axis=2)
+        return np.divide(np.abs(a - b).sum(axis=2), den, out=np.zeros(den.shape), where=den > 0)
+    return ((a - b) ** 2).sum(axis=2)
+
+
 def knn_direct(comp, k=10):
     """Small-case cross-check of knn(): every pair by direct differences."""
     x = np.asarray(comp, dtype=np.float64)

@@ -97,9 +97,11 @@ def knn_dist(comp, idx1):
     return np.einsum('ijk,ijk->ij', d, d)
 
 
-def assert_knn_equal(ours, ref, comp, rtol=1e-12):
+def assert_knn_equal(ours, ref, comp, rtol=1e-12, dist_rows=None):
     """1-based (n, k) index arrays; mismatches allowed only where the distance at that rank is
-    the same (documented tie).  Returns the number of tied mismatches."""
+    the same (documented tie).  Returns the number of tied mismatches.  dist_rows(x, rows, idx1):
+    the metric (default: squared Euclidean)."""
+    dist_rows = dist_rows or knn_dist_rows
     ours, ref = np.asarray(ours, dtype=np.int64), np.asarray(ref, dtype=np.int64)
     assert ours.shape == ref.shape
     mism = ours != ref
@@ -107,8 +109,8 @@ def assert_knn_equal(ours, ref, comp, rtol=1e-12):
         return 0
     rows = np.flatnonzero(mism.any(axis=1))
     x = np.asarray(comp, dtype=np.float64)
-    do = knn_dist_rows(x, rows, ours[rows])
-    dr = knn_dist_rows(x, rows, ref[rows])
+    do = dist_rows(x, rows, ours[rows])
+    dr = dist_rows(x, rows, ref[rows])
     scale = np.maximum(dr, 1e-300)
     ok = np.abs(do - dr) <= rtol * scale + 1e-300
     assert np.all(ok | ~mism[rows]), 'kNN mismatch that is not a distance tie in rows %s' % rows[(~ok & mism[rows]).any(axis=1)][:10]

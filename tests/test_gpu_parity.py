@@ -129,6 +129,37 @@ def test_knn_duplicates_and_tiny(eng):
     P.assert_knn_equal(eng.knn(y, 12), O.knn(y, 12), y)                   # k == n, n < one tile
 
 
+@pytest.mark.parametrize('distance', ['manhattan', 'chebyshev', 'hamming', 'canberra', 'braycurtis'])
+def test_knn_other_metrics(eng, distance):
+    """clustering.knn(distance=...) (clustering.py:47-48): the fp64 brute-force kernel against the oracle's restatement
+    of sklearn's metrics (itself pinned to the ball tree on the CPU), duplicates and a ragged last tile included."""
+    from functools import partial
+    from oracle import adobo_oracle as O
+    from adobo_b200 import clustering
+    rng = np.random.default_rng(13)
+    x = rng.normal(size=(1237, 23))
+    if distance == 'hamming':
+        x = np.round(x)
+    x[500:540] = x[500]
+    for k in (10, 33):
+        nn = clustering.knn(x, k, distance, eng=eng)
+        assert nn.dtype == np.int64 and nn.shape == (1237, k)
+        P.assert_knn_equal(nn, O.knn_metric(x, k, distance), x, dist_rows=partial(O.metric_dist_rows, distance=distance))
+        assert np.array_equal(nn[:, 0], np.arange(1, 1238))               # self first
+    with pytest.raises(ValueError):
+        clustering.knn(x, 10, 'mahalanobis', eng=eng)
+
+
+def test_knn_fp64_brute_force_is_the_tensor_path(eng):
+    """ADOBO_METRIC_EUCLIDEAN_FP64 (the brute-force kernel with squared differences) and the tcgen05 shortlist + fp64
+    re-rank give the same neighbours."""
+    from adobo_b200.synth import synth_embedding
+    x = synth_embedding(5000, 50, seed=3)
+    a = eng.knn(x, 20)
+    b = eng.knn(x, 20, metric=6)
+    P.assert_knn_equal(a, b, x)
+
+
 def test_snn_edges_bit_exact(eng, case):
     edges, pruned, total, ne = eng.snn(case['nn_idx'], case['k'], 0.067)
     assert np.array_equal(P.edges_sorted(edges), case['edges'])

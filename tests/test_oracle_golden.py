@@ -64,3 +64,22 @@ def test_formula_kat_from_notebook():
     counts = sp.csr_matrix(np.array([[1, 2, lib - 3]], dtype=np.int64))
     norm, _ = O.normalize_standard(counts)
     assert abs(norm.data[0] - y1) < 2e-5 and abs(norm.data[1] - y2) < 2e-5
+
+
+@pytest.mark.parametrize('distance', ['manhattan', 'chebyshev', 'canberra', 'braycurtis', 'hamming', 'l1', 'infinity',
+                                      'minkowski'])
+def test_knn_metric_is_the_ball_tree(distance):
+    """oracle.knn_metric restates sklearn's metrics: the reference's own call (clustering.py:47-50) on the same
+    points gives the same neighbours (up to ties in the metric)."""
+    from functools import partial
+    from sklearn.neighbors import NearestNeighbors
+    rng = np.random.default_rng(11)
+    x = rng.normal(size=(300, 7))
+    if distance == 'hamming':
+        x = np.round(x)                                      # coordinates that can be equal
+    x[40:44] = x[40]                                         # duplicate cells
+    ref = NearestNeighbors(n_neighbors=9, algorithm='ball_tree', metric=distance).fit(x).kneighbors(x)[1] + 1
+    ours = O.knn_metric(x, 9, distance)
+    tied = P.assert_knn_equal(ours, ref, x, dist_rows=partial(O.metric_dist_rows, distance=distance))
+    if distance != 'hamming':
+        assert tied <= 100                                   # of 2700 entries: only around the duplicate cells
