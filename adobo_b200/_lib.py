@@ -66,6 +66,7 @@ SIGNATURES = {
     'adobo_synth_counts': (C.c_int, [ctx_p, C.c_int64, C.c_int32, C.c_int64, C.c_uint64, _arr(_f32, 2), C.c_int32,
                                      C.POINTER(C.c_int64)]),
     'adobo_download_counts': (C.c_int, [ctx_p, _OptArr(_i64), _OptArr(_i32), _OptArr(_i32)]),
+    'adobo_count_stats': (C.c_int, [ctx_p, _OptArr(_i64), _OptArr(_i64), _OptArr(_i64)]),
     'adobo_normalize': (C.c_int, [ctx_p, C.c_double, C.c_int, C.c_double, _OptArr(_i64), _OptArr(_f64)]),
     'adobo_gene_moments': (C.c_int, [ctx_p, _OptArr(_f64), _OptArr(_f64)]),
     'adobo_hvg_seurat': (C.c_int, [ctx_p, C.c_int32, C.c_int32, _OptArr(_i32), C.POINTER(C.c_int32), _OptArr(_f64)]),

@@ -588,6 +588,21 @@ int adobo_normalize(adobo_ctx* c, double scaling_factor, int log_mode, double sm
   API_END
 }
 
+int adobo_count_stats(adobo_ctx* c, int64_t* out_total_reads, int64_t* out_detected_genes, int64_t* out_expressed) {
+  API_BEGIN
+  CUDA_CHECK(cudaSetDevice(c->device));
+  run_count_stats(c, (i64*)out_total_reads, (i64*)out_detected_genes, (i64*)out_expressed);
+  if (c->world > 1 && out_expressed) {  // cells are sharded: the per-gene counts are sums over the ranks
+    DevBuf<i64> e;
+    e.ensure((size_t)std::max<i64>(c->g, 1));
+    CUDA_CHECK(cudaMemcpyAsync(e.p, out_expressed, sizeof(i64) * c->g, cudaMemcpyHostToDevice, c->stream));
+    allreduce_sum_i64(c, e.p, (size_t)c->g);
+    CUDA_CHECK(cudaMemcpyAsync(out_expressed, e.p, sizeof(i64) * c->g, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  }
+  API_END
+}
+
 int adobo_gene_moments(adobo_ctx* c, double* out_mean, double* out_var) {
   API_BEGIN
   CUDA_CHECK(cudaSetDevice(c->device));

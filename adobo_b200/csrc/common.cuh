@@ -279,6 +279,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu_dev, const
 template <typename VT>
 void build_csc(adobo_ctx* c, SparsePair<VT>& A);
 
+void run_count_stats(adobo_ctx* c, i64* out_total, i64* out_detected, i64* out_expressed);
 void run_knn(adobo_ctx* c, const double* comp_dev_local, i64 n_local, int p, int k, int metric = 0);
 void run_snn(adobo_ctx* c, const int* nn_dev_all, i64 n_all, i64 row_begin, i64 row_end, int k, double prune,
              i64* n_edges, i64* pruned, i64* total);

@@ -143,6 +143,58 @@ void run_normalize(adobo_ctx* c, double scaling, int log_mode, double small_cons
   if (out_lib || out_vals) CUDA_CHECK(cudaStreamSynchronize(c->stream));
 }
 
+// ---- dataset metadata (data.py:75-84): reads per cell, detected genes per cell, expressing cells per gene ------------
+// warp per cell, 128-bit loads where the row is aligned; the per-gene counts are integer REDs (order independent).
+__global__ void __launch_bounds__(256) csr_count_stats(const i64* __restrict__ indptr, const int* __restrict__ indices,
+                                                       const int* __restrict__ counts, i64 n, i64* __restrict__ total,
+                                                       i64* __restrict__ detected, int* __restrict__ expressed) {
+  const int lane = threadIdx.x & 31;
+  const i64 nw = ((i64)gridDim.x * blockDim.x) >> 5;
+  for (i64 r = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += nw) {
+    const i64 b = indptr[r], e = indptr[r + 1];
+    i64 s = 0;
+    int d = 0;
+    for (i64 i = b + lane; i < e; i += 32) {
+      const int v = __ldg(counts + i);
+      s += v;
+      if (v > 0) {
+        ++d;
+        atomicAdd(expressed + __ldg(indices + i), 1);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      d += __shfl_xor_sync(0xffffffffu, d, o);
+    }
+    if (lane == 0) total[r] = s, detected[r] = d;
+  }
+}
+
+void run_count_stats(adobo_ctx* c, i64* out_total, i64* out_detected, i64* out_expressed) {
+  REQUIRE(c->have_counts, ADOBO_ERR_STATE, "adobo_count_stats: no count matrix on the device");
+  DevBuf<i64> tot, det;
+  DevBuf<int> expr;
+  tot.ensure((size_t)std::max<i64>(c->n, 1));
+  det.ensure((size_t)std::max<i64>(c->n, 1));
+  expr.ensure((size_t)std::max<i64>(c->g, 1));
+  CUDA_CHECK(cudaMemsetAsync(expr.p, 0, sizeof(int) * std::max<i64>(c->g, 1), c->stream));
+  if (c->n > 0) {
+    const i64 blocks = std::max<i64>(1, std::min<i64>((c->n + 7) / 8, (i64)c->sm_count * 8));
+    WORK(c, 8.0 * (double)c->nnz + 24.0 * c->n);
+    LAUNCH(c, "csr_count_stats", (csr_count_stats<<<(unsigned)blocks, 256, 0, c->stream>>>(
+                                     c->indptr.p, c->indices.p, c->counts.p, c->n, tot.p, det.p, expr.p)));
+  }
+  std::vector<int> he((size_t)c->g);
+  if (out_total) CUDA_CHECK(cudaMemcpyAsync(out_total, tot.p, sizeof(i64) * c->n, cudaMemcpyDeviceToHost, c->stream));
+  if (out_detected) CUDA_CHECK(cudaMemcpyAsync(out_detected, det.p, sizeof(i64) * c->n, cudaMemcpyDeviceToHost, c->stream));
+  if (out_expressed && c->g > 0)
+    CUDA_CHECK(cudaMemcpyAsync(he.data(), expr.p, sizeof(int) * c->g, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (out_expressed)
+    for (i64 j = 0; j < c->g; ++j) out_expressed[j] = he[(size_t)j];
+}
+
 void upload_normalized_values(adobo_ctx* c, const double* values) {
   DevBuf<double> tmp;
   tmp.ensure((size_t)c->nnz);

@@ -19,12 +19,18 @@ class CsrFrame:
     `transpose()` -- and converts to the real thing with `to_frame()` when the matrix is small enough to want one."""
 
     def __init__(self, csr, genes, cells):
-        self.csr = sp.csr_matrix(csr)
-        if not self.csr.has_sorted_indices:
-            self.csr.sort_indices()
+        # an existing CSR object is kept as it is: scipy caches has_sorted_indices on the object, and the check is a
+        # pass over all non-zeros (35 ms at 70 M) that a fresh wrapper object would repeat
+        self._csr = csr if isinstance(csr, sp.csr_matrix) else sp.csr_matrix(csr)
+        if not self._csr.has_sorted_indices:
+            self._csr.sort_indices()
         self.index = pd.Index(genes)
         self.columns = pd.Index(cells)
-        assert self.csr.shape == (len(self.columns), len(self.index)), 'CSR is cells x genes'
+        assert self._csr.shape == (len(self.columns), len(self.index)), 'CSR is cells x genes'
+
+    @property
+    def csr(self):
+        return self._csr
 
     @property
     def shape(self):
@@ -70,6 +76,51 @@ class CsrFrame:
         return 'CsrFrame(%d genes x %d cells, %d non-zeros, %s)' % (self.shape + (self.csr.nnz, self.csr.dtype))
 
 
+class DeviceCsrFrame(CsrFrame):
+    """The normalized matrix of normalize.norm on a CsrFrame-backed dataset: labels on the host, VALUES LEFT ON THE
+    DEVICE where find_hvg / pca / generate consume them (the resident matrix; normalize.ResidentKey).  The host copy
+    -- 8 bytes per non-zero, 0.56 GB at 68 k cells, more than the rest of the call sequence together -- is made when
+    `.csr` is first read, or, at the latest, when the engine is about to replace its resident matrix (Engine._evict),
+    so the frame never loses its data.  Values are the fp64 ones adobo_normalize delivers (the kernel is re-run on the
+    resident counts with the same parameters)."""
+
+    def __init__(self, eng, params, genes, cells):
+        import weakref
+        self._csr = None
+        self._eng = eng
+        self._params = params                            # (scaling_factor, log mode, small_const)
+        self._shape_csr = (len(cells), len(genes))
+        self.nnz = eng.nnz
+        self.index = pd.Index(genes)
+        self.columns = pd.Index(cells)
+        eng._lazy = [r for r in eng._lazy if r() is not None] + [weakref.ref(self)]
+
+    @property
+    def materialized(self):
+        return self._csr is not None
+
+    def materialize(self):
+        if self._csr is None:
+            eng, self._eng = self._eng, None
+            if eng is None or eng.h is None:
+                raise Exception('DeviceCsrFrame: the engine that held the normalized values was closed')
+            from .normalize import ResidentKey
+            key = eng.resident_key
+            mine = isinstance(key, ResidentKey) and key.matches(self)
+            self._csr, _ = eng.normalize(*self._params)  # re-runs K1 on the resident counts: the device values are now these
+            eng.resident_key = ResidentKey(self) if mine else None
+            eng._lazy = [r for r in eng._lazy if r() is not None and r() is not self]
+        return self._csr
+
+    @property
+    def csr(self):
+        return self.materialize()
+
+    def __repr__(self):
+        return 'DeviceCsrFrame(%d genes x %d cells, %d non-zeros, %s)' % (
+            self.shape + (self.nnz, 'on the host' if self.materialized else 'values on the device'))
+
+
 def _row_sums(csr):
     """Row sums of a CSR matrix in int64 / float64 without the dtype-converted copy of `data` that scipy's sum makes
     (0.2 s at 70 M non-zeros): one reduceat over the row starts, empty rows set to zero afterwards."""
@@ -84,7 +135,12 @@ def _row_sums(csr):
 
 
 class dataset:
-    def __init__(self, raw_mat, desc='no desc set', output_file=None, input_file=None, sparse=True, verbose=False):
+    def __init__(self, raw_mat, desc='no desc set', output_file=None, input_file=None, sparse=True, verbose=False,
+                 eng=None):
+        """adobo.data.dataset (data.py:54-93).  `eng` (extension; default: the process-wide engine IF one exists):
+        for a CsrFrame-backed dataset the counts are uploaded once, here, and the summary statistics come from the
+        device (adobo_count_stats); normalize.norm then finds the counts resident.  Without an engine, and for pandas
+        frames, the statistics are computed on the host like the reference does."""
         self.sparse = sparse
         self.desc = desc
         self.output_file = output_file
@@ -99,13 +155,24 @@ class dataset:
         self.imp_count_data = pd.DataFrame()
         self._norm_data = {}
         csr = frame_to_csr(self.count_data)                                  # cells x genes
+        if eng is None and isinstance(raw_mat, CsrFrame):
+            from . import engine as _engine
+            eng = _engine._default
+        if eng is not None and isinstance(raw_mat, CsrFrame) and eng.world == 1:
+            from .normalize import ResidentKey
+            eng.upload_counts(csr, key=ResidentKey(raw_mat))
+            total, detected, expressed = eng.count_stats()
+        else:
+            total = _row_sums(csr)
+            allpos = csr.nnz == 0 or csr.data.min() > 0
+            detected = np.diff(csr.indptr) if allpos else _row_sums(sp.csr_matrix(
+                ((csr.data > 0).astype(np.int64), csr.indices, csr.indptr), shape=csr.shape))
+            expressed = np.bincount(csr.indices if allpos else csr.indices[csr.data > 0], minlength=raw_mat.shape[0])
         self.meta_cells = pd.DataFrame(index=raw_mat.columns)                # data.py:75-78
-        self.meta_cells['total_reads'] = _row_sums(csr)
+        self.meta_cells['total_reads'] = total
         self.meta_cells['status'] = ['OK'] * raw_mat.shape[1]
-        self.meta_cells['detected_genes'] = np.diff(csr.indptr)
+        self.meta_cells['detected_genes'] = detected
         self.meta_genes = pd.DataFrame(index=raw_mat.index)                  # data.py:80-89
-        pos = csr.data > 0
-        expressed = np.bincount(csr.indices if pos.all() else csr.indices[pos], minlength=raw_mat.shape[0])
         self.meta_genes['expressed'] = expressed
         self.meta_genes['expressed_perc'] = expressed / raw_mat.shape[1] * 100
         self.meta_genes['status'] = ['OK'] * raw_mat.shape[0]
@@ -118,7 +185,8 @@ class dataset:
         """counts: scipy CSR cells x genes.  frame=True builds the pandas sparse frame the reference holds
         (data.py:67); frame=False keeps the matrix as a CsrFrame -- no per-cell pandas objects, the only way to hold
         BASELINE's 68 k- and 1.3 M-cell shapes; 'auto' = a pandas frame up to 10,000 cells."""
-        counts = sp.csr_matrix(counts)
+        if not isinstance(counts, sp.csr_matrix):
+            counts = sp.csr_matrix(counts)
         genes = genes if genes is not None else ['g%d' % i for i in range(counts.shape[1])]
         cells = cells if cells is not None else ['c%d' % i for i in range(counts.shape[0])]
         if frame == 'auto':

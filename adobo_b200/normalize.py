@@ -10,7 +10,7 @@ import numpy as np
 import pandas as pd
 
 from . import engine as _engine
-from .data import frame_to_csr, csr_to_frame, CsrFrame
+from .data import frame_to_csr, csr_to_frame, CsrFrame, DeviceCsrFrame
 
 _LOG_MODES = {np.log2: (_engine.LOG_2, 0.0), np.log: (_engine.LOG_E, 0.0), np.log10: (_engine.LOG_10, 0.0),
               np.log1p: (_engine.LOG_E, 1.0)}
@@ -79,10 +79,19 @@ def norm(obj, method='standard', name=None, use_imputed=False, log=True, log_fun
         raise Exception('Unknown normalization method.')
     mode, sc = _log_mode(log, log_func, small_const)
     eng = eng or _engine.default_engine()
-    counts = frame_to_csr(data)
-    eng.upload_counts(counts)
-    vals, _ = eng.normalize(scaling_factor, mode, sc)
-    normf = csr_to_frame(vals, data.index, data.columns, like=data)
+    ck = eng.counts_key
+    if not (isinstance(ck, ResidentKey) and ck.matches(data)):      # dataset(..., eng) left these counts on the device
+        eng.upload_counts(frame_to_csr(data), key=ResidentKey(data) if isinstance(data, CsrFrame) else None)
+    if isinstance(data, CsrFrame):
+        # no pandas frame on this path: the values stay where find_hvg / pca / generate read them (DeviceCsrFrame);
+        # library sizes only come back
+        ck = eng.counts_key
+        eng.normalize(scaling_factor, mode, sc, want_values=False)
+        eng.counts_key = ck
+        normf = DeviceCsrFrame(eng, (scaling_factor, mode, sc), data.index, data.columns)
+    else:
+        vals, _ = eng.normalize(scaling_factor, mode, sc)
+        normf = csr_to_frame(vals, data.index, data.columns, like=data)
     ne = None
     ercc = obj.meta_genes.ERCC.reindex(normf.index)
     if np.any(ercc == True):  # noqa: E712             # normalize.py:562-566
@@ -119,6 +128,8 @@ class ResidentKey:
 
 
 def _fingerprint(df):
+    if isinstance(df, DeviceCsrFrame) and not df.materialized:
+        return ('device', df.shape, df.nnz)              # nothing on the host that could have been edited
     if isinstance(df, CsrFrame):
         m = df.csr
         pos = np.linspace(0, max(m.nnz - 1, 0), num=min(m.nnz, 64), dtype=np.int64)

@@ -444,7 +444,8 @@ def main():
             api = {'value': n_total / api_s[-1], 'unit': 'cells/s', 'ms': api_s[-1] * 1e3, 'first_call_ms': api_s[0] * 1e3,
                    'edges': int(n_api_edges),
                    'path': 'dataset.from_csr(frame=False) -> normalize.norm -> hvg.find_hvg -> dr.pca -> clustering.generate'
-                           '(clust_alg=None): host CSR in, norm_data entries out'}
+                           '(clust_alg=None): host CSR in, norm_data entries out (PCA frames, edge frame; the normalized '
+                           'matrix is a DeviceCsrFrame: labels on the host, values left on the device until read)'}
         except Exception as ex:  # the figure is informative; the contract keys above do not depend on it
             api = {'error': '%s: %s' % (type(ex).__name__, ex)}
 
@@ -499,8 +500,8 @@ def main():
 
     roof = roofline_of(kernels[0])
     roof['event_overhead_us'] = event_overhead_us
-    shown = ('csr_libsize_scale_log', 'csr_gene_moments', 'w_step_t', 'v_step_t', 'w_step', 'spmvT_csc', 'v_step',
-             'rotate_basis', 'knn_scores_tc', 'snn_rows')
+    shown = ('csr_libsize_scale_log', 'csr_gene_moments', 'gene_moments_tiles', 'w_step_t', 'v_step_t', 'w_step', 'spmvT_csc',
+             'v_step', 'rotate_basis', 'rotate_mma', 'knn_scores_tc', 'snn_rows')
     rooflines = [roofline_of(kd) for kd in kernels if kd['kernel'] in shown]
 
     # ---------------- CPU baseline + parity (rank 0, N=1) ----------------

@@ -92,6 +92,12 @@ int adobo_synth_counts(adobo_ctx* ctx, int64_t n_rows, int32_t n_genes, int64_t 
                        const float* lam_table, int32_t n_clusters, int64_t* out_nnz);
 int adobo_download_counts(adobo_ctx* ctx, int64_t* indptr, int32_t* indices, int32_t* counts);
 
+/* The summary statistics adobo.data.dataset computes when it is constructed (adobo/data.py:75-84), from the resident
+ * count matrix: total_reads[n] = raw_mat.sum(axis=0), detected_genes[n] = (raw_mat > 0).sum(axis=0) per cell (this
+ * rank's cells), expressed[g] = number of cells with a positive count per gene (summed over all ranks).  Integers:
+ * exact and order independent.  Any output may be NULL. */
+int adobo_count_stats(adobo_ctx* ctx, int64_t* out_total_reads, int64_t* out_detected_genes, int64_t* out_expressed);
+
 /* ---- normalize.standard + log step (adobo/normalize.py:285-287, 559-560) ------------------- */
 /* y = log_f((c / S_cell) * scaling_factor + small_const) on the non-zeros; zeros stay zero.
  * out_libsize int64[n] and out_values float64[nnz] may be NULL (device-resident use). */

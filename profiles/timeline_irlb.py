@@ -7,10 +7,19 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from adobo_b200.engine import Engine
 from adobo_b200.synth import synth_counts
 
-cells = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 eng = Engine(0)
-counts = synth_counts(cells, 3000, 0.05, 77)
-eng.upload_counts(counts)
+if len(sys.argv) > 1 and sys.argv[1] in ('c2', 'c3'):        # a bench.py configuration, generated on the device
+    import bench
+    from adobo_b200.synth import CountModel
+    cfg = bench.CONFIGS[sys.argv[1]]
+    if cfg['gen'] == 'host':
+        eng.upload_counts(synth_counts(cfg['cells'], cfg['genes'], cfg['density'], cfg['seed']))
+    else:
+        eng.synth_counts(CountModel(cfg['genes'], cfg['density'], cfg['seed']), 0, cfg['cells'])
+else:
+    cells = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+    counts = synth_counts(cells, 3000, 0.05, 77)
+    eng.upload_counts(counts)
 np.random.seed(42)
 v0 = np.random.randn(1000)
 for rep in range(2):

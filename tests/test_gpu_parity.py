@@ -322,6 +322,54 @@ def test_api_on_csr_backed_dataset(eng):
     assert list(g2) != list(g1)                     # other values: other dispersions, other ranking
 
 
+def test_device_metadata_and_lazy_normalized_frame(eng):
+    """A CsrFrame-backed dataset made while an engine exists: counts uploaded once, data.py:75-84's statistics from
+    the device (adobo_count_stats) equal the host ones; norm() leaves the values on the device (DeviceCsrFrame) and
+    they reach the host intact on first use, or when another matrix is about to replace the resident one."""
+    import adobo_b200 as ad
+    from adobo_b200 import engine as E
+    from adobo_b200.data import DeviceCsrFrame
+    case = P.load_case('medium')
+    counts = case['counts_csr'].copy()
+    counts.data[::97] = 0                                   # explicit zeros: not 'detected', not 'expressed'
+    E.set_default_engine(None)
+    host = ad.data.dataset.from_csr(counts, frame=False)    # no engine: host statistics
+    E.set_default_engine(eng)
+    dev = ad.data.dataset.from_csr(counts, frame=False)
+    for col in ('total_reads', 'detected_genes'):
+        assert np.array_equal(host.meta_cells[col].values, dev.meta_cells[col].values), col
+    assert np.array_equal(host.meta_genes['expressed'].values, dev.meta_genes['expressed'].values)
+    dense = np.asarray(counts.todense())
+    assert np.array_equal(dev.meta_cells['detected_genes'].values, (dense > 0).sum(axis=1))      # data.py:78
+    assert np.array_equal(dev.meta_genes['expressed'].values, (dense > 0).sum(axis=0))           # data.py:83-84
+    l0 = eng.launch_count()
+    ad.normalize.norm(dev)
+    ad.normalize.norm(dev, name='nolog', log=False)         # a second normalization of the same resident counts
+    d1, d2 = dev.norm_data['standard']['data'], dev.norm_data['nolog']['data']
+    assert isinstance(d1, DeviceCsrFrame) and not d1.materialized and not d2.materialized
+    ad.hvg.find_hvg(dev, normalization='nolog', ngenes=200)
+    ref1, _ = _eager_norm(eng.__class__, counts, 1)
+    ref2, _ = _eager_norm(eng.__class__, counts, 0)
+    # another dataset takes the device: both lazy frames are brought to the host first
+    other = ad.data.dataset.from_csr(case['counts_csr'][:500], frame=False)
+    assert d1.materialized and d2.materialized
+    assert np.array_equal(d1.csr.data, ref1.data) and np.array_equal(d2.csr.data, ref2.data)
+    assert np.array_equal(d1.csr.indices, counts.indices)
+    hv = list(dev.norm_data['nolog']['hvg']['genes'])
+    ad.hvg.find_hvg(dev, normalization='nolog', ngenes=200)  # re-uploaded from the host copy: same list
+    assert list(dev.norm_data['nolog']['hvg']['genes']) == hv
+    del other
+    assert eng.launch_count() > l0
+
+
+def _eager_norm(engine_cls, counts, log_mode):
+    e = engine_cls(0)
+    e.upload_counts(counts)
+    out = e.normalize(10000, log_mode, 1.0)
+    e.close()
+    return out
+
+
 def test_snn_counts_are_the_reference_matrix_entries(eng):
     """north_star: 'SNN edge weights bit-exact' -- V_ij = (M M^T)_ij of every kept edge against the oracle's sparse
     product (the reference computes V and keeps only its coordinates, clustering.py:99-112)."""
