@@ -279,6 +279,14 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu_dev, const
 template <typename VT>
 void build_csc(adobo_ctx* c, SparsePair<VT>& A);
 
+// B[m-1][m-1] = ||y|| of an outer iteration's last W column for svd_arrow, which then does not wait for w_finish_t:
+// from w_step_t's per-CTA partials (one GPU; column col0 of [nblk][stride], summed exactly as w_finish_t sums it --
+// sum_partials_two in irlb.cu -- so both get the same bits) or from the pair w_norm_exchange left (several GPUs).
+struct LastDiag {
+  const double* parts = nullptr;
+  int nblk = 0, col0 = 0, stride = 0;
+  const double* n2p = nullptr;
+};
 void run_count_stats(adobo_ctx* c, i64* out_total, i64* out_detected, i64* out_expressed);
 void run_knn(adobo_ctx* c, const double* comp_dev_local, i64 n_local, int p, int k, int metric = 0);
 void run_snn(adobo_ctx* c, const int* nn_dev_all, i64 n_all, i64 row_begin, i64 row_end, int k, double prune,

@@ -18,6 +18,8 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace adobo {
@@ -27,7 +29,7 @@ namespace cg = cooperative_groups;
 bool svd_arrow_supported(int m, int k);
 void svd_arrow_prepare(int m);
 void launch_svd_arrow(adobo_ctx* c, const double* B, int m, int k, double* Su, double* sv, double* Sv, int* info,
-                      cudaStream_t st);
+                      cudaStream_t st, LastDiag ldg = LastDiag());
 int svd_arrow_cluster();
 
 enum { SC_S = 0, SC_FN, SC_FNINV, SC_SU, SC_MVS, SC_SMAX, SC_NRM2, SC_AUX, SC_COUNT = 16 };
@@ -1604,10 +1606,29 @@ static jacobi_fn jacobi_for(int m) {
 // info[5] = outer iterations completed.  `force`: run although the halt flag is set (host fallback path).
 // With St != nullptr all CTAs also lay out the two rotation matrices of the coming restart (transpose_s, for
 // the k this kernel has just decided), so the restart starts with the rotation itself.
+// The host reads info without a copy node or an event in the stream: thread 0 of CTA 0 publishes the words the host
+// needs into the context's page-locked mailbox (device-visible host memory).  Every word travels as ONE 8-byte store
+// {value, version} -- the version (info[7], advanced per publication) makes the set self-validating, so no system
+// fence sits in the kernel (two fences were 2 us of conv_check): the reader takes the five words when their versions
+// agree.  A D2H copy node + event record between two iteration graphs cost ~8 us per restart at 68 k cells.
+constexpr int INFO_PUB = 5;
+__constant__ int info_pub_field[INFO_PUB] = {0, 1, 4, 5, 6};
+__device__ __forceinline__ void publish_info(int* __restrict__ info, unsigned long long* __restrict__ hinfo) {
+  if (hinfo == nullptr) return;
+  const unsigned ver = (unsigned)info[7] + 1u;
+#pragma unroll
+  for (int i = 0; i < INFO_PUB; ++i) {
+    const unsigned long long w = ((unsigned long long)ver << 32) | (unsigned)info[info_pub_field[i]];
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(hinfo + i), "l"(w) : "memory");
+  }
+  info[7] = (int)ver;
+}
+
 __global__ void conv_check(const double* __restrict__ Su, const double* __restrict__ sv, double* __restrict__ sc,
                            int m, int nu, int k, int it, double tol, double* __restrict__ R, int* __restrict__ info,
                            int honour_flag, int force, const double* __restrict__ Sv, double* __restrict__ St,
-                           const double* __restrict__ cvec, const double* __restrict__ sumW, double* __restrict__ crot) {
+                           const double* __restrict__ cvec, const double* __restrict__ sumW, double* __restrict__ crot,
+                           unsigned long long* __restrict__ hinfo) {
   __shared__ int cnt, s_kn;
   if (!force && info[4] != 0) return;
   TL_ENTRY(386);
@@ -1616,6 +1637,7 @@ __global__ void conv_check(const double* __restrict__ Su, const double* __restri
       info[0] = -1;
       info[1] = k;
       info[4] = 2;
+      publish_info(info, hinfo);
     }
     return;
   }
@@ -1640,6 +1662,7 @@ __global__ void conv_check(const double* __restrict__ Su, const double* __restri
       info[1] = kn;
       info[4] = (cnt >= nu) ? 1 : 0;
       info[5] += 1;
+      publish_info(info, hinfo);
     }
   }
   if (St == nullptr) return;
@@ -1827,6 +1850,9 @@ __device__ __forceinline__ void dmma_884(double (&c)[2], double a, double b) {
 template <int MB, int WM, int WN>
 __global__ void __launch_bounds__(512) rotate_mma(const RotJob ja, const RotJob jb, const RotJob jc, int nba, int nbb,
                                                   int ld, int m, int kc, int nbuf, const int* __restrict__ halt) {
+  // launched with a full dependency on its predecessor: a kernel behind it with a programmatic edge (lazy_p0, which
+  // touches nothing this kernel writes until its own dependency wait) may start at once
+  cudaTriggerProgrammaticLaunchCompletion();
   if (halt && *halt) return;
   TL_ENTRY(384);
   constexpr int TR = 8 * MB, NWM = MB / WM;
@@ -2110,17 +2136,12 @@ struct IrlbWs {
   DevBuf<int> info;
   std::map<i64, cudaGraphExec_t> graphs;  // key: first iteration?, k, state of the lazy rotation
   std::map<i64, i64> graph_launches;
-  cudaEvent_t ev[4] = {};  // completion of the outer iterations in flight (run-ahead)
   void clear_graphs() {
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
     graphs.clear();
     graph_launches.clear();
   }
-  ~IrlbWs() {
-    clear_graphs();
-    for (auto& e : ev)
-      if (e) cudaEventDestroy(e);
-  }
+  ~IrlbWs() { clear_graphs(); }
 };
 static void free_irlb_ws(void* p) { delete (IrlbWs*)p; }
 
@@ -2382,7 +2403,40 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   const bool force_fallback = hook(HK_SVD_FALLBACK);
   if (use_arrow) svd_arrow_prepare(m_b);
   const unsigned fin_h = (unsigned)((h + 255) / 256), fin_n = (unsigned)std::max<i64>(1, (n + 255) / 256);
-  int* h_info = (int*)c->pinned;
+  // page-locked, device-visible: conv_check publishes the iteration's info words here (publish_info)
+  unsigned long long* h_info = (unsigned long long*)c->pinned;
+  for (int i = 0; i < 8; ++i) h_info[i] = 0;   // (no device work of this context is in flight here)
+  int hi[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  auto read_info = [&]() {  // consistent snapshot of the mailbox: five {value, version} words with one version
+    static const int field[5] = {0, 1, 4, 5, 6};
+    volatile unsigned long long* hv = h_info;
+    for (;;) {
+      unsigned long long w[5];
+      for (int i = 0; i < 5; ++i) w[i] = hv[i];
+      bool same = true;
+      for (int i = 1; i < 5; ++i) same = same && (w[i] >> 32) == (w[0] >> 32);
+      if (!same) continue;
+      for (int i = 0; i < 5; ++i) hi[field[i]] = (int)(unsigned)(w[i] & 0xffffffffull);
+      return;
+    }
+  };
+  // run-ahead: the host polls the mailbox instead of waiting on an event recorded between the iteration graphs
+  auto wait_iteration = [&](int iter) {
+    unsigned spins = 0;
+    for (;;) {
+      read_info();
+      if (hi[5] > iter || hi[4] != 0) return;
+      if ((++spins & 255u) == 0) {
+        const cudaError_t q = cudaStreamQuery(st);
+        if (q == cudaSuccess) {  // everything enqueued has run: the words are final
+          read_info();
+          REQUIRE(hi[5] > iter || hi[4] != 0, ADOBO_ERR_STATE, "lanczos: iteration %d finished without publishing its result", iter);
+          return;
+        }
+        if (q != cudaErrorNotReady) CUDA_CHECK(q);
+      }
+    }
+  };
 
   // ---- start vector (irlb.py:151-153): V[:,0] = v0 / ||v0|| ----
   CUDA_CHECK(cudaMemcpyAsync(ybuf_h.p, v0_host, sizeof(double) * h, cudaMemcpyHostToDevice, st));
@@ -2462,6 +2516,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   };
   // restart update (irlb.py:238-246): Ritz vectors into the leading k columns, V[:,k] = F, new B.
   // `prev`: lazy-rotation state of the iteration that just ended (ignored without the lazy rotation)
+  bool restart_mat = true;  // whether the kernel before the iteration's first w_step_t is NOT lazy_p0 (no programmatic edge then)
   auto restart_update = [&](int k, const LState& prev) {
     const unsigned sr_grid = (unsigned)((std::max(h, m_b * m_b) + 255) / 256);
     if (!lazy) {
@@ -2475,29 +2530,32 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     const LState next = lazy_next(prev, k, &mat);
     const int kcp = (k + 7) & ~7;
     rotate2(k, nullptr, nullptr, 0, nullptr, true, false);  // V and Z
-    // (lazy_p0 beside this rotation on the side stream was measured: the fork / join nodes cost what the overlap saves)
-    LAUNCH(c, "lazy_p0", (lazy_p0<<<prev.S, 128, 0, st>>>(ws.P0.p, ws.P0t.p, ldp, prev.U0, prev.kp, Su.p, m_b, k,
-                                                         mat ? ws.Pmat.p : nullptr, kcp, hp_halt,
-                                                         mat ? nullptr : (const double*)ws.crot.p, cvec.p)));
+    // lazy_p0 + set_restart in one kernel, beside the rotation (programmatic edge; see lazy_p0)
+    RestartArgs ra;
+    ra.V = V.p, ra.ldv = ld, ra.h = h, ra.m = m_b, ra.k = k, ra.fbuf = fbuf.p, ra.B = B.p, ra.sv = svd_s.p, ra.R = R.p;
+    ra.sumW = sumW.p, ra.cvec = cvec.p, ra.crot = ws.crot.p;
+    ra.U0n = next.U0, ra.kpn = next.kp, ra.nds = next.U0 + (k - next.kp);
+    LAUNCH(c, "lazy_p0", CUDA_CHECK(launch_k(lazy_p0, dim3(prev.S), dim3(128), 0, st, pdl, 1, ws.P0.p, ws.P0t.p, ldp, prev.U0,
+                                             prev.kp, (const double*)Su.p, m_b, k, mat ? ws.Pmat.p : (double*)nullptr, kcp,
+                                             hp_halt, mat ? (const double*)nullptr : (const double*)ws.crot.p, cvec.p, ra)));
     if (mat) rotate_w_stored(prev.S, k, nullptr, 0, nullptr);  // W_s[:, :k] = the Ritz vectors themselves again
-    LAUNCH(c, "set_restart", (set_restart<<<sr_grid, 256, 0, st>>>(V.p, ld, h, fbuf.p, B.p, m_b, k, svd_s.p, R.p, cvec.p, sumW.p,
-                                                                ws.crot.p, hp_halt, lazy_args(next), next.U0 + (k - next.kp))));
+    restart_mat = mat;
   };
   const bool use_graphs = !c->profiling && !hook(HK_NO_GRAPH);
   // SVD of B (irlb.py:224): restarts have the diag + spike + bidiagonal-tail structure (svd_arrow), the first
   // iteration is a plain bidiagonal matrix (Jacobi).  B is complete once the last column of W is normalised,
   // so under graph capture the SVD is forked onto the side stream and overlaps the last V step.
-  auto enqueue_svd = [&](bool first, int k, cudaStream_t s) {
+  auto enqueue_svd = [&](bool first, int k, cudaStream_t s, const LastDiag& ldg = LastDiag()) {
     if (!first && use_arrow && svd_arrow_supported(m_b, k))
-      launch_svd_arrow(c, B.p, m_b, k, Su.p, svd_s.p, Sv.p, info.p, s);
+      launch_svd_arrow(c, B.p, m_b, k, Su.p, svd_s.p, Sv.p, info.p, s, ldg);
     else
       LAUNCH(c, "jacobi_svd", (jacobi<<<1, JTHREADS, svd_smem, s>>>(B.p, m_b, Su.p, svd_s.p, Sv.p, info.p)));
   };
   const bool fork_svd = use_graphs && !hook(HK_NO_FORK);
-  auto fork_svd_here = [&](bool first, int k) {
+  auto fork_svd_here = [&](bool first, int k, const LastDiag& ldg = LastDiag()) {
     CUDA_CHECK(cudaEventRecord(c->fork_ev, st));
     CUDA_CHECK(cudaStreamWaitEvent(c->side, c->fork_ev, 0));
-    enqueue_svd(first, k, c->side);
+    enqueue_svd(first, k, c->side, ldg);
     CUDA_CHECK(cudaEventRecord(c->join_ev, c->side));
   };
   constexpr int RUN_DEPTH = 3, CC_BLOCKS = 16;
@@ -2515,10 +2573,13 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   auto enqueue_steps_fused = [&](bool first, int k, const LState& ls) {
     const LazyArgs lz = lazy_args(ls);
     auto slot = [&](int col) { return ls.U0 + (col - ls.kp); };  // where column col of W is stored
+    // the first column of an iteration follows lazy_p0 (programmatic edge: its prologue reads the static CSR and rows
+    // of W_s only) unless W_s has just been rotated for real
+    const bool first_pdl = !first && lazy && !restart_mat;
     auto w_launch = [&](int jprev, int nd) {                     // effective indices in, stored indices to the kernel
       const int nds = slot(nd), jps = jprev >= 0 ? nds - 1 : -1;
       WORK(c, w_bytes(nds, jps));
-      LAUNCH(c, "w_step_t", CUDA_CHECK(launch_k(wt_fn, dim3(gb_w2), dim3(W2_THREADS), wt_smem, st, pdl && jprev >= 0, 1, A.rptr.p,
+      LAUNCH(c, "w_step_t", CUDA_CHECK(launch_k(wt_fn, dim3(gb_w2), dim3(W2_THREADS), wt_smem, st, pdl && (jprev >= 0 || first_pdl), 1, A.rptr.p,
                                                 A.cidx.p, A.rval.p, xs.p, sc.p, W.p, ldw, jps, nds, (int)n, cvec.p, ybuf_n.p,
                                                 partials.p, tpart.p, hp_halt, h, hp)));
     };
@@ -2531,13 +2592,22 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
         // W[:, m_b-1] and B[m_b-1, m_b-1] now: B is complete and its SVD runs beside the last V step
         if (c->world > 1)
           LAUNCH(c, "w_norm_exchange", (w_norm_exchange<<<1, 256, 0, st>>>(partials.p, (int)gb_w2, sj, gout.p, hp_halt, pcw)));
+        // the structured SVD takes B[m_b-1, m_b-1] = ||y|| from the partials / the exchanged pair itself (LastDiag) and
+        // is forked BEFORE w_finish_t: it is the longer branch beside the last V step
+        const bool early = fork_svd && !first && use_arrow && svd_arrow_supported(m_b, k);
+        if (early) {
+          LastDiag ldg;
+          if (c->world > 1) ldg.n2p = gout.p;
+          else ldg.parts = partials.p, ldg.nblk = (int)gb_w2, ldg.col0 = sj, ldg.stride = MAXB;
+          fork_svd_here(first, k, ldg);
+        }
         LAUNCH(c, "w_finish", (w_finish_t<<<fin_n, 256, 0, st>>>(ybuf_n.p, gout.p, sc.p, W.p, ldw, sj, j, n, B.p, m_b, hp_halt,
                                                                  c->world > 1 ? nullptr : partials.p, (int)gb_w2)));
-        if (fork_svd) fork_svd_here(first, k);
+        if (fork_svd && !early) fork_svd_here(first, k);
       }
       WORK(c, 8.0 * gb_w2 * (hp + sj + 2.0) + 8.0 * h * (2.0 * (j + 1) + 8));
       LAUNCH(c, "v_step_t", CUDA_CHECK(launch_k(m_b <= 96 ? v_step_t<3> : v_step_t<4>, dim3(VS_CLUSTER), dim3(VS_THREADS),
-                                                vs_one_smem, st, pdl && !last, VS_CLUSTER, (const double*)tpart.p, hp,
+                                                vs_one_smem, st, pdl, VS_CLUSTER, (const double*)tpart.p, hp,
                                                 (const double*)partials.p, (int)gb_w2, mu, rs,
                                                 (const double*)(centered ? murs.p : nullptr), sc.p, V.p, ld, j, m_b, h,
                                                 ybuf_h.p, fbuf.p, xs.p, B.p, zargs(j), hp_halt, pcw, lz)));
@@ -2610,8 +2680,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
       enqueue_svd(first, k, st);
     LAUNCH(c, "conv_check", (conv_check<<<CC_BLOCKS, 256, 0, st>>>(Su.p, svd_s.p, sc.p, m_b, nu, k, first ? 0 : 1, tol, R.p,
                                                                  info.p, arrow ? 1 : 0, 0, Sv.p, St.p,
-                                                                 zpath ? cvec.p : nullptr, sumW.p, ws.crot.p)));
-    CUDA_CHECK(cudaMemcpyAsync(h_info, info.p, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
+                                                                 zpath ? cvec.p : nullptr, sumW.p, ws.crot.p, h_info)));
     hp_halt = nullptr;
   };
   // fallback when svd_arrow rejected its own result: generic Jacobi SVD of the same B
@@ -2620,9 +2689,9 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     LAUNCH(c, "jacobi_svd", (jacobi<<<1, JTHREADS, svd_smem, st>>>(B.p, m_b, Su.p, svd_s.p, Sv.p, info.p)));
     LAUNCH(c, "conv_check", (conv_check<<<CC_BLOCKS, 256, 0, st>>>(Su.p, svd_s.p, sc.p, m_b, nu, k, first ? 0 : 1, tol, R.p,
                                                                  info.p, 0, 1, Sv.p, St.p, zpath ? cvec.p : nullptr,
-                                                                 sumW.p, ws.crot.p)));
-    CUDA_CHECK(cudaMemcpyAsync(h_info, info.p, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
+                                                                 sumW.p, ws.crot.p, h_info)));
     CUDA_CHECK(cudaStreamSynchronize(st));
+    read_info();
   };
   auto run_iteration = [&](bool first, int k, const LState& prev) {
     if (!use_graphs) {
@@ -2670,43 +2739,42 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
   fresh.S = m_b;
   int it = 0, k = nu, enq = 0;
   bool converged = false;
-  if (runahead)
-    for (auto& e : ws.ev)
-      if (!e) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   while (it < maxit) {
     while (enq < maxit && (enq == it || (runahead && enq - it < RUN_DEPTH && it > 0 && k == m_b - 3))) {
       const LState prev = enq == 0 ? fresh : lst[enq - 1];
       run_iteration(enq == 0, k, prev);
-      if (runahead) CUDA_CHECK(cudaEventRecord(ws.ev[enq % RUN_DEPTH], st));
       ks.push_back(k);
       lst.push_back((enq == 0 || !lazy) ? fresh : lazy_next(prev, k, nullptr));
       ++enq;
     }
-    if (runahead)
-      CUDA_CHECK(cudaEventSynchronize(ws.ev[it % RUN_DEPTH]));
-    else
+    if (runahead) {
+      wait_iteration(it);
+    } else {
       CUDA_CHECK(cudaStreamSynchronize(st));
-    REQUIRE(h_info[6] == 0, ADOBO_ERR_NCCL, "lanczos: rank %d did not answer an exchange over NVLink peer memory within %d s",
-            h_info[6] - 1, (int)(PEER_TIMEOUT_NS / 1000000000ull));
-    if (runahead && h_info[4] != 0) {
+      read_info();
+    }
+    REQUIRE(hi[6] == 0, ADOBO_ERR_NCCL, "lanczos: rank %d did not answer an exchange over NVLink peer memory within %d s",
+            hi[6] - 1, (int)(PEER_TIMEOUT_NS / 1000000000ull));
+    if (runahead && hi[4] != 0) {
       // something stopped: drain the (no-op) iterations behind it and read the final state
       CUDA_CHECK(cudaStreamSynchronize(st));
-      it = (h_info[4] == 1) ? h_info[5] - 1 : h_info[5];
+      read_info();
+      it = (hi[4] == 1) ? hi[5] - 1 : hi[5];
       k = ks[it];
       enq = it + 1;
       ks.resize(enq);
       lst.resize(enq);
     }
-    if (h_info[0] < 0 || (force_fallback && it > 0)) {  // structured SVD failed its self-check (kept for safety)
+    if (hi[0] < 0 || (force_fallback && it > 0)) {  // structured SVD failed its self-check (kept for safety)
       svd_fallback(it == 0, k);
       ++res.svd_fallbacks;
     }
-    if (trace) fprintf(stderr, "irlb it=%d k=%d conv=%d next_k=%d\n", it, k, h_info[0], h_info[1]);
-    if (h_info[0] >= nu) {  // irlb.py:232-236
+    if (trace) fprintf(stderr, "irlb it=%d k=%d conv=%d next_k=%d\n", it, k, hi[0], hi[1]);
+    if (hi[0] >= nu) {  // irlb.py:232-236
       converged = true;
       break;
     }
-    k = h_info[1];
+    k = hi[1];
     ++it;
   }
   int nmult = 0;  // 1 + sum over j of (1 + [j < m_b-1]) mat-vecs per outer iteration
@@ -2725,7 +2793,7 @@ IrlbResult run_irlb(adobo_ctx* c, SparsePair<VT>& A, const double* mu, const dou
     // U = W_s [P0 0; 0 I] Su[:, :nu]: the small product first, then one real rotation of the stored columns
     rotate2(nu, outV.p, nullptr, nu, nullptr, false, false);
     LAUNCH(c, "lazy_p0", (lazy_p0<<<fin.S, 128, 0, st>>>(ws.P0.p, ws.P0t.p, ldp, fin.U0, fin.kp, Su.p, m_b, nu, ws.Pmat.p,
-                                                        (nu + 7) & ~7, nullptr, nullptr, nullptr)));
+                                                        (nu + 7) & ~7, nullptr, nullptr, nullptr, RestartArgs())));
     rotate_w_stored(fin.S, nu, outU.p, nu, var_weigh ? svd_s.p : nullptr);
   } else {
     // Not converged within maxit.  The reference then rotates the first k columns of V and W once more and multiplies

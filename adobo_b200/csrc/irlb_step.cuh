@@ -559,6 +559,9 @@ __global__ void __launch_bounds__(256) w_norm_exchange(const double* __restrict_
 __global__ void w_finish_t(const double* __restrict__ ybuf, const double* __restrict__ n2p, double* __restrict__ sc,
                            double* __restrict__ W, int ldw, int slot, int jn, i64 n, double* __restrict__ B, int m_b,
                            const int* __restrict__ halt, const double* __restrict__ parts, int nblk) {
+  // launched with a full dependency on w_step_t; the last v_step_t of the iteration follows with a programmatic edge
+  // (its prologue reads V and Z only, and its dependency wait covers this kernel)
+  cudaTriggerProgrammaticLaunchCompletion();
   if (halt && *halt) return;
   __shared__ double s_n2[2];
   if (parts) {
@@ -588,10 +591,30 @@ __global__ void w_finish_t(const double* __restrict__ ybuf, const double* __rest
 // kcp = kn rounded up to 8, the layout the rotation kernels read their matrix in.
 // With crot != nullptr the CTA also leaves c_s[s] = P0_new[s, :] . crot, the coefficients of the restart's first new
 // column in stored space (crot: conv_check's coefficients in the new rotated basis).
+// set_restart's work (irlb.py:239-244) folded into lazy_p0, for the restarts of the two-kernel path: V[:, k] = F,
+// B = diag(sv[:k]) + R[:k] in column k, the rotated column sums and the raw tail of the coefficients.
+struct RestartArgs {
+  double* V = nullptr;  // nullptr: lazy_p0 only
+  int ldv = 0, h = 0, m = 0, k = 0;
+  const double* fbuf = nullptr;
+  double* B = nullptr;
+  const double* sv = nullptr;
+  const double* R = nullptr;
+  double* sumW = nullptr;
+  double* cvec = nullptr;
+  const double* crot = nullptr;   // conv_check's coefficients [0, MAXB) and column sums [MAXB, 2 MAXB) in the new basis
+  int U0n = 0, kpn = 0, nds = 0;  // lazy state of the coming iteration, stored index of its first new column
+};
+
+// Launched with a PROGRAMMATIC edge behind the rotation of V and Z (rotate_mma triggers at its start): nothing below
+// reads what the rotation writes, so the two run side by side; only V[:, k] = F waits for the rotation to complete
+// (the rotation reads whole rows of V, column k included).  The trigger at the top lets the first w_step_t of the
+// iteration start its prologue (static CSR, rows of W_s) in turn; its own dependency wait covers this kernel.
 __global__ void __launch_bounds__(128) lazy_p0(double* __restrict__ P0, double* __restrict__ P0t, int ldp, int U0, int kp,
                                                const double* __restrict__ Su, int m, int kn, double* __restrict__ Pmat,
                                                int kcp, const int* __restrict__ halt, const double* __restrict__ crot,
-                                               double* __restrict__ cvec_s) {
+                                               double* __restrict__ cvec_s, const RestartArgs ra) {
+  cudaTriggerProgrammaticLaunchCompletion();
   if (halt && *halt) return;
   __shared__ double row[MAXB];
   __shared__ double red[4];
@@ -617,4 +640,22 @@ __global__ void __launch_bounds__(128) lazy_p0(double* __restrict__ P0, double* 
     __syncthreads();
     if (c == 0) cvec_s[sidx] = (red[0] + red[1]) + (red[2] + red[3]);
   }
+  if (ra.V == nullptr) return;
+  // ---- set_restart ----
+  if (blockIdx.x == 0) {  // the raw tail of c_s (disjoint from the entries written above: sidx < U0n) and sum W
+    for (int t = c; t < MAXB; t += 128) {
+      if (t < ra.k) ra.sumW[t] = ra.crot[MAXB + t];
+      if (t >= ra.U0n && t < ra.nds) ra.cvec[t] = ra.crot[ra.kpn + t - ra.U0n];
+    }
+  }
+  const int nthr = (int)gridDim.x * 128, gid = (int)blockIdx.x * 128 + c;
+  for (int i = gid; i < ra.m * ra.m; i += nthr) {
+    const int r = i / ra.m, cc = i - r * ra.m;
+    double b = 0.0;
+    if (r < ra.k && cc == r) b = ra.sv[r];
+    if (r < ra.k && cc == ra.k) b = ra.R[r];
+    ra.B[i] = b;
+  }
+  cudaGridDependencySynchronize();  // the rotation has read its last row of V
+  for (int i = gid; i < ra.h; i += nthr) ra.V[(size_t)i * ra.ldv + ra.k] = ra.fbuf[i];
 }

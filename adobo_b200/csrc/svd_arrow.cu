@@ -70,7 +70,8 @@ __device__ __forceinline__ double wmax(double v) {
 // info[3] = 1 when the decomposition passed its self-check, 0 -> caller falls back to jacobi_svd
 __global__ void __launch_bounds__(SA_THREADS, 1) svd_arrow(const double* __restrict__ B, int m, int k,
                                                            double* __restrict__ Su, double* __restrict__ svout,
-                                                           double* __restrict__ Sv, int* __restrict__ info) {
+                                                           double* __restrict__ Sv, int* __restrict__ info,
+                                                           const LastDiag ldg) {
   extern __shared__ __align__(16) double sm[];
   const int t = m - k;
   double* X = sm;                          // [m][m] column-major: X[j*m + i] = coordinate i of eigenvector j
@@ -119,9 +120,34 @@ __global__ void __launch_bounds__(SA_THREADS, 1) svd_arrow(const double* __restr
     dD[i] = d * d;
     wv[i] = B[(size_t)i * m + k];
   }
+  const bool own_last = ldg.parts != nullptr || ldg.n2p != nullptr;  // B[m-1][m-1] is not in memory yet (LastDiag)
   for (int j = tid; j < t; j += SA_THREADS) {
-    ta[j] = B[(size_t)(k + j) * m + (k + j)];
+    if (!(own_last && j == t - 1)) ta[j] = B[(size_t)(k + j) * m + (k + j)];
     tb[j] = (j + 1 < t) ? B[(size_t)(k + j) * m + (k + j + 1)] : 0.0;
+  }
+  if (own_last && warp == SA_THREADS / 32 - 1) {
+    double t0;
+    if (ldg.parts) {  // the order of sum_partials_two: 16 parts of every 16th CTA (ascending), then the parts in order
+      double p = 0;
+      if (lane < 16) {
+        for (int base = lane; base < ldg.nblk; base += 160) {
+          double v[10];
+#pragma unroll
+          for (int i = 0; i < 10; ++i) {
+            const int b = base + 16 * i;
+            v[i] = b < ldg.nblk ? __ldcg(ldg.parts + (size_t)b * ldg.stride + ldg.col0) : 0.0;
+          }
+#pragma unroll
+          for (int i = 0; i < 10; ++i) p += v[i];
+        }
+      }
+      t0 = __shfl_sync(0xffffffffu, p, 0);
+#pragma unroll
+      for (int l = 1; l < 16; ++l) t0 += __shfl_sync(0xffffffffu, p, l);
+    } else {
+      t0 = ldg.n2p[0];
+    }
+    if (lane == 0) ta[t - 1] = sqrt(t0);
   }
   for (int idx = tid; idx < SA_MAXT * 32; idx += SA_THREADS) {
     G[idx] = 0.0;
@@ -635,7 +661,7 @@ void svd_arrow_prepare(int m) {
 }
 
 void launch_svd_arrow(adobo_ctx* c, const double* B, int m, int k, double* Su, double* sv, double* Sv, int* info,
-                      cudaStream_t st) {
+                      cudaStream_t st, LastDiag ldg) {
   WORK(c, 24.0 * m * m);
   const int cs = svd_arrow_cluster();
   cudaLaunchConfig_t cfg = {};
@@ -650,7 +676,7 @@ void launch_svd_arrow(adobo_ctx* c, const double* B, int m, int k, double* Su, d
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  LAUNCH(c, "svd_arrow", CUDA_CHECK(cudaLaunchKernelEx(&cfg, svd_arrow, B, m, k, Su, sv, Sv, info)));
+  LAUNCH(c, "svd_arrow", CUDA_CHECK(cudaLaunchKernelEx(&cfg, svd_arrow, B, m, k, Su, sv, Sv, info, ldg)));
 }
 
 }  // namespace adobo

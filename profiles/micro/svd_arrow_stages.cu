@@ -48,7 +48,7 @@ int main() {
     float ms = 0;
     for (int rep = 0; rep < 3; ++rep) {
       cudaEventRecord(e0);
-      launch_svd_arrow(&ctx, dB, m, k, dSu, dsv, dSv, dinfo, 0);
+      launch_svd_arrow(&ctx, dB, m, k, dSu, dsv, dSv, dinfo, 0, LastDiag());
       cudaEventRecord(e1);
       cudaEventSynchronize(e1);
       cudaEventElapsedTime(&ms, e0, e1);
