@@ -511,7 +511,7 @@ void run_knn(adobo_ctx* c, const double* comp_local, i64 n_local, int p, int k, 
   ctr.ensure(MAXP);
   maxnorm.ensure(1);
   CUDA_CHECK(cudaMemsetAsync(maxnorm.p, 0, sizeof(unsigned), st));
-  LAUNCH(c, "knn_center", (knn_center<<<1, 1024, 0, st>>>(x, std::min<i64>(n, 4096), p, ctr.p)));
+  LAUNCH(c, "knn_center", (knn_center<<<1, 1024, 0, st>>>(x, std::min<i64>(n, 1024), p, ctr.p)));
   skey.ensure((size_t)std::max<i64>(n_local, 1) * KP);
   sidx.ensure((size_t)std::max<i64>(n_local, 1) * KP);
   const i64 q_end = q_begin + n_local;

@@ -161,40 +161,52 @@ __device__ __forceinline__ float tf32_round(float x) {
 
 // ---- operand preparation ------------------------------------------------------------------------
 // x: n x p fp64; writes A' = [q_hi | q_lo] and B' = [r_hi | r_lo] (npad x 2 Kp fp32), fp32 norms of the centred points
-__global__ void knn_tc_prep(const double* __restrict__ x, i64 n, i64 npad, int p, int Kp, const double* __restrict__ ctr,
-                            float* __restrict__ Aop, float* __restrict__ Bop, float* __restrict__ norms,
-                            unsigned* __restrict__ maxnorm_bits) {
-  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per point: the lanes stride the columns, so every row of A' / B' is written with coalesced stores (a thread
+// per point wrote 32 different rows per store instruction: 0.36 ms at 68 k points for 100 MB).  The fp32 norm is
+// accumulated in coordinate order by every lane (broadcast loads), the same bits as before.
+__global__ void __launch_bounds__(256) knn_tc_prep(const double* __restrict__ x, i64 n, i64 npad, int p, int Kp,
+                                                   const double* __restrict__ ctr, float* __restrict__ Aop,
+                                                   float* __restrict__ Bop, float* __restrict__ norms,
+                                                   unsigned* __restrict__ maxnorm_bits) {
+  const int lane = threadIdx.x & 31;
+  const i64 i = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= npad) return;
   const int Kt = 2 * Kp;
   float* a = Aop + (size_t)i * Kt;
   float* b = Bop + (size_t)i * Kt;
-  for (int d = 0; d < Kt; ++d) {
-    a[d] = 0.f;
-    b[d] = 0.f;
-  }
   if (i < n) {
+    const double* xr = x + i * p;
     float nrm = 0.f;
     for (int d = 0; d < p; ++d) {
-      const float v = (float)(x[i * p + d] - ctr[d]);
+      const float v = (float)(xr[d] - ctr[d]);
       nrm = fmaf(v, v, nrm);
-      const float hi = tf32_round(v), lo = tf32_round(v - hi);
-      a[d] = hi;
-      a[Kp + d] = lo;
-      b[d] = hi;
-      b[Kp + d] = lo;
     }
-    norms[i] = nrm;
-    atomicMax(maxnorm_bits, __float_as_uint(nrm));
     const float hn = -0.5f * nrm, hh = tf32_round(hn), hl = tf32_round(hn - hh);
-    a[p] = 1.f;
-    a[p + 1] = 1.f;
-    b[p] = hh;
-    b[p + 1] = hl;
+    for (int d = lane; d < Kt; d += 32) {
+      const int dd = d < Kp ? d : d - Kp;
+      float av = 0.f, bv = 0.f;
+      if (dd < p) {
+        const float v = (float)(xr[dd] - ctr[dd]);
+        const float hi = tf32_round(v);
+        av = bv = (d < Kp) ? hi : tf32_round(v - hi);
+      } else if (d == p) {
+        av = 1.f, bv = hh;
+      } else if (d == p + 1) {
+        av = 1.f, bv = hl;
+      }
+      a[d] = av;
+      b[d] = bv;
+    }
+    if (lane == 0) {
+      norms[i] = nrm;
+      atomicMax(maxnorm_bits, __float_as_uint(nrm));
+    }
   } else {
-    norms[i] = INFINITY;
-    a[p] = 1.f;
-    b[p] = -1e30f;  // padding rows score -1e30: never a candidate
+    for (int d = lane; d < Kt; d += 32) {
+      a[d] = (d == p) ? 1.f : 0.f;
+      b[d] = (d == p) ? -1e30f : 0.f;  // padding rows score -1e30: never a candidate
+    }
+    if (lane == 0) norms[i] = INFINITY;
   }
 }
 
@@ -657,8 +669,8 @@ void run_knn_shortlist_tc(adobo_ctx* c, const double* x, i64 n, int p, const dou
   Aop.ensure((size_t)npad * Kt);
   Bop.ensure((size_t)npad * Kt);
   norms.ensure((size_t)npad);
-  LAUNCH(c, "knn_tc_prep", (knn_tc_prep<<<(unsigned)((npad + 127) / 128), 128, 0, st>>>(x, n, npad, p, Kp, ctr, Aop.p, Bop.p,
-                                                                                      norms.p, maxnorm)));
+  LAUNCH(c, "knn_tc_prep", (knn_tc_prep<<<(unsigned)((npad + 7) / 8), 256, 0, st>>>(x, n, npad, p, Kp, ctr, Aop.p, Bop.p,
+                                                                                  norms.p, maxnorm)));
   const CUtensorMap mapB = make_map(Bop.p, npad, Kt);
   const int KP = 32 * E;
   const i64 qt0 = q_begin / TC_M, qt1 = (q_end + TC_M - 1) / TC_M;
