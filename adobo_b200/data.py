@@ -165,7 +165,7 @@ class dataset:
         else:
             total = _row_sums(csr)
             allpos = csr.nnz == 0 or csr.data.min() > 0
-            detected = np.diff(csr.indptr) if allpos else _row_sums(sp.csr_matrix(
+            detected = np.diff(csr.indptr).astype(np.int64) if allpos else _row_sums(sp.csr_matrix(
                 ((csr.data > 0).astype(np.int64), csr.indices, csr.indptr), shape=csr.shape))
             expressed = np.bincount(csr.indices if allpos else csr.indices[csr.data > 0], minlength=raw_mat.shape[0])
         self.meta_cells = pd.DataFrame(index=raw_mat.columns)                # data.py:75-78

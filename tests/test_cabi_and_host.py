@@ -136,6 +136,82 @@ def test_csr_backed_dataset_matches_frame_backed():
     assert kf.matches(fa) and not kf.matches(fa.copy())
 
 
+class _StubEngine:
+    """Host-logic stand-in for engine.Engine (no GPU): keeps the 'resident' counts, normalizes with the oracle, counts
+    what the host layer asks for.  Only the bookkeeping of norm() / dataset() / DeviceCsrFrame is under test here."""
+
+    def __init__(self):
+        from adobo_b200.engine import Engine
+        self.world, self.rank, self.h = 1, 0, object()
+        self.resident_key = self.counts_key = None
+        self._lazy, self._pattern = [], None
+        self.uploads = self.norm_calls = self.value_downloads = 0
+        self._evict = Engine._evict.__get__(self)            # the real eviction logic
+
+    def upload_counts(self, counts, key=None):
+        self._evict()
+        self.counts = sp.csr_matrix(counts).copy()
+        self.n, self.g, self.nnz = self.counts.shape[0], self.counts.shape[1], self.counts.nnz
+        self.uploads += 1
+        self.resident_key, self.counts_key = None, key
+
+    def upload_normalized(self, norm, key=None):
+        self._evict()
+        self.counts = None
+        self.resident_key = key
+
+    def count_stats(self):
+        c = self.counts
+        return (np.asarray(c.sum(axis=1)).ravel().astype(np.int64), np.asarray((c > 0).sum(axis=1)).ravel().astype(np.int64),
+                np.asarray((c > 0).sum(axis=0)).ravel().astype(np.int64))
+
+    def normalize(self, scaling_factor=10000, log_mode=1, small_const=1.0, want_values=True):
+        from oracle import adobo_oracle as O
+        assert self.counts is not None, 'normalize without resident counts'
+        self.norm_calls += 1
+        lib = np.asarray(self.counts.sum(axis=1)).ravel()
+        if not want_values:
+            return None, lib
+        self.value_downloads += 1
+        vals, _ = O.normalize_standard(self.counts, scaling_factor, log=(log_mode != 0))
+        return vals, lib
+
+
+def test_device_csr_frame_bookkeeping():
+    """A CsrFrame-backed dataset made with an engine: one upload (dataset), none in norm(); the normalized values stay
+    'on the device' until read; a second normalization keeps the first frame valid; replacing the resident matrix
+    brings every lazy frame to the host first; a materialised frame that was the resident one stays the resident one."""
+    from adobo_b200.data import dataset, DeviceCsrFrame
+    from adobo_b200 import normalize as N
+    from adobo_b200.synth import synth_counts
+    from oracle import adobo_oracle as O
+    counts = synth_counts(50, 70, 0.2, seed=8)
+    eng = _StubEngine()
+    exp = dataset.from_csr(counts, frame=False, eng=eng)
+    assert eng.uploads == 1 and eng.counts_key.matches(exp.count_data)
+    assert np.array_equal(exp.meta_cells['total_reads'].values, np.asarray(counts.sum(axis=1)).ravel())
+    N.norm(exp, eng=eng)
+    N.norm(exp, name='nolog', log=False, eng=eng)
+    assert eng.uploads == 1 and eng.value_downloads == 0             # counts found resident, no values copied
+    d1, d2 = exp.norm_data['standard']['data'], exp.norm_data['nolog']['data']
+    assert isinstance(d1, DeviceCsrFrame) and not d1.materialized and d1.shape == (70, 50)
+    assert eng.resident_key.matches(d2) and not eng.resident_key.matches(d1)
+    assert 'values on the device' in repr(d1)
+    v2 = d2.csr                                                      # read: one download, still the resident frame
+    assert eng.value_downloads == 1 and d2.materialized and eng.resident_key.matches(d2)
+    assert np.array_equal(v2.data, O.normalize_standard(counts, 10000, log=False)[0].data)
+    other = dataset.from_csr(synth_counts(20, 70, 0.2, seed=9), frame=False, eng=eng)   # replaces the resident counts
+    assert d1.materialized and eng.value_downloads == 2 and eng.uploads == 2
+    assert np.array_equal(d1.csr.data, O.normalize_standard(counts, 10000)[0].data)
+    assert not eng.counts_key.matches(exp.count_data) and eng.counts_key.matches(other.count_data)
+    N.norm(exp, name='again', eng=eng)                               # the first dataset again: its counts are uploaded again
+    assert eng.uploads == 3
+    # without an engine the statistics are computed on the host (pandas-frame datasets always are): same numbers
+    host = dataset.from_csr(counts, frame=False)
+    pd.testing.assert_frame_equal(host.meta_cells, exp.meta_cells)
+    pd.testing.assert_frame_equal(host.meta_genes, exp.meta_genes)
+
+
 def test_partitioner_hand_off_builds_the_reference_graph(monkeypatch):
     """f2: `_igraph_from_edges` (arrays straight into igraph) executed against a recording stand-in for igraph --
     the package is absent here -- and compared with what the reference's construction hands over
