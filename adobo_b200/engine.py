@@ -61,6 +61,10 @@ class Engine:
 
     def close(self):
         if getattr(self, 'h', None):
+            try:
+                self._evict()                            # frames whose values live here only get their host copy first
+            except Exception:
+                pass
             self.lib.adobo_ctx_destroy(self.h)
             self.h = None
 
