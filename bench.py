@@ -157,6 +157,19 @@ def sample_counts(cfg, eng=None):
     return m
 
 
+def host_threads():
+    """All host cores for the CPU arm's BLAS: torchrun exports OMP_NUM_THREADS=1 to every rank, which would time a
+    single-threaded reference at N > 1.  Returns the thread count in use."""
+    n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=n)
+        used = [p.get('num_threads', 1) for p in threadpool_info()]
+        return max(used) if used else n
+    except Exception:
+        return int(os.environ.get('OMP_NUM_THREADS', n))
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle port (the reference is pure Python + pandas and cannot travel to the GPU box;
     oracle/adobo_oracle.py restates its arithmetic on scipy.sparse and is pinned to the reference's own outputs by
@@ -164,6 +177,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import adobo_oracle as O
+    host_threads()
     if args.config == 'c5':
         return run_reference_c5(args)
     cfg = config_of(args)
@@ -182,7 +196,7 @@ def run_reference(args, rank, world):
             times.append(dt)
     total = float(np.sum(times))
     value = ns * args.steps / total
-    cores = os.cpu_count()
+    cores = host_threads()
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'cells/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total / args.steps * 1e3,
@@ -512,13 +526,14 @@ def main():
         if not args.no_cpu_baseline:
             ns = min(SAMPLE_CELLS, n_total)
             sample = counts[:ns]
+            ncores = host_threads()
             tm = {}
             t0 = time.perf_counter()
             O.embed_path(sample, cfg['ngenes'], cfg['ncomp'], cfg['k'], 0.067, 42, tm)
             dt = time.perf_counter() - t0
-            cpu = {'value': ns / dt, 'unit': 'cells/s', 'cores': os.cpu_count(), 'kind': 'port',
+            cpu = {'value': ns / dt, 'unit': 'cells/s', 'cores': ncores, 'kind': 'port',
                    'sample': 'first %d of the %d cells, whole path once (%.1f s); numpy/scipy restatement, BLAS threads <= %d'
-                             % (ns, n_total, dt, os.cpu_count()),
+                             % (ns, n_total, dt, ncores),
                    'stage_s': {k: float(v) for k, v in tm.items()}}
         if args.parity != 'off':
             eng.upload_counts(counts)
@@ -654,7 +669,7 @@ def run_reference_c5(args):
             'unit': 'cells/s', 'n_gpus': args.gpus, 'steps': 1, 'warmup': 0, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
             'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': 'kNN/SNN graph sweep on a %d x %d PCA embedding' % (n, p), 'config': 'c5'},
-            'cpu_baseline': {'value': value, 'unit': 'cells/s', 'cores': os.cpu_count(), 'kind': 'port',
+            'cpu_baseline': {'value': value, 'unit': 'cells/s', 'cores': host_threads(), 'kind': 'port',
                              'sample': 'exact kNN of %d of the %d queries against all references (queries/s; SNN not included)' % (q, n)},
             'e2e': {'value': value, 'unit': 'cells/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     print(json.dumps(line))
