@@ -370,6 +370,19 @@ def _eager_norm(engine_cls, counts, log_mode):
     return out
 
 
+def test_snn_two_pass_fallback_is_the_single_pass(eng, monkeypatch):
+    """The single pass (kept pairs staged, snn_emit) and the two-pass scheme it falls back to when the staging buffer
+    overflows give the same edge list, counts included."""
+    case = P.load_case('medium')
+    e1, p1, t1, _ = eng.snn(case['nn_idx'], case['k'], 0.067)
+    _, v1 = eng.fetch_edges(counts=True)
+    monkeypatch.setenv('ADOBO_B200_SNN_TWOPASS', '1')
+    e2, p2, t2, _ = eng.snn(case['nn_idx'], case['k'], 0.067)
+    _, v2 = eng.fetch_edges(counts=True)
+    assert np.array_equal(e1, e2) and (p1, t1) == (p2, t2) and np.array_equal(v1, v2)
+    assert np.array_equal(P.edges_sorted(e1), case['edges'])
+
+
 def test_snn_counts_are_the_reference_matrix_entries(eng):
     """north_star: 'SNN edge weights bit-exact' -- V_ij = (M M^T)_ij of every kept edge against the oracle's sparse
     product (the reference computes V and keeps only its coordinates, clustering.py:99-112)."""
